@@ -1,0 +1,93 @@
+"""ctypes binding of libryolo_b200.so (the C ABI declared in include/ryolo_b200.h).
+
+There is no CPU fallback: if the shared library is missing or a kernel reports an error the call
+raises.  torch is used only as the owner of device memory and streams.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libryolo_b200.so")
+
+_vp, _i64, _i32, _f32, _sz = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ryolo_b200.h
+SIGNATURES = {
+    "ryolo_abi_version": (_i32, []),
+    "ryolo_last_error": (ctypes.c_char_p, []),
+    "ryolo_set_error": (None, [ctypes.c_char_p]),
+    "ryolo_check_device": (_i32, [_i32]),
+    "ryolo_pairwise_iou_rotated_workspace": (_sz, [_i64, _i64]),
+    "ryolo_pairwise_iou_rotated": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "ryolo_nms_rotated_workspace": (_sz, [_i64]),
+    "ryolo_nms_rotated": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _vp, _sz, _vp]),
+    "ryolo_post_process_workspace": (_sz, [_i64, _i64, _i32, _i32]),
+    "ryolo_post_process": (_i32, [_vp, _i64, _i64, _i32, _f32, _f32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp,
+                                  _sz, _vp]),
+    "ryolo_decode_csl": (_i32, [_vp, _i64, _i32, _i32, _f32, ctypes.POINTER(_f32), _vp, _i64, _i64, _vp]),
+    "ryolo_decode_kfiou": (_i32, [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp]),
+    "ryolo_pos_record_bytes": (_sz, []),
+    "ryolo_loss_workspace": (_sz, [_i64, _i32, ctypes.POINTER(ctypes.c_int32), _i64]),
+    "ryolo_build_targets": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i64, ctypes.POINTER(ctypes.c_int32), _vp, _vp,
+                                   _vp, _sz, _vp]),
+    "ryolo_loss": (_i32, [_i32, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _i64, _i32, _i32,
+                          ctypes.POINTER(ctypes.c_int32), _vp, _i64, _i32, _vp, ctypes.POINTER(_f32), _vp, _vp, _sz,
+                          _vp]),
+}
+
+_lib = None
+
+
+class RyoloError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises if the extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise RyoloError(
+                f"{SO_PATH} not found: build it with `python r-yolov4_b200/build.py` "
+                "(there is no CPU / PyTorch fallback for the hot path)")
+        h = ctypes.CDLL(SO_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name, None)
+            if fn is None:
+                continue
+            fn.restype, fn.argtypes = res, args
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise RyoloError(f"libryolo_b200 error {rc}: {lib().ryolo_last_error().decode()}")
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RyoloError(f"{what} must be a CUDA tensor: the ryolo_b200 hot path has no CPU fallback")
+
+
+_ws = {}
+
+
+def workspace(nbytes, device, tag="default"):
+    """Grow-only scratch buffer per (device, tag)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), tag)
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf

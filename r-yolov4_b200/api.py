@@ -1,0 +1,23 @@
+"""Public call surface: the three Python callables the reference's train.py /
+test.py / detect.py use, under their real names plus the aliases BASELINE.json's north_star uses."""
+from ._lib import RyoloError, SO_PATH, lib
+from .lib.general import (nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
+                          post_process_device)
+from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss
+from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
+
+try:  # the conv stack is built on top of the kernels above
+    from .model.yolo import Yolo
+    Model = Yolo
+except ImportError:  # pragma: no cover - during bring-up only
+    Yolo = Model = None
+
+
+def compute_loss(model, hyp, mode="csl"):
+    """north_star alias: returns the loss callable train.py binds to `compute_loss` (train.py:140,143)."""
+    return ComputeCSLLoss(model, hyp) if mode == "csl" else ComputeKFIoULoss(model, hyp)
+
+
+__all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "compute_loss", "post_process",
+           "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
+           "YoloCSLLayer", "YoloKFIoULayer", "RyoloError", "SO_PATH", "lib"]

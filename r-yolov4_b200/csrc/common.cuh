@@ -1,0 +1,61 @@
+// Shared helpers for the ryolo_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define RYOLO_OK 0
+#define RYOLO_ERR_INVALID 1
+#define RYOLO_ERR_CUDA 2
+#define RYOLO_ERR_WORKSPACE 3
+
+extern "C" void ryolo_set_error(const char* msg);
+
+#define RY_CHECK_ARG(cond, msg)   \
+  do {                            \
+    if (!(cond)) {                \
+      ryolo_set_error(msg);       \
+      return RYOLO_ERR_INVALID;   \
+    }                             \
+  } while (0)
+
+#define RY_CHECK_LAUNCH()                            \
+  do {                                               \
+    cudaError_t e__ = cudaGetLastError();            \
+    if (e__ != cudaSuccess) {                        \
+      ryolo_set_error(cudaGetErrorString(e__));      \
+      return RYOLO_ERR_CUDA;                         \
+    }                                                \
+  } while (0)
+
+static inline size_t ry_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__device__ __forceinline__ float ry_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ double ry_warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// order-preserving map float -> uint32 (ascending)
+__device__ __forceinline__ uint32_t ry_float_order(float f) {
+  uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ry_order_float(uint32_t o) {
+  uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+  return __uint_as_float(u);
+}
+
+// streaming 128-bit load that does not pollute L1
+__device__ __forceinline__ float4 ry_ld_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
