@@ -79,6 +79,62 @@ int ryolo_loss(int mode, const float* const* levels, float* const* grads, int64_
                const int32_t* grid_hw, const float* targets, int64_t T, int tcols, const float* anchors,
                const float* hyp, float* items, void* workspace, size_t ws_bytes, void* stream);
 
+
+/* ---- conv stack ---------------------------------------------------------------------------------
+ * Activations are NHWC bf16 "views": a pointer to the first channel of a slice of a (possibly wider,
+ * concat) buffer plus the buffer's channel pitch in elements.  Weights are bf16 [Cout][kh][kw][Cin]
+ * (derived from the reference's OIHW fp32 state-dict tensors by ryolo_pack_weights).              */
+enum { RYOLO_ACT_LINEAR = 0, RYOLO_ACT_LEAKY = 1, RYOLO_ACT_MISH = 2, RYOLO_ACT_SWISH = 3 };
+enum { RYOLO_OUT_NHWC_BF16 = 0, RYOLO_OUT_HEAD_F32 = 1 };
+
+typedef struct ryolo_conv_desc {
+  const void* x;          /* bf16 NHWC input view                                   */
+  int N, H, W, Cin;       /* Cin = channels of the view (multiple of 8)             */
+  long long x_cpitch;     /* channel pitch of the input buffer (elements)           */
+  const void* w;          /* bf16 [Cout][ksize*ksize*Cin]                           */
+  int Cout, ksize, stride;/* ksize 1|3, stride 1|2, pad = (ksize-1)/2               */
+  void* out;              /* mode 0: bf16 NHWC view; mode 1: fp32 [N,na,Ho,Wo,ch]   */
+  int out_mode;
+  long long out_cpitch;
+  const float* scale;     /* per-Cout multiplier or NULL  (folded BN gamma*rsqrt)   */
+  const float* shift;     /* per-Cout addend or NULL      (folded BN beta / bias)   */
+  int act;                /* RYOLO_ACT_*                                            */
+  const void* residual;   /* optional bf16 NHWC view added after the activation     */
+  long long res_cpitch;
+  int head_na, head_ch;   /* mode 1: Cout == head_na*head_ch                        */
+} ryolo_conv_desc;
+
+/* model/utils.py:6-32 Conv (Conv2d + eval-folded BN + activation) / raw conv for train-mode BN.
+ * tcgen05 implicit GEMM (csrc/conv.cu).                                                           */
+int ryolo_conv2d_forward(const ryolo_conv_desc* d, void* stream);
+/* same contract on CUDA cores: device-side checker for the tensor-core path, never a fallback     */
+int ryolo_conv2d_reference(const ryolo_conv_desc* d, void* stream);
+
+/* nn.BatchNorm2d train-mode forward, split in three (model/utils.py:16-17):
+ *   ryolo_bn_stats     per-channel sum / sum of squares of a bf16 NHWC view (sum, sumsq pre-zeroed, fp32[C])
+ *   ryolo_bn_finalize  scale = gamma*rsqrt(var+eps), shift = beta-mean*scale; running-stat EMA (unbiased var),
+ *                      num_batches_tracked += 1; optional save_mean / save_invstd for the backward pass
+ *   ryolo_scale_shift_act  y = act(x*scale+shift [+ x2*scale2+shift2]) [+ residual]   (bf16 NHWC views, P pixels)
+ *                      also used for RepConv's two-branch sum (model/utils.py:209-215) and the Bottleneck
+ *                      shortcut (model/utils.py:45-46)                                                   */
+int ryolo_bn_stats(const void* x, long long pitch, long long P, int C, float* sum, float* sumsq, void* stream);
+int ryolo_bn_finalize(const float* sum, const float* sumsq, double count, int C, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, long long* num_batches,
+                      float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);
+int ryolo_scale_shift_act(const void* x, long long xp, const float* scale, const float* shift, const void* x2,
+                          long long x2p, const float* scale2, const float* shift2, int act, const void* residual,
+                          long long rp, void* y, long long yp, long long P, int C, void* stream);
+/* nn.MaxPool2d (model/utils.py:152,231-233,252) on a bf16 NHWC view; padding acts as -inf              */
+int ryolo_maxpool(const void* x, long long xp, int N, int H, int W, int C, int k, int stride, int pad, void* y,
+                  long long yp, void* stream);
+/* nn.Upsample(scale_factor=factor, nearest) (model/neck.py:9,19) / strided copy into a concat slice     */
+int ryolo_resize_copy(const void* x, long long xp, int N, int H, int W, int C, int factor, void* y, long long yp,
+                      void* stream);
+/* fp32 NCHW image [N,3,H,W] -> bf16 [N,H,W,64] 3x3 patches (27 taps + zero pad) for the stem conv       */
+int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stream);
+/* state-dict OIHW fp32 -> bf16 [Cout][kh][kw][Cin]; stem != 0 -> [Cout][64] in the im2col channel order  */
+int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

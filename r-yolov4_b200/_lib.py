@@ -37,6 +37,29 @@ SIGNATURES = {
                           _vp]),
 }
 
+_f32p, _dbl, _ll = ctypes.POINTER(_f32), ctypes.c_double, ctypes.c_longlong
+
+
+class ConvDesc(ctypes.Structure):
+    """struct ryolo_conv_desc (include/ryolo_b200.h)."""
+    _fields_ = [("x", _vp), ("N", _i32), ("H", _i32), ("W", _i32), ("Cin", _i32), ("x_cpitch", _ll), ("w", _vp),
+                ("Cout", _i32), ("ksize", _i32), ("stride", _i32), ("out", _vp), ("out_mode", _i32),
+                ("out_cpitch", _ll), ("scale", _vp), ("shift", _vp), ("act", _i32), ("residual", _vp),
+                ("res_cpitch", _ll), ("head_na", _i32), ("head_ch", _i32)]
+
+
+SIGNATURES.update({
+    "ryolo_conv2d_forward": (_i32, [ctypes.POINTER(ConvDesc), _vp]),
+    "ryolo_conv2d_reference": (_i32, [ctypes.POINTER(ConvDesc), _vp]),
+    "ryolo_bn_stats": (_i32, [_vp, _ll, _ll, _i32, _vp, _vp, _vp]),
+    "ryolo_bn_finalize": (_i32, [_vp, _vp, _dbl, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ryolo_scale_shift_act": (_i32, [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i32, _vp, _ll, _vp, _ll, _ll, _i32, _vp]),
+    "ryolo_maxpool": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
+    "ryolo_resize_copy": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
+    "ryolo_stem_im2col": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "ryolo_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+})
+
 _lib = None
 
 

@@ -1,0 +1,472 @@
+// Implicit-GEMM convolution on the 5th-gen tensor cores (tcgen05.mma, accumulators in TMEM, operands
+// staged by TMA) — K1 in SURVEY.md §2.1.  Replaces nn.Conv2d(+BatchNorm2d eval-folded +activation) of
+// the reference's Conv block (model/utils.py:6-32) for NHWC bf16 activations.
+//
+//   GEMM view      D[M = pixels, N = Cout] = sum over taps (kh,kw) and Cin chunks of  A_tap[M, 64] * W[N, 64]^T
+//   M tile         128 rows = a TH x TW spatial patch of ONE image, so that the A operand of tap (kh,kw)
+//                  is a single 4-D TMA box of the NHWC input at coordinates shifted by (kh-pad, kw-pad):
+//                  zero padding falls out of TMA's out-of-bounds fill, stride-2 convs use the tensor map's
+//                  element strides.  No im2col buffer ever exists.
+//   operands       bf16, K-major, 128-byte swizzle (TMA writes it, the UMMA descriptor reads it)
+//   pipeline       warp 0: TMA producer | warp 1: TMEM alloc + single-thread MMA issue | warps 2-5: epilogue
+//                  (tcgen05.ld -> scale/shift/activation/residual -> global), mbarrier ring of kStages
+//   epilogue       mode 0: bf16 NHWC into a channel slice of a (concat) buffer; per-channel scale/shift =
+//                  folded BatchNorm (eval) or identity (train: raw conv output, BN statistics follow);
+//                  mode 1: fp32 head written directly in the reference's [B, na, gs, gs, ch] layout
+//                  (the permute+contiguous of model/yololayer.py:25,76 is fused away).
+#include "common.cuh"
+#include "ryolo_b200.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int kBM = 128;        // UMMA M (rows of the patch tile, TH*TW <= 128)
+constexpr int kBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int kThreads = 192;   // 6 warps
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) /* LBO (unused for swizzled K-major) */ |
+         ((uint64_t)(1024 >> 4) << 32) /* SBO */ | ((uint64_t)1 << 46) /* descriptor version (sm_100) */ |
+         ((uint64_t)2 << 61) /* SWIZZLE_128B */;
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == RYOLO_ACT_LEAKY) return x > 0.f ? x : 0.1f * x;
+  if (act == RYOLO_ACT_MISH) {           // x * tanh(softplus(x)) = x * n / (n + 2), n = e^x (e^x + 2)
+    if (x > 20.f) return x;
+    const float e = __expf(x);
+    const float n = e * (e + 2.f);
+    return x * __fdividef(n, n + 2.f);
+  }
+  if (act == RYOLO_ACT_SWISH) return x * __fdividef(1.f, 1.f + __expf(-x));
+  return x;
+}
+
+struct ConvKernelParams {
+  int N, Ho, Wo, Cout, Cin;
+  int TH, TW, tiles_h, tiles_w, n_tiles;
+  int ksize, stride, pad, kb_per_tap;
+  int mode, act;
+  void* out;
+  long long out_cpitch;
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  long long res_cpitch;
+  int head_na, head_ch;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(kThreads)
+conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const ConvKernelParams p) {
+  constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = BN * kBK * 2;
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
+  const uint32_t sA = smem_base, sB = smem_base + STAGES * kABytes;
+  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]),
+                 bar_acc = smem_u32(&bars[2 * STAGES]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // tile coordinates: n-tile fastest so that CTAs sharing an A patch run back to back (L2 reuse)
+  const int nt = blockIdx.x % p.n_tiles;
+  int mt = blockIdx.x / p.n_tiles;
+  const int pw = mt % p.tiles_w; mt /= p.tiles_w;
+  const int ph = mt % p.tiles_h;
+  const int img = mt / p.tiles_h;
+  const int h0 = ph * p.TH, w0 = pw * p.TW, n0 = nt * BN;
+  const int taps = p.ksize * p.ksize;
+  const int KB = taps * p.kb_per_tap;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer (one lane) ================================
+    if (lane == 0) {
+      const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * kBK * 2;
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; kb++) {
+        const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+        mbar_wait(bar_empty + 8 * s, phase ^ 1u);
+        mbar_expect_tx(bar_full + 8 * s, a_bytes + kBBytes);
+        tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, w0 * p.stride + kw - p.pad,
+                    h0 * p.stride + kh - p.pad, img);
+        tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, tap * p.Cin + cb * kBK, n0);
+        if (++s == STAGES) { s = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer (one lane) ==================================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BN < 16 ? 16 : BN);
+      int s = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < KB; kb++) {
+        mbar_wait(bar_full + 8 * s, phase);
+        tc_fence_after();
+        const uint32_t a0 = sA + s * kABytes, b0 = sB + s * kBBytes;
+#pragma unroll
+        for (int k = 0; k < kBK / 16; k++) {
+          umma_bf16(tmem_base, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
+                    (kb | k) ? 1u : 0u);
+        }
+        umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
+        if (++s == STAGES) { s = 0; phase ^= 1u; }
+      }
+      umma_commit(bar_acc);                 // accumulator complete
+    }
+  } else {
+    // ================================ epilogue (4 warps, one TMEM sub-partition each) =========
+    const int sub = warp & 3;               // TMEM lanes [32*sub, 32*sub+32) are accessible to this warp
+    const int r = sub * 32 + lane;          // accumulator row = pixel of the patch
+    const int hl = r / p.TW, wl = r - hl * p.TW;
+    const int ho = h0 + hl, wo = w0 + wl;
+    const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo);
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const long long pix = ((long long)img * p.Ho + ho) * p.Wo + wo;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, v);
+      tmem_ld_wait();
+      if (!row_ok) continue;
+      if (p.mode == RYOLO_OUT_NHWC_BF16) {
+        __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
+        const __nv_bfloat16* res = p.residual ? p.residual + pix * p.res_cpitch + n0 + c0 : nullptr;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+          const int c = n0 + c0 + 8 * g;
+          if (c >= p.Cout) break;
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            float x = __uint_as_float(v[8 * g + j]);
+            if (p.scale) x = x * __ldg(p.scale + c + j);
+            if (p.shift) x = x + __ldg(p.shift + c + j);
+            f[j] = act_apply(x, p.act);
+          }
+          if (res) {
+            const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
+            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              const float2 t = __bfloat1622float2(rb[j]);
+              f[2 * j] += t.x;
+              f[2 * j + 1] += t.y;
+            }
+          }
+          uint4 pk;
+          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+          for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+        }
+      } else {  // RYOLO_OUT_HEAD_F32: out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k
+        float* o = (float*)p.out;
+#pragma unroll 4
+        for (int j = 0; j < 32; j++) {
+          const int c = n0 + c0 + j;
+          if (c >= p.Cout) break;
+          float x = __uint_as_float(v[j]);
+          if (p.scale) x = x * __ldg(p.scale + c);
+          if (p.shift) x = x + __ldg(p.shift + c);
+          const int a = c / p.head_ch, k = c - a * p.head_ch;
+          o[((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k] = act_apply(x, p.act);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------ reference kernel
+// Plain CUDA-core direct convolution on the same bf16 operands (fp32 accumulate).  Not a fallback: it is
+// only reachable through ryolo_conv2d_reference and exists so that the tcgen05 path can be checked on the
+// device, layer by layer, independently of any library.
+__global__ void conv_ref_kernel(const __nv_bfloat16* __restrict__ x, long long x_cpitch, int N, int H, int W, int Cin,
+                                const __nv_bfloat16* __restrict__ w, ConvKernelParams p) {
+  const long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  if (idx >= total) return;
+  const int c = (int)(idx % p.Cout);
+  long long pix = idx / p.Cout;
+  const int wo = (int)(pix % p.Wo);
+  const int ho = (int)((pix / p.Wo) % p.Ho);
+  const int img = (int)(pix / ((long long)p.Wo * p.Ho));
+  float acc = 0.f;
+  for (int kh = 0; kh < p.ksize; kh++) {
+    const int hi = ho * p.stride + kh - p.pad;
+    if (hi < 0 || hi >= H) continue;
+    for (int kw = 0; kw < p.ksize; kw++) {
+      const int wi = wo * p.stride + kw - p.pad;
+      if (wi < 0 || wi >= W) continue;
+      const __nv_bfloat16* xp = x + (((long long)img * H + hi) * W + wi) * x_cpitch;
+      const __nv_bfloat16* wp = w + ((long long)c * p.ksize * p.ksize + kh * p.ksize + kw) * Cin;
+      for (int ci = 0; ci < Cin; ci++) acc += __bfloat162float(xp[ci]) * __bfloat162float(wp[ci]);
+    }
+  }
+  float v = acc;
+  if (p.scale) v = v * p.scale[c];
+  if (p.shift) v = v + p.shift[c];
+  v = act_apply(v, p.act);
+  if (p.mode == RYOLO_OUT_NHWC_BF16) {
+    if (p.residual) v += __bfloat162float(p.residual[pix * p.res_cpitch + c]);
+    ((__nv_bfloat16*)p.out)[pix * p.out_cpitch + c] = __float2bfloat16_rn(v);
+  } else {
+    const int a = c / p.head_ch, k = c - a * p.head_ch;
+    ((float*)p.out)[((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Patch shape (TH x TW <= 128) that wastes the fewest accumulator rows for an Ho x Wo output.
+void pick_patch(int Ho, int Wo, int stride, int* TH, int* TW) {
+  double best = -1.0;
+  const int tw_max = 128;
+  for (int tw = 1; tw <= tw_max && tw <= Wo; tw++) {
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    if (th * stride > 256) th = 256 / stride;
+    const double tiles = (double)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+    const double eff = (double)Ho * Wo / (tiles * 128.0);
+    // prefer wider rows on ties (longer contiguous runs for TMA)
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > *TW)) { best = eff; *TH = th; *TW = tw; }
+  }
+}
+
+int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
+  RY_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3");
+  RY_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
+  RY_CHECK_ARG(d->Cin % 8 == 0 && d->x_cpitch % 8 == 0, "conv: Cin and the input channel pitch must be multiples of 8");
+  RY_CHECK_ARG((((uintptr_t)d->x) & 15) == 0 && (((uintptr_t)d->w) & 15) == 0, "conv: operands must be 16-byte aligned");
+  p->N = d->N; p->Cin = d->Cin; p->Cout = d->Cout;
+  p->ksize = d->ksize; p->stride = d->stride; p->pad = (d->ksize - 1) / 2;
+  p->Ho = (d->H + 2 * p->pad - d->ksize) / d->stride + 1;
+  p->Wo = (d->W + 2 * p->pad - d->ksize) / d->stride + 1;
+  p->kb_per_tap = (d->Cin + kBK - 1) / kBK;
+  p->mode = d->out_mode; p->act = d->act;
+  p->out = d->out; p->out_cpitch = d->out_cpitch;
+  p->scale = d->scale; p->shift = d->shift;
+  p->residual = (const __nv_bfloat16*)d->residual; p->res_cpitch = d->res_cpitch;
+  p->head_na = d->head_na; p->head_ch = d->head_ch;
+  if (d->out_mode == RYOLO_OUT_NHWC_BF16) {
+    RY_CHECK_ARG(d->Cout % 8 == 0 && d->out_cpitch % 8 == 0 && (((uintptr_t)d->out) & 15) == 0,
+                 "conv: bf16 output needs Cout and channel pitch multiples of 8 and a 16-byte aligned pointer");
+    RY_CHECK_ARG(!d->residual || (d->res_cpitch % 8 == 0 && (((uintptr_t)d->residual) & 15) == 0),
+                 "conv: residual must be 16-byte aligned with a channel pitch multiple of 8");
+  } else {
+    RY_CHECK_ARG(d->out_mode == RYOLO_OUT_HEAD_F32 && d->head_na * d->head_ch == d->Cout && !d->residual,
+                 "conv: head output needs na*ch == Cout and no residual");
+  }
+  p->TH = 1; p->TW = 1;
+  pick_patch(p->Ho, p->Wo, d->stride, &p->TH, &p->TW);
+  p->tiles_h = (p->Ho + p->TH - 1) / p->TH;
+  p->tiles_w = (p->Wo + p->TW - 1) / p->TW;
+  return RYOLO_OK;
+}
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
+    configured = true;
+  }
+  p.n_tiles = (p.Cout + BN - 1) / BN;
+  const long long blocks = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  RY_CHECK_ARG(blocks > 0 && blocks < (1ll << 31), "conv: grid too large");
+  conv_fwd_kernel<BN, STAGES><<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmB, p);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Conv2d(k in {1,3}, stride in {1,2}, pad=(k-1)/2, no bias) on NHWC bf16 + fused epilogue; see conv_desc.h.
+int ryolo_conv2d_forward(const ryolo_conv_desc* d, void* stream) {
+  ConvKernelParams p{};
+  int rc = fill_params(d, &p);
+  if (rc) return rc;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
+  if (d->N == 0) return RYOLO_OK;
+
+  int BN = 128;
+  if (d->Cout <= 32) BN = 32;
+  else if (d->Cout <= 64 || (d->Cout % 128 != 0 && d->Cout % 128 <= 64)) BN = 64;
+
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
+    cuuint64_t strides[3] = {(cuuint64_t)d->x_cpitch * 2, (cuuint64_t)d->x_cpitch * 2 * d->W,
+                             (cuuint64_t)d->x_cpitch * 2 * d->W * d->H};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->x, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the activation operand"); return RYOLO_ERR_CUDA; }
+  }
+  {
+    const int Ktot = d->ksize * d->ksize * d->Cin;
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)d->Cout};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->w, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the weight operand"); return RYOLO_ERR_CUDA; }
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (BN == 32) return launch<32, 4>(tmA, tmB, p, st);
+  if (BN == 64) return launch<64, 4>(tmA, tmB, p, st);
+  return launch<128, 3>(tmA, tmB, p, st);
+}
+
+// Same contract as ryolo_conv2d_forward, computed by a plain CUDA-core kernel (device-side checker).
+int ryolo_conv2d_reference(const ryolo_conv_desc* d, void* stream) {
+  ConvKernelParams p{};
+  int rc = fill_params(d, &p);
+  if (rc) return rc;
+  if (d->N == 0) return RYOLO_OK;
+  const long long total = (long long)p.N * p.Ho * p.Wo * p.Cout;
+  conv_ref_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)d->x, d->x_cpitch, d->N, d->H, d->W, d->Cin, (const __nv_bfloat16*)d->w, p);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+}  // extern "C"

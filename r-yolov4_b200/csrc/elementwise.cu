@@ -1,0 +1,337 @@
+// HBM-bound companions of the conv stack on NHWC bf16 views (K4, K5 in SURVEY.md §2.1):
+//   BatchNorm2d train-mode statistics / finalize / normalise+activation(+residual)   model/utils.py:16-23
+//   MaxPool2d (SPP 5/9/13 s1, MaxConv 2x2 s2)                                         model/utils.py:152,231-233
+//   nearest x2 upsample into a concat slice                                           model/neck.py:9,19
+//   stem im2col (fp32 NCHW image -> bf16 NHWC 27(+37 zero)-channel rows)              model/backbone.py:7
+//   weight packing OIHW fp32 -> [Cout][kh][kw][Cin] bf16
+// Every thread moves 8 channels (one 128-bit word) so loads/stores are fully vectorised and coalesced.
+#include "common.cuh"
+#include "ryolo_b200.h"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ float act_apply(float x, int act) {
+  if (act == RYOLO_ACT_LEAKY) return x > 0.f ? x : 0.1f * x;
+  if (act == RYOLO_ACT_MISH) {
+    if (x > 20.f) return x;
+    const float e = __expf(x);
+    const float n = e * (e + 2.f);
+    return x * __fdividef(n, n + 2.f);
+  }
+  if (act == RYOLO_ACT_SWISH) return x * __fdividef(1.f, 1.f + __expf(-x));
+  return x;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float2 t = __bfloat1622float2(b[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------ BN statistics
+// grid.x blocks stride over pixels; blockDim = (C/8 channel groups) x rows.  sum/sumsq must be zeroed.
+__global__ void __launch_bounds__(256)
+bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long pitch, long long P, int C, float* __restrict__ sum,
+                float* __restrict__ sumsq) {
+  extern __shared__ float red[];   // [rows][C] x 2
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < rows) {
+    for (long long pix = (long long)blockIdx.x * rows + r; pix < P; pix += (long long)gridDim.x * rows) {
+      const uint4 v = *reinterpret_cast<const uint4*>(x + pix * pitch + 8 * g);
+      float f[8];
+      unpack8(v, f);
+#pragma unroll
+      for (int j = 0; j < 8; j++) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+    }
+  }
+  float* rs = red;
+  float* rq = red + (size_t)rows * C;
+  if (r < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { rs[r * C + 8 * g + j] = s[j]; rq[r * C + 8 * g + j] = q[j]; }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; rr++) { a += rs[rr * C + c]; b += rq[rr * C + c]; }
+    atomicAdd(sum + c, a);
+    atomicAdd(sumsq + c, b);
+  }
+}
+
+// scale = gamma * rsqrt(var + eps), shift = beta - mean * scale; running stats EMA (unbiased variance)
+__global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* __restrict__ sumsq, double count, int C,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float momentum, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   long long* __restrict__ num_batches, float* __restrict__ scale,
+                                   float* __restrict__ shift, float* __restrict__ save_mean,
+                                   float* __restrict__ save_invstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0 && num_batches) *num_batches += 1;
+  if (c >= C) return;
+  const double mean = (double)sum[c] / count;
+  double var = (double)sumsq[c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - (float)mean * sc;
+  if (save_mean) save_mean[c] = (float)mean;
+  if (save_invstd) save_invstd[c] = invstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// y = act(x*scale + shift) (+ x2*scale2 + shift2 before the activation) (+ residual after it)
+__global__ void __launch_bounds__(256)
+scale_shift_act_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
+                       const float* __restrict__ shift, const __nv_bfloat16* __restrict__ x2, long long x2p,
+                       const float* __restrict__ scale2, const float* __restrict__ shift2, int act,
+                       const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
+                       long long P, int C) {
+  const int groups = C >> 3;
+  const long long total = P * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / groups;
+    const int c = (int)(i - pix * groups) * 8;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + pix * xp + c), f);
+    const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(shift + c), b1 = *reinterpret_cast<const float4*>(shift + c + 4);
+    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = f[j] * sc[j] + sh[j];
+    if (x2) {
+      float h[8];
+      unpack8(*reinterpret_cast<const uint4*>(x2 + pix * x2p + c), h);
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] += h[j] * scale2[c + j] + shift2[c + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = act_apply(f[j], act);
+    if (res) {
+      float h[8];
+      unpack8(*reinterpret_cast<const uint4*>(res + pix * rp + c), h);
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] += h[j];
+    }
+    *reinterpret_cast<uint4*>(y + pix * yp + c) = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------ pooling / resize / copy
+__global__ void __launch_bounds__(256)
+maxpool_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, int W, int C, int k, int stride,
+               int pad, __nv_bfloat16* __restrict__ y, long long yp, int Ho, int Wo) {
+  const int groups = C >> 3;
+  const long long total = (long long)N * Ho * Wo * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    long long pix = i / groups;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float m[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) m[j] = -INFINITY;
+    for (int dh = 0; dh < k; dh++) {
+      const int hi = ho * stride + dh - pad;
+      if (hi < 0 || hi >= H) continue;
+      for (int dw = 0; dw < k; dw++) {
+        const int wi = wo * stride + dw - pad;
+        if (wi < 0 || wi >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * H + hi) * W + wi) * xp + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) m[j] = fmaxf(m[j], f[j]);
+      }
+    }
+    *reinterpret_cast<uint4*>(y + pix * yp + c) = pack8(m);
+  }
+}
+
+// nearest-neighbour x`f` upsample (f = 1 is a plain strided copy between views)
+__global__ void __launch_bounds__(256)
+resize_copy_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, int W, int C, int f,
+                   __nv_bfloat16* __restrict__ y, long long yp) {
+  const int groups = C >> 3, Ho = H * f, Wo = W * f;
+  const long long total = (long long)N * Ho * Wo * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    long long pix = i / groups;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    const uint4 v = *reinterpret_cast<const uint4*>(x + (((long long)n * H + ho / f) * W + wo / f) * xp + c);
+    *reinterpret_cast<uint4*>(y + pix * yp + c) = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ stem im2col
+// img fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64]: channel (kh*3+kw)*3 + ci holds img[ci, h+kh-1, w+kw-1] (zero
+// padded), channels 27..63 are zero.  The 3->32 3x3 stem then runs as a K=64 1x1 conv on the tensor cores.
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
+  const long long total = (long long)N * H * W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) f[j] = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++) {
+      const int hi = h + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; kw++) {
+        const int wi = w + kw - 1;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+#pragma unroll
+          for (int ci = 0; ci < 3; ci++)
+            f[(kh * 3 + kw) * 3 + ci] = __ldg(img + (((long long)n * 3 + ci) * H + hi) * W + wi);
+        }
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(y + pix * 64);
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      const float t[8] = {f[8 * g], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3], f[8 * g + 4], f[8 * g + 5], f[8 * g + 6],
+                          f[8 * g + 7]};
+      o[g] = pack8(t);
+    }
+    const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int g = 4; g < 8; g++) o[g] = z;
+  }
+}
+
+// ------------------------------------------------------------------------------------ weight packing
+// OIHW fp32 -> [Cout][kh][kw][Cin] bf16.  stem != 0: [Cout,3,3,3] -> [Cout][64] in the im2col channel order.
+__global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int stem,
+                                    __nv_bfloat16* __restrict__ out) {
+  const int Kp = stem ? 64 : k * k * Cin;
+  const long long total = (long long)Cout * Kp;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i / Kp), kk = (int)(i % Kp);
+    float v = 0.f;
+    if (stem) {
+      if (kk < 27) {
+        const int tap = kk / 3, ci = kk % 3;
+        v = w[((long long)co * 3 + ci) * 9 + tap];
+      }
+    } else {
+      const int tap = kk / Cin, ci = kk % Cin;
+      v = w[((long long)co * Cin + ci) * k * k + tap];
+    }
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+int ryolo_bn_stats(const void* x, long long pitch, long long P, int C, float* sum, float* sumsq, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && pitch % 8 == 0, "bn_stats: C must be a multiple of 8 in [8, 2048]");
+  if (P == 0) return RYOLO_OK;
+  const int groups = C / 8;
+  const int threads = groups >= 256 ? groups : 256;       // C > 2048 excluded above -> threads <= 256
+  const int rows = threads / groups;
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  long long want = (P + rows - 1) / rows;
+  int blocks = (int)(want > 148 * 8 ? 148 * 8 : want);
+  bn_stats_kernel<<<blocks, threads, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, pitch, P, C, sum, sumsq);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_bn_finalize(const float* sum, const float* sumsq, double count, int C, const float* gamma, const float* beta,
+                      float eps, float momentum, float* running_mean, float* running_var, long long* num_batches,
+                      float* scale, float* shift, float* save_mean, float* save_invstd, void* stream) {
+  RY_CHECK_ARG(C > 0 && count > 0, "bn_finalize: bad shape");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sum, sumsq, count, C, gamma, beta, eps, momentum,
+                                                                        running_mean, running_var, num_batches, scale,
+                                                                        shift, save_mean, save_invstd);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_scale_shift_act(const void* x, long long xp, const float* scale, const float* shift, const void* x2,
+                          long long x2p, const float* scale2, const float* shift2, int act, const void* residual,
+                          long long rp, void* y, long long yp, long long P, int C, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && xp % 8 == 0 && yp % 8 == 0, "scale_shift_act: channels must be multiples of 8");
+  if (P == 0) return RYOLO_OK;
+  scale_shift_act_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, xp, scale, shift, (const __nv_bfloat16*)x2, x2p, scale2, shift2, act,
+      (const __nv_bfloat16*)residual, rp, (__nv_bfloat16*)y, yp, P, C);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_maxpool(const void* x, long long xp, int N, int H, int W, int C, int k, int stride, int pad, void* y,
+                  long long yp, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && k >= 1 && stride >= 1, "maxpool: bad arguments");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  if (total == 0) return RYOLO_OK;
+  maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, xp, N, H, W, C, k,
+                                                                         stride, pad, (__nv_bfloat16*)y, yp, Ho, Wo);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_resize_copy(const void* x, long long xp, int N, int H, int W, int C, int factor, void* y, long long yp,
+                      void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && factor >= 1, "resize_copy: bad arguments");
+  const long long total = (long long)N * H * factor * W * factor * (C / 8);
+  if (total == 0) return RYOLO_OK;
+  resize_copy_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, xp, N, H, W, C,
+                                                                             factor, (__nv_bfloat16*)y, yp);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stream) {
+  const long long total = (long long)N * H * W;
+  if (total == 0) return RYOLO_OK;
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W, (__nv_bfloat16*)y);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream) {
+  RY_CHECK_ARG(Cout > 0 && Cin > 0 && k > 0, "pack_weights: bad shape");
+  RY_CHECK_ARG(!stem || (Cin == 3 && k == 3), "pack_weights: the stem layout is for 3-channel 3x3 convs");
+  const long long total = (long long)Cout * (stem ? 64 : k * k * Cin);
+  pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, k, stem,
+                                                                             (__nv_bfloat16*)out);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,147 @@
+"""Thin Python wrappers over the conv-stack entry points of libryolo_b200.so.
+
+`Act` is an NHWC bf16 *view*: a channel slice [coff, coff+C) of a [N,H,W,Cbuf] buffer, so producers
+write straight into their slot of a concat buffer (torch.cat of the reference never materialises).
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+ACT = {"linear": 0, "leaky": 1, "mish": 2, "swish": 3}
+
+
+class Act:
+    __slots__ = ("buf", "N", "H", "W", "C", "coff")
+
+    def __init__(self, buf, C=None, coff=0):
+        assert buf.dtype == torch.bfloat16 and buf.dim() == 4 and buf.is_contiguous()
+        self.buf = buf
+        self.N, self.H, self.W = buf.shape[0], buf.shape[1], buf.shape[2]
+        self.C = buf.shape[3] - coff if C is None else C
+        self.coff = coff
+        assert coff % 8 == 0 and self.C % 8 == 0 and coff + self.C <= buf.shape[3]
+
+    @staticmethod
+    def empty(N, H, W, C, device):
+        return Act(torch.empty((N, H, W, C), dtype=torch.bfloat16, device=device))
+
+    @property
+    def ptr(self):
+        return self.buf.data_ptr() + 2 * self.coff
+
+    @property
+    def pitch(self):
+        return self.buf.shape[3]
+
+    @property
+    def P(self):
+        return self.N * self.H * self.W
+
+    def slice(self, coff, C):
+        return Act(self.buf, C, self.coff + coff)
+
+    def torch(self):
+        """[N,H,W,C] torch view (for tests)."""
+        return self.buf[..., self.coff:self.coff + self.C]
+
+
+def _vp(x):
+    return ctypes.c_void_p(x)
+
+
+def _tp(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def out_hw(H, W, k, s):
+    p = (k - 1) // 2
+    return (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+
+
+def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear", residual=None, head=None,
+           reference=False):
+    """x: Act; w: packed bf16 [Cout, k*k*Cin]; out: Act (bf16 NHWC) or, with head=(na, ch), an fp32
+    [N, na, Ho, Wo, ch] tensor.  Returns out."""
+    Ho, Wo = out_hw(x.H, x.W, k, stride)
+    dev = x.buf.device
+    d = L.ConvDesc()
+    d.x, d.N, d.H, d.W, d.Cin, d.x_cpitch = x.ptr, x.N, x.H, x.W, x.C, x.pitch
+    d.w, d.Cout, d.ksize, d.stride = w.data_ptr(), Cout, k, stride
+    assert w.dtype == torch.bfloat16 and w.numel() == Cout * k * k * x.C, (w.shape, Cout, k, x.C)
+    if head is None:
+        if out is None:
+            out = Act.empty(x.N, Ho, Wo, Cout, dev)
+        assert (out.N, out.H, out.W, out.C) == (x.N, Ho, Wo, Cout)
+        d.out, d.out_mode, d.out_cpitch = out.ptr, 0, out.pitch
+    else:
+        na, ch = head
+        if out is None:
+            out = torch.empty((x.N, na, Ho, Wo, ch), dtype=torch.float32, device=dev)
+        assert out.dtype == torch.float32 and tuple(out.shape) == (x.N, na, Ho, Wo, ch) and out.is_contiguous()
+        d.out, d.out_mode, d.out_cpitch, d.head_na, d.head_ch = out.data_ptr(), 1, 0, na, ch
+    d.scale = scale.data_ptr() if scale is not None else None
+    d.shift = shift.data_ptr() if shift is not None else None
+    d.act = ACT[act]
+    if residual is not None:
+        d.residual, d.res_cpitch = residual.ptr, residual.pitch
+    fn = L.lib().ryolo_conv2d_reference if reference else L.lib().ryolo_conv2d_forward
+    L.check(fn(ctypes.byref(d), L.stream()))
+    return out
+
+
+def pack_weights(w_oihw, stem=False):
+    """fp32 OIHW (state-dict layout) -> bf16 [Cout, kh*kw*Cin] ([Cout, 64] for the stem)."""
+    w = w_oihw.detach().contiguous().float()
+    Cout, Cin, k, _ = w.shape
+    out = torch.empty((Cout, 64 if stem else k * k * Cin), dtype=torch.bfloat16, device=w.device)
+    L.check(L.lib().ryolo_pack_weights(_tp(w), Cout, Cin, k, 1 if stem else 0, _tp(out), L.stream()))
+    return out
+
+
+def stem_im2col(img):
+    img = img.contiguous().float()
+    N, C, H, W = img.shape
+    assert C == 3
+    out = Act.empty(N, H, W, 64, img.device)
+    L.check(L.lib().ryolo_stem_im2col(_tp(img), N, H, W, _vp(out.ptr), L.stream()))
+    return out
+
+
+def bn_stats(x, sum_, sumsq):
+    L.check(L.lib().ryolo_bn_stats(_vp(x.ptr), x.pitch, x.P, x.C, _tp(sum_), _tp(sumsq), L.stream()))
+
+
+def bn_finalize(sum_, sumsq, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches, scale, shift,
+                save_mean=None, save_invstd=None):
+    L.check(L.lib().ryolo_bn_finalize(_tp(sum_), _tp(sumsq), float(count), gamma.numel(), _tp(gamma), _tp(beta),
+                                      float(eps), float(momentum), _tp(running_mean), _tp(running_var),
+                                      _tp(num_batches), _tp(scale), _tp(shift), _tp(save_mean), _tp(save_invstd),
+                                      L.stream()))
+
+
+def scale_shift_act(x, scale, shift, act, out, residual=None, x2=None, scale2=None, shift2=None):
+    L.check(L.lib().ryolo_scale_shift_act(
+        _vp(x.ptr), x.pitch, _tp(scale), _tp(shift), _vp(x2.ptr if x2 is not None else 0),
+        x2.pitch if x2 is not None else 0, _tp(scale2), _tp(shift2), ACT[act],
+        _vp(residual.ptr if residual is not None else 0), residual.pitch if residual is not None else 0,
+        _vp(out.ptr), out.pitch, x.P, x.C, L.stream()))
+    return out
+
+
+def maxpool(x, k, stride, pad, out=None):
+    Ho, Wo = (x.H + 2 * pad - k) // stride + 1, (x.W + 2 * pad - k) // stride + 1
+    if out is None:
+        out = Act.empty(x.N, Ho, Wo, x.C, x.buf.device)
+    L.check(L.lib().ryolo_maxpool(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, k, stride, pad, _vp(out.ptr), out.pitch,
+                                  L.stream()))
+    return out
+
+
+def resize_copy(x, factor, out=None):
+    if out is None:
+        out = Act.empty(x.N, x.H * factor, x.W * factor, x.C, x.buf.device)
+    L.check(L.lib().ryolo_resize_copy(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, factor, _vp(out.ptr), out.pitch,
+                                      L.stream()))
+    return out
