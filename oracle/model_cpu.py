@@ -21,18 +21,13 @@ class Net:
 
     # -- primitives -------------------------------------------------------------------------
     def bn(self, x, pre):
+        """nn.BatchNorm2d forward (model/utils.py:16-17) through the same ATen op the reference runs."""
         g, b = self.sd[pre + ".weight"], self.sd[pre + ".bias"]
-        rm, rv = self.sd[pre + ".running_mean"], self.sd[pre + ".running_var"]
+        rm, rv = self.sd[pre + ".running_mean"].clone(), self.sd[pre + ".running_var"].clone()
+        y = F.batch_norm(x, rm, rv, g, b, self.train, self.mom, self.eps)
         if self.train:
-            mean = x.mean((0, 2, 3))
-            var = x.var((0, 2, 3), unbiased=False)
-            n = x.numel() / x.shape[1]
-            self.new_stats[pre + ".running_mean"] = (1 - self.mom) * rm + self.mom * mean
-            self.new_stats[pre + ".running_var"] = (1 - self.mom) * rv + self.mom * var * n / max(n - 1, 1)
-        else:
-            mean, var = rm, rv
-        return (x - mean[None, :, None, None]) * torch.rsqrt(var + self.eps)[None, :, None, None] \
-            * g[None, :, None, None] + b[None, :, None, None]
+            self.new_stats[pre + ".running_mean"], self.new_stats[pre + ".running_var"] = rm, rv
+        return y
 
     def conv(self, x, pre, act, s=1):
         """model/utils.py:6-32 Conv = conv(+BN)(+act). `pre` is the module path of the Conv."""
@@ -46,11 +41,11 @@ class Net:
     @staticmethod
     def act(x, a):
         if a == "mish":
-            return x * torch.tanh(F.softplus(x))
+            return F.mish(x)
         if a == "leaky":
             return F.leaky_relu(x, 0.1)
         if a == "swish":
-            return x * torch.sigmoid(x)
+            return F.silu(x)
         return x
 
     # -- composites (model/utils.py) -----------------------------------------------------------
@@ -122,7 +117,7 @@ class Net:
         y = d + o
         if (pre + ".rbr_identity.weight") in self.sd:
             y = y + self.bn(x, pre + ".rbr_identity")
-        return y * torch.sigmoid(y)
+        return F.silu(y)
 
     # -- backbones / necks (model/backbone.py, model/neck.py) -------------------------------------
     def backbone_v4(self, x):  # backbone.py:4-36

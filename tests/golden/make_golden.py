@@ -76,8 +76,39 @@ class _FakeModel:
         return iter([self._p])
 
 
+def make_model_goldens(Yolo):
+    """Reference Yolo fwd (train + eval) on weights that tests can regenerate: tests.util.det_init
+    seeds every state-dict entry from its NAME (distributions of train.py:28-33), so the fixture does
+    not depend on module traversal order or on the unseeded default inits of biases / implicit params."""
+    from tests.util import det_init
+    torch.set_num_threads(8)
+    gen = torch.Generator().manual_seed(4321)
+    for ver, mode, nc, S in (("yolov4", "csl", 2, 64), ("yolov4", "kfiou", 2, 64), ("yolov7", "csl", 16, 64),
+                             ("yolov5", "csl", 2, 64)):
+        model = Yolo(nc, CFG, mode, ver)
+        det_init(model)
+        img = torch.rand(2, 3, S, S, generator=gen)
+        model.train()
+        tr = model(img, training=True)
+        stats = {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
+        keys = list(model.state_dict().keys())
+        model.eval()
+        with torch.no_grad():
+            ev_levels, ev_infer = model(img, training=False)
+        probe = {k: float(v.double().sum()) for k, v in model.state_dict().items()}
+        torch.save(dict(ver=ver, mode=mode, nc=nc, img=img, train_levels=[t.detach() for t in tr],
+                        running_after=stats, eval_levels=ev_levels, eval_infer=ev_infer, keys=keys,
+                        weight_probe=probe),
+                   os.path.join(HERE, f"model_{ver}_{mode}_nc{nc}.pt"))
+        print("model", ver, mode, nc, len(keys), [tuple(t.shape) for t in tr])
+
+
 def main():
     _install_stubs()
+    if "--only-model" in sys.argv:
+        from model.yolo import Yolo
+        make_model_goldens(Yolo)
+        return
     from lib import general as rgen
     from lib import loss as rloss
     from model.yolo import Yolo
@@ -178,35 +209,8 @@ def main():
         print("post_process", ct, it, [o.shape[0] for o in outs], "score ties:", ties)
     torch.save(dict(pred=pred, cases=cases), os.path.join(HERE, "post_process.pt"))
 
-    # ---- conv stack (weights regenerated from a seed by the tests: see tests/util.py) -------
-    def winit(m):  # restated from train.py:28-33
-        cn = m.__class__.__name__
-        if cn.find("Conv2d") != -1:
-            torch.nn.init.normal_(m.weight.data, 0.0, 0.02)
-        elif cn.find("BatchNorm2d") != -1:
-            torch.nn.init.normal_(m.weight.data, 1.0, 0.02)
-            torch.nn.init.constant_(m.bias.data, 0.0)
-
-    torch.set_num_threads(8)
-    for ver, mode, nc, S in (("yolov4", "csl", 2, 64), ("yolov4", "kfiou", 2, 64), ("yolov7", "csl", 16, 64),
-                             ("yolov5", "csl", 2, 64)):
-        model = Yolo(nc, CFG, mode, ver)
-        torch.manual_seed(777)
-        model.apply(winit)
-        img = torch.rand(2, 3, S, S, generator=gen)
-        model.train()
-        tr = model(img, training=True)
-        stats = {k: v.clone() for k, v in model.state_dict().items() if "running" in k}
-        keys = list(model.state_dict().keys())
-        model.eval()
-        with torch.no_grad():
-            ev_levels, ev_infer = model(img, training=False)
-        probe = {k: float(v.double().sum()) for k, v in list(model.state_dict().items())[:6]}
-        torch.save(dict(ver=ver, mode=mode, nc=nc, img=img, train_levels=[t.detach() for t in tr],
-                        running_after=stats, eval_levels=ev_levels, eval_infer=ev_infer, keys=keys,
-                        weight_probe=probe),
-                   os.path.join(HERE, f"model_{ver}_{mode}_nc{nc}.pt"))
-        print("model", ver, mode, nc, len(keys), [tuple(t.shape) for t in tr])
+    # ---- conv stack ---------------------------------------------------------------------
+    make_model_goldens(Yolo)
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):

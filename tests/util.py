@@ -53,3 +53,33 @@ def winit(m):
     elif cn.find("BatchNorm2d") != -1:
         torch.nn.init.normal_(m.weight.data, 1.0, 0.02)
         torch.nn.init.constant_(m.bias.data, 0.0)
+
+
+def det_init(model):
+    """Order-independent deterministic init: every state-dict entry is seeded from its NAME.
+    Distributions follow the reference's weights_init_normal (train.py:28-33): conv weights N(0,.02),
+    BN gamma N(1,.02), BN beta 0; plus small seeded values for the entries the reference leaves to
+    unseeded default inits (head-conv biases, ImplicitA ~N(0,.02), ImplicitM ~N(1,.02))."""
+    import zlib
+    sd = model.state_dict()
+    with torch.no_grad():
+        for name, t in sd.items():
+            g = torch.Generator().manual_seed(zlib.crc32(name.encode()))
+            if name.endswith("num_batches_tracked"):
+                t.zero_()
+            elif name.endswith("running_mean"):
+                t.zero_()
+            elif name.endswith("running_var"):
+                t.fill_(1.0)
+            elif name.endswith("implicit"):
+                base = 1.0 if ".im" in name else 0.0
+                t.copy_(base + 0.02 * torch.randn(t.shape, generator=g))
+            elif t.dim() == 4:                                   # conv weight
+                t.copy_(0.02 * torch.randn(t.shape, generator=g))
+            elif name.endswith(".bias") and ".conv.0." in name:   # head conv bias
+                t.copy_(0.05 * torch.randn(t.shape, generator=g))
+            elif name.endswith(".weight"):                       # BN gamma
+                t.copy_(1.0 + 0.02 * torch.randn(t.shape, generator=g))
+            else:                                                # BN beta
+                t.zero_()
+    return model
