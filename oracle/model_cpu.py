@@ -18,6 +18,7 @@ class Net:
     def __init__(self, sd, train, eps=1e-5, momentum=0.1):
         self.sd, self.train, self.eps, self.mom = sd, train, eps, momentum
         self.new_stats = {}
+        self.trace = None      # optional list of (module path, input, output) per Conv / RepConv
 
     # -- primitives -------------------------------------------------------------------------
     def bn(self, x, pre):
@@ -33,10 +34,13 @@ class Net:
         """model/utils.py:6-32 Conv = conv(+BN)(+act). `pre` is the module path of the Conv."""
         w = self.sd[pre + ".conv.0.weight"]
         bias = self.sd.get(pre + ".conv.0.bias")
-        x = F.conv2d(x, w, bias, stride=s, padding=(w.shape[2] - 1) // 2)
+        y = F.conv2d(x, w, bias, stride=s, padding=(w.shape[2] - 1) // 2)
         if (pre + ".conv.1.weight") in self.sd:
-            x = self.bn(x, pre + ".conv.1")
-        return self.act(x, act)
+            y = self.bn(y, pre + ".conv.1")
+        y = self.act(y, act)
+        if self.trace is not None:
+            self.trace.append((pre, x, y))
+        return y
 
     @staticmethod
     def act(x, a):
@@ -117,7 +121,10 @@ class Net:
         y = d + o
         if (pre + ".rbr_identity.weight") in self.sd:
             y = y + self.bn(x, pre + ".rbr_identity")
-        return F.silu(y)
+        y = F.silu(y)
+        if self.trace is not None:
+            self.trace.append((pre, x, y))
+        return y
 
     # -- backbones / necks (model/backbone.py, model/neck.py) -------------------------------------
     def backbone_v4(self, x):  # backbone.py:4-36
@@ -196,9 +203,10 @@ class Net:
         return x6, x5, x4
 
 
-def forward(sd, img, ver, mode, nc, train, anchors_cfg=None, angles=None, decode=True):
+def forward(sd, img, ver, mode, nc, train, anchors_cfg=None, angles=None, decode=True, trace=None):
     """Yolo.forward (model/yolo.py:46-51).  Returns (levels, infer|None, new_running_stats)."""
     net = Net(sd, train)
+    net.trace = trace
     d3, d4, d5 = getattr(net, "backbone_" + ver[-2:])(img)
     heads = getattr(net, "neck_" + ver[-2:])(d5, d4, d3)
     na, ch = (3, nc + 185) if mode == "csl" else (18, nc + 6)

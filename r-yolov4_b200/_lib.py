@@ -85,6 +85,13 @@ def lib():
     return _lib
 
 
+LAUNCHES = [0]          # kernels launched through the library (bench.py reports it as gpu_launches)
+
+
+def count(n):
+    LAUNCHES[0] += n
+
+
 def check(rc):
     if rc != 0:
         raise RyoloError(f"libryolo_b200 error {rc}: {lib().ryolo_last_error().decode()}")

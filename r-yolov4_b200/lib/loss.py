@@ -40,6 +40,7 @@ class _FusedLoss(torch.autograd.Function):
         gp = (ctypes.c_void_p * 3)(*[g.data_ptr() for g in grads]) if need_grad else None
         L.check(lib.ryolo_loss(mode, lp, gp, B, na, nc, ghw, L.ptr(tg), T, tg.shape[1], L.ptr(anchors), hyp,
                                L.ptr(items), L.ptr(ws), nb, L.stream()))
+        L.count(10 if T else 4)
         ctx.grads = grads
         ctx.mark_non_differentiable(items)
         return items[4:5].clone(), items

@@ -50,6 +50,7 @@ class YoloCSLLayer(_YoloLayer):
             awh = (ctypes.c_float * 6)(*[float(v) for a in anc for v in a[:2]])
             L.check(lib.ryolo_decode_csl(L.ptr(p.detach()), B, gs, nc, float(s), awh, L.ptr(infer), row0, R,
                                          L.stream()))
+            L.count(1)
             row0 += self.na * gs * gs
         return out, infer
 
@@ -77,5 +78,6 @@ class YoloKFIoULayer(_YoloLayer):
             gs = p.shape[2]
             L.check(lib.ryolo_decode_kfiou(L.ptr(p.detach()), B, self.na, gs, nc, float(s), L.ptr(anc), L.ptr(infer),
                                            row0, R, L.stream()))
+            L.count(1)
             row0 += self.na * gs * gs
         return out, infer

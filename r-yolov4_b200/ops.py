@@ -11,6 +11,22 @@ from . import _lib as L
 
 ACT = {"linear": 0, "leaky": 1, "mish": 2, "swish": 3}
 
+# Optional per-launch timing of the conv kernel (bench.py): list of (tag, start_event, end_event).
+PROFILE = None
+_pending = []
+
+
+def _prof_begin():
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    _pending.append(e)
+
+
+def _prof_end(tag):
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    PROFILE.append((tag, _pending.pop(), e))
+
 
 class Act:
     __slots__ = ("buf", "N", "H", "W", "C", "coff")
@@ -87,7 +103,12 @@ def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear"
     if residual is not None:
         d.residual, d.res_cpitch = residual.ptr, residual.pitch
     fn = L.lib().ryolo_conv2d_reference if reference else L.lib().ryolo_conv2d_forward
+    if PROFILE is not None:
+        _prof_begin()
     L.check(fn(ctypes.byref(d), L.stream()))
+    L.count(1)
+    if PROFILE is not None:
+        _prof_end(('conv', x.N * Ho * Wo, Cout, k * k * x.C))
     return out
 
 
@@ -97,6 +118,7 @@ def pack_weights(w_oihw, stem=False):
     Cout, Cin, k, _ = w.shape
     out = torch.empty((Cout, 64 if stem else k * k * Cin), dtype=torch.bfloat16, device=w.device)
     L.check(L.lib().ryolo_pack_weights(_tp(w), Cout, Cin, k, 1 if stem else 0, _tp(out), L.stream()))
+    L.count(1)
     return out
 
 
@@ -106,11 +128,13 @@ def stem_im2col(img):
     assert C == 3
     out = Act.empty(N, H, W, 64, img.device)
     L.check(L.lib().ryolo_stem_im2col(_tp(img), N, H, W, _vp(out.ptr), L.stream()))
+    L.count(1)
     return out
 
 
 def bn_stats(x, sum_, sumsq):
     L.check(L.lib().ryolo_bn_stats(_vp(x.ptr), x.pitch, x.P, x.C, _tp(sum_), _tp(sumsq), L.stream()))
+    L.count(1)
 
 
 def bn_finalize(sum_, sumsq, count, gamma, beta, eps, momentum, running_mean, running_var, num_batches, scale, shift,
@@ -119,6 +143,7 @@ def bn_finalize(sum_, sumsq, count, gamma, beta, eps, momentum, running_mean, ru
                                       float(eps), float(momentum), _tp(running_mean), _tp(running_var),
                                       _tp(num_batches), _tp(scale), _tp(shift), _tp(save_mean), _tp(save_invstd),
                                       L.stream()))
+    L.count(1)
 
 
 def scale_shift_act(x, scale, shift, act, out, residual=None, x2=None, scale2=None, shift2=None):
@@ -127,6 +152,7 @@ def scale_shift_act(x, scale, shift, act, out, residual=None, x2=None, scale2=No
         x2.pitch if x2 is not None else 0, _tp(scale2), _tp(shift2), ACT[act],
         _vp(residual.ptr if residual is not None else 0), residual.pitch if residual is not None else 0,
         _vp(out.ptr), out.pitch, x.P, x.C, L.stream()))
+    L.count(1)
     return out
 
 
@@ -136,6 +162,7 @@ def maxpool(x, k, stride, pad, out=None):
         out = Act.empty(x.N, Ho, Wo, x.C, x.buf.device)
     L.check(L.lib().ryolo_maxpool(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, k, stride, pad, _vp(out.ptr), out.pitch,
                                   L.stream()))
+    L.count(1)
     return out
 
 
@@ -144,4 +171,5 @@ def resize_copy(x, factor, out=None):
         out = Act.empty(x.N, x.H * factor, x.W * factor, x.C, x.buf.device)
     L.check(L.lib().ryolo_resize_copy(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, factor, _vp(out.ptr), out.pitch,
                                       L.stream()))
+    L.count(1)
     return out
