@@ -8,8 +8,9 @@
 //                  zero padding falls out of TMA's out-of-bounds fill, stride-2 convs use the tensor map's
 //                  element strides.  No im2col buffer ever exists.
 //   operands       bf16, K-major, 128-byte swizzle (TMA writes it, the UMMA descriptor reads it)
-//   pipeline       warp 0: TMA producer | warp 1: TMEM alloc + single-thread MMA issue | warps 2-5: epilogue
-//                  (tcgen05.ld -> scale/shift/activation/residual -> global), mbarrier ring of kStages
+//   pipeline       persistent CTAs (one per SM); warp 0: TMA producer | warp 1: TMEM alloc + single-thread MMA
+//                  issue into two alternating TMEM accumulators | warps 2-5: epilogue (tcgen05.ld -> scale/shift/
+//                  activation/residual -> global) overlapping the next tile's main loop; mbarrier smem ring
 //   epilogue       mode 0: bf16 NHWC into a channel slice of a (concat) buffer; per-channel scale/shift =
 //                  folded BatchNorm (eval) or identity (train: raw conv output, BN statistics follow);
 //                  mode 1: fp32 head written directly in the reference's [B, na, gs, gs, ch] layout
@@ -24,6 +25,7 @@ namespace {
 constexpr int kBM = 128;        // UMMA M (rows of the patch tile, TH*TW <= 128)
 constexpr int kBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kThreads = 192;   // 6 warps
+constexpr int kMaxStages = 12;
 
 // ------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -131,6 +133,8 @@ __device__ __forceinline__ float act_apply(float x, int act) {
 struct ConvKernelParams {
   int N, Ho, Wo, Cout, Cin;
   int TH, TW, tiles_h, tiles_w, n_tiles;
+  int BN, stages;
+  uint32_t tmem_cols;
   int ksize, stride, pad, kb_per_tap;
   int mode, act;
   void* out;
@@ -142,30 +146,30 @@ struct ConvKernelParams {
   int head_na, head_ch;
 };
 
-template <int BN, int STAGES>
-__global__ void __launch_bounds__(kThreads)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// Persistent, warp-specialised implicit-GEMM conv.  One CTA per SM walks tiles  t = blockIdx.x + i*gridDim.x
+// (n-tile fastest, so CTAs running side by side share the activation patch in L2).  The TMA producer runs
+// ahead across tile boundaries through a ring of `stages` smem slots; the MMA warp alternates between two
+// TMEM accumulators so that the epilogue of tile i overlaps the main loop of tile i+1.
+__global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ConvKernelParams p) {
-  constexpr uint32_t kABytes = kBM * kBK * 2, kBBytes = BN * kBK * 2;
-  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  const int BN = p.BN, STAGES = p.stages;
+  const uint32_t kABytes = kBM * kBK * 2, kBBytes = (uint32_t)BN * kBK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t sA = smem_base, sB = smem_base + STAGES * kABytes;
-  __shared__ __align__(8) uint64_t bars[2 * STAGES + 1];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
   __shared__ uint32_t tmem_slot;
-  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[STAGES]),
-                 bar_acc = smem_u32(&bars[2 * STAGES]);
+  const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
+                 bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + 2]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // tile coordinates: n-tile fastest so that CTAs sharing an A patch run back to back (L2 reuse)
-  const int nt = blockIdx.x % p.n_tiles;
-  int mt = blockIdx.x / p.n_tiles;
-  const int pw = mt % p.tiles_w; mt /= p.tiles_w;
-  const int ph = mt % p.tiles_h;
-  const int img = mt / p.tiles_h;
-  const int h0 = ph * p.TH, w0 = pw * p.TW, n0 = nt * BN;
   const int taps = p.ksize * p.ksize;
   const int KB = taps * p.kb_per_tap;
+  const long long total_tiles = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -174,11 +178,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    mbar_init(bar_acc, 1);
+    for (int b = 0; b < 2; b++) {
+      mbar_init(bar_acc_full + 8 * b, 1);
+      mbar_init(bar_acc_empty + 8 * b, 4);     // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&tmem_slot), kTmemCols);
+    tmem_alloc(smem_u32(&tmem_slot), p.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -192,102 +199,130 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * kBK * 2;
       int s = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < KB; kb++) {
-        const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-        const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-        mbar_wait(bar_empty + 8 * s, phase ^ 1u);
-        mbar_expect_tx(bar_full + 8 * s, a_bytes + kBBytes);
-        tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, w0 * p.stride + kw - p.pad,
-                    h0 * p.stride + kh - p.pad, img);
-        tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, tap * p.Cin + cb * kBK, n0);
-        if (++s == STAGES) { s = 0; phase ^= 1u; }
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = (int)(t % p.n_tiles);
+        long long mt = t / p.n_tiles;
+        const int pw = (int)(mt % p.tiles_w); mt /= p.tiles_w;
+        const int ph = (int)(mt % p.tiles_h);
+        const int img = (int)(mt / p.tiles_h);
+        const int hs = ph * p.TH * p.stride - p.pad, ws = pw * p.TW * p.stride - p.pad, n0 = nt * BN;
+        for (int kb = 0; kb < KB; kb++) {
+          const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+          const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+          mbar_wait(bar_empty + 8 * s, phase ^ 1u);
+          mbar_expect_tx(bar_full + 8 * s, a_bytes + kBBytes);
+          tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, ws + kw, hs + kh, img);
+          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, tap * p.Cin + cb * kBK, n0);
+          if (++s == STAGES) { s = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer (one lane) ==================================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BN < 16 ? 16 : BN);
+      const uint32_t idesc = umma_idesc_bf16(BN);
       int s = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < KB; kb++) {
-        mbar_wait(bar_full + 8 * s, phase);
+      uint32_t phase = 0, it = 0;
+      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+        const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+        mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a0 = sA + s * kABytes, b0 = sB + s * kBBytes;
+        const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+        for (int kb = 0; kb < KB; kb++) {
+          mbar_wait(bar_full + 8 * s, phase);
+          tc_fence_after();
+          const uint32_t a0 = sA + s * kABytes, b0 = sB + s * kBBytes;
 #pragma unroll
-        for (int k = 0; k < kBK / 16; k++) {
-          umma_bf16(tmem_base, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                    (kb | k) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; k++) {
+            umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
+                      (kb | k) ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
+          if (++s == STAGES) { s = 0; phase ^= 1u; }
         }
-        umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
-        if (++s == STAGES) { s = 0; phase ^= 1u; }
+        umma_commit(bar_acc_full + 8 * buf);  // accumulator complete
       }
-      umma_commit(bar_acc);                 // accumulator complete
     }
   } else {
     // ================================ epilogue (4 warps, one TMEM sub-partition each) =========
     const int sub = warp & 3;               // TMEM lanes [32*sub, 32*sub+32) are accessible to this warp
     const int r = sub * 32 + lane;          // accumulator row = pixel of the patch
     const int hl = r / p.TW, wl = r - hl * p.TW;
-    const int ho = h0 + hl, wo = w0 + wl;
-    const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo);
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    const long long pix = ((long long)img * p.Ho + ho) * p.Wo + wo;
+    uint32_t it = 0;
+    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const int nt = (int)(t % p.n_tiles);
+      long long mt = t / p.n_tiles;
+      const int pw = (int)(mt % p.tiles_w); mt /= p.tiles_w;
+      const int ph = (int)(mt % p.tiles_h);
+      const int img = (int)(mt / p.tiles_h);
+      const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
+      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo);
+      const long long pix = ((long long)img * p.Ho + ho) * p.Wo + wo;
+      const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+      mbar_wait(bar_acc_full + 8 * buf, aphase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + buf * (uint32_t)BN + ((uint32_t)(sub * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-      if (p.mode == RYOLO_OUT_NHWC_BF16) {
-        __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
-        const __nv_bfloat16* res = p.residual ? p.residual + pix * p.res_cpitch + n0 + c0 : nullptr;
-#pragma unroll
-        for (int g = 0; g < 4; g++) {
-          const int c = n0 + c0 + 8 * g;
-          if (c >= p.Cout) break;
-          float f[8];
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            float x = __uint_as_float(v[8 * g + j]);
-            if (p.scale) x = x * __ldg(p.scale + c + j);
-            if (p.shift) x = x + __ldg(p.shift + c + j);
-            f[j] = act_apply(x, p.act);
-          }
-          if (res) {
-            const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
-            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-              const float2 t = __bfloat1622float2(rb[j]);
-              f[2 * j] += t.x;
-              f[2 * j + 1] += t.y;
-            }
-          }
-          uint4 pk;
-          __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-          for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(t_row + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BN) {                 // last chunk is in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
         }
-      } else {  // RYOLO_OUT_HEAD_F32: out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k
-        float* o = (float*)p.out;
+        if (!row_ok) continue;
+        if (p.mode == RYOLO_OUT_NHWC_BF16) {
+          __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
+          const __nv_bfloat16* res = p.residual ? p.residual + pix * p.res_cpitch + n0 + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const int c = n0 + c0 + 8 * g;
+            if (c >= p.Cout) break;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+              float x = __uint_as_float(v[8 * g + j]);
+              if (p.scale) x = x * __ldg(p.scale + c + j);
+              if (p.shift) x = x + __ldg(p.shift + c + j);
+              f[j] = act_apply(x, p.act);
+            }
+            if (res) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
+              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                const float2 tt = __bfloat1622float2(rb[j]);
+                f[2 * j] += tt.x;
+                f[2 * j + 1] += tt.y;
+              }
+            }
+            uint4 pk;
+            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+            for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+          }
+        } else {  // RYOLO_OUT_HEAD_F32: out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k
+          float* o = (float*)p.out;
 #pragma unroll 4
-        for (int j = 0; j < 32; j++) {
-          const int c = n0 + c0 + j;
-          if (c >= p.Cout) break;
-          float x = __uint_as_float(v[j]);
-          if (p.scale) x = x * __ldg(p.scale + c);
-          if (p.shift) x = x + __ldg(p.shift + c);
-          const int a = c / p.head_ch, k = c - a * p.head_ch;
-          o[((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k] = act_apply(x, p.act);
+          for (int j = 0; j < 32; j++) {
+            const int c = n0 + c0 + j;
+            if (c >= p.Cout) break;
+            float x = __uint_as_float(v[j]);
+            if (p.scale) x = x * __ldg(p.scale + c);
+            if (p.shift) x = x + __ldg(p.shift + c);
+            const int a = c / p.head_ch, k = c - a * p.head_ch;
+            o[((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k] = act_apply(x, p.act);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
 // ------------------------------------------------------------------------------------ reference kernel
@@ -392,22 +427,56 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   return RYOLO_OK;
 }
 
-template <int BN, int STAGES>
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+constexpr size_t kSmemBudget = 200 * 1024;
+
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (kBM * kBK * 2 + BN * kBK * 2) + 1024;
+  const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
+  int stages = (int)((kSmemBudget - 1024) / stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  uint32_t cols = 32;
+  while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
+  p.tmem_cols = cols;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBudget);
     if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     configured = true;
   }
-  p.n_tiles = (p.Cout + BN - 1) / BN;
-  const long long blocks = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
-  RY_CHECK_ARG(blocks > 0 && blocks < (1ll << 31), "conv: grid too large");
-  conv_fwd_kernel<BN, STAGES><<<(unsigned)blocks, kThreads, smem, st>>>(tmA, tmB, p);
+  p.n_tiles = (p.Cout + p.BN - 1) / p.BN;
+  const long long tiles = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  RY_CHECK_ARG(tiles > 0, "conv: empty problem");
+  int grid = sm_count();
+  if (p.n_tiles > 1 && grid > p.n_tiles) grid -= grid % p.n_tiles;   // a CTA always sees the same n-tile
+  if (tiles < grid) grid = (int)tiles;
+  conv_fwd_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
+}
+
+// Output-channel tile: multiple of 32 (16 for tiny Cout) up to 256, minimising padded columns.
+int pick_bn(int Cout) {
+  if (Cout <= 16) return 16;
+  if (Cout <= 256) return (Cout + 31) / 32 * 32;
+  int best = 256, best_waste = 1 << 30;
+  for (int bn = 256; bn >= 128; bn -= 32) {
+    const int waste = (Cout + bn - 1) / bn * bn - Cout;
+    if (waste < best_waste) { best_waste = waste; best = bn; }
+  }
+  return best;
 }
 
 }  // namespace
@@ -423,9 +492,8 @@ int ryolo_conv2d_forward(const ryolo_conv_desc* d, void* stream) {
   if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
   if (d->N == 0) return RYOLO_OK;
 
-  int BN = 128;
-  if (d->Cout <= 32) BN = 32;
-  else if (d->Cout <= 64 || (d->Cout % 128 != 0 && d->Cout % 128 <= 64)) BN = 64;
+  const int BN = pick_bn(d->Cout);
+  p.BN = BN;
 
   CUtensorMap tmA, tmB;
   {
@@ -451,9 +519,7 @@ int ryolo_conv2d_forward(const ryolo_conv_desc* d, void* stream) {
     if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the weight operand"); return RYOLO_ERR_CUDA; }
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (BN == 32) return launch<32, 4>(tmA, tmB, p, st);
-  if (BN == 64) return launch<64, 4>(tmA, tmB, p, st);
-  return launch<128, 3>(tmA, tmB, p, st);
+  return launch(tmA, tmB, p, st);
 }
 
 // Same contract as ryolo_conv2d_forward, computed by a plain CUDA-core kernel (device-side checker).
