@@ -154,6 +154,14 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // (n-tile fastest, so CTAs running side by side share the activation patch in L2).  The TMA producer runs
 // ahead across tile boundaries through a ring of `stages` smem slots; the MMA warp alternates between two
 // TMEM accumulators so that the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// EPI selects the epilogue at compile time so that its inner loops carry no per-element branches:
+//   EPI_RAW     bf16 NHWC store of the bare accumulator (train mode: BatchNorm statistics come next)
+//   EPI_AFFINE  y = ACT(acc*scale + shift) [+ residual] -> bf16 NHWC   (eval-folded BN, scale/shift staged in smem)
+//   EPI_HEAD    y = acc*scale + shift -> fp32 [B, na, gs, gs, ch]
+enum { EPI_RAW = 0, EPI_AFFINE = 1, EPI_HEAD = 2 };
+
+template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const ConvKernelParams p) {
@@ -169,7 +177,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int taps = p.ksize * p.ksize;
   const int KB = taps * p.kb_per_tap;
-  const long long total_tiles = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  __shared__ __align__(16) float s_aff[2 * 256];           // scale | shift of this CTA's n-tile (EPI_AFFINE / EPI_HEAD)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -199,12 +208,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * kBK * 2;
       int s = 0;
       uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const int nt = (int)(t % p.n_tiles);
-        long long mt = t / p.n_tiles;
-        const int pw = (int)(mt % p.tiles_w); mt /= p.tiles_w;
-        const int ph = (int)(mt % p.tiles_h);
-        const int img = (int)(mt / p.tiles_h);
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int nt = t % p.n_tiles;
+        int mt = t / p.n_tiles;
+        const int pw = mt % p.tiles_w; mt /= p.tiles_w;
+        const int ph = mt % p.tiles_h;
+        const int img = mt / p.tiles_h;
         const int hs = ph * p.TH * p.stride - p.pad, ws = pw * p.TW * p.stride - p.pad, n0 = nt * BN;
         for (int kb = 0; kb < KB; kb++) {
           const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
@@ -223,7 +232,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const uint32_t idesc = umma_idesc_bf16(BN);
       int s = 0;
       uint32_t phase = 0, it = 0;
-      for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
         const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
@@ -248,13 +257,24 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int sub = warp & 3;               // TMEM lanes [32*sub, 32*sub+32) are accessible to this warp
     const int r = sub * 32 + lane;          // accumulator row = pixel of the patch
     const int hl = r / p.TW, wl = r - hl * p.TW;
+    const int et = threadIdx.x - 64;        // 0..127
+    if (EPI != EPI_RAW) {
+      // every tile of this CTA has the same n-tile when n_tiles divides gridDim.x (host guarantees it)
+      const int n0c = (blockIdx.x % p.n_tiles) * BN;
+      for (int i = et; i < BN; i += 128) {
+        const int c = n0c + i;
+        s_aff[i] = (p.scale && c < p.Cout) ? p.scale[c] : 1.f;
+        s_aff[256 + i] = (p.shift && c < p.Cout) ? p.shift[c] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     uint32_t it = 0;
-    for (long long t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-      const int nt = (int)(t % p.n_tiles);
-      long long mt = t / p.n_tiles;
-      const int pw = (int)(mt % p.tiles_w); mt /= p.tiles_w;
-      const int ph = (int)(mt % p.tiles_h);
-      const int img = (int)(mt / p.tiles_h);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const int nt = t % p.n_tiles;
+      int mt = t / p.n_tiles;
+      const int pw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int ph = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
       const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
       const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo);
       const long long pix = ((long long)img * p.Ho + ho) * p.Wo + wo;
@@ -262,6 +282,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(bar_acc_full + 8 * buf, aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * (uint32_t)BN + ((uint32_t)(sub * 32) << 16);
+      const int nvalid = min(BN, p.Cout - n0);       // channels of this tile that exist
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -272,49 +293,59 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
         }
-        if (!row_ok) continue;
-        if (p.mode == RYOLO_OUT_NHWC_BF16) {
+        if (!row_ok || c0 >= nvalid) continue;
+        if (EPI == EPI_HEAD) {   // out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k
+          float* o = (float*)p.out;
+          const int cmax = min(32, nvalid - c0);
+          int c = n0 + c0;
+          int a = c / p.head_ch, k = c - a * p.head_ch;
+          float* op = o + ((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k;
+          const long long astride = (long long)p.Ho * p.Wo * p.head_ch;
+#pragma unroll 8
+          for (int j = 0; j < 32; j++) {
+            if (j < cmax) {
+              *op = __uint_as_float(v[j]) * s_aff[c0 + j] + s_aff[256 + c0 + j];
+              op++;
+              if (++k == p.head_ch) { k = 0; op += astride - p.head_ch; }
+            }
+          }
+        } else {
           __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
-          const __nv_bfloat16* res = p.residual ? p.residual + pix * p.res_cpitch + n0 + c0 : nullptr;
+          const __nv_bfloat16* res = (EPI == EPI_AFFINE && p.residual) ? p.residual + pix * p.res_cpitch + n0 + c0
+                                                                       : nullptr;
+          const int ng = min(4, (nvalid - c0) >> 3);   // Cout is a multiple of 8
 #pragma unroll
           for (int g = 0; g < 4; g++) {
-            const int c = n0 + c0 + 8 * g;
-            if (c >= p.Cout) break;
-            float f[8];
+            if (g < ng) {
+              float f[8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-              float x = __uint_as_float(v[8 * g + j]);
-              if (p.scale) x = x * __ldg(p.scale + c + j);
-              if (p.shift) x = x + __ldg(p.shift + c + j);
-              f[j] = act_apply(x, p.act);
-            }
-            if (res) {
-              const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
-              const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[8 * g + j]);
+              if (EPI == EPI_AFFINE) {
+                const float4 s0 = *reinterpret_cast<const float4*>(&s_aff[c0 + 8 * g]);
+                const float4 s1 = *reinterpret_cast<const float4*>(&s_aff[c0 + 8 * g + 4]);
+                const float4 b0 = *reinterpret_cast<const float4*>(&s_aff[256 + c0 + 8 * g]);
+                const float4 b1 = *reinterpret_cast<const float4*>(&s_aff[256 + c0 + 8 * g + 4]);
+                f[0] = act_apply(f[0] * s0.x + b0.x, ACT); f[1] = act_apply(f[1] * s0.y + b0.y, ACT);
+                f[2] = act_apply(f[2] * s0.z + b0.z, ACT); f[3] = act_apply(f[3] * s0.w + b0.w, ACT);
+                f[4] = act_apply(f[4] * s1.x + b1.x, ACT); f[5] = act_apply(f[5] * s1.y + b1.y, ACT);
+                f[6] = act_apply(f[6] * s1.z + b1.z, ACT); f[7] = act_apply(f[7] * s1.w + b1.w, ACT);
+                if (res) {
+                  const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
+                  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
-              for (int j = 0; j < 4; j++) {
-                const float2 tt = __bfloat1622float2(rb[j]);
-                f[2 * j] += tt.x;
-                f[2 * j + 1] += tt.y;
+                  for (int j = 0; j < 4; j++) {
+                    const float2 tt = __bfloat1622float2(rb[j]);
+                    f[2 * j] += tt.x;
+                    f[2 * j + 1] += tt.y;
+                  }
+                }
               }
-            }
-            uint4 pk;
-            __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+              uint4 pk;
+              __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
-            for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            *reinterpret_cast<uint4*>(o + 8 * g) = pk;
-          }
-        } else {  // RYOLO_OUT_HEAD_F32: out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k
-          float* o = (float*)p.out;
-#pragma unroll 4
-          for (int j = 0; j < 32; j++) {
-            const int c = n0 + c0 + j;
-            if (c >= p.Cout) break;
-            float x = __uint_as_float(v[j]);
-            if (p.scale) x = x * __ldg(p.scale + c);
-            if (p.shift) x = x + __ldg(p.shift + c);
-            const int a = c / p.head_ch, k = c - a * p.head_ch;
-            o[((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k] = act_apply(x, p.act);
+              for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+            }
           }
         }
       }
@@ -449,20 +480,34 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvKernelParams);
+  KernelFn fn = nullptr;
+  const bool affine = p.scale || p.shift || p.act != RYOLO_ACT_LINEAR || p.residual;
+  if (p.mode == RYOLO_OUT_HEAD_F32) fn = conv_fwd_kernel<EPI_HEAD, 0>;
+  else if (!affine) fn = conv_fwd_kernel<EPI_RAW, 0>;
+  else if (p.act == RYOLO_ACT_LEAKY) fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY>;
+  else if (p.act == RYOLO_ACT_MISH) fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH>;
+  else if (p.act == RYOLO_ACT_SWISH) fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH>;
+  else fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBudget);
-    if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
+    KernelFn all[6] = {conv_fwd_kernel<EPI_HEAD, 0>, conv_fwd_kernel<EPI_RAW, 0>,
+                       conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH>,
+                       conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR>};
+    for (KernelFn k : all) {
+      cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+      if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
+    }
     configured = true;
   }
   p.n_tiles = (p.Cout + p.BN - 1) / p.BN;
   const long long tiles = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
-  RY_CHECK_ARG(tiles > 0, "conv: empty problem");
+  RY_CHECK_ARG(tiles > 0 && tiles < (1ll << 31), "conv: tile count out of range");
+  RY_CHECK_ARG(p.n_tiles <= sm_count(), "conv: too many output-channel tiles");
   int grid = sm_count();
-  if (p.n_tiles > 1 && grid > p.n_tiles) grid -= grid % p.n_tiles;   // a CTA always sees the same n-tile
-  if (tiles < grid) grid = (int)tiles;
-  conv_fwd_kernel<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  grid -= grid % p.n_tiles;                          // a CTA always sees the same n-tile
+  if (tiles < grid) grid = (int)tiles;               // tiles is a multiple of n_tiles, so this keeps the property
+  fn<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }
