@@ -87,6 +87,19 @@ int ryolo_loss(int mode, const float* const* levels, float* const* grads, int64_
 enum { RYOLO_ACT_LINEAR = 0, RYOLO_ACT_LEAKY = 1, RYOLO_ACT_MISH = 2, RYOLO_ACT_SWISH = 3 };
 enum { RYOLO_OUT_NHWC_BF16 = 0, RYOLO_OUT_HEAD_F32 = 1 };
 
+/* Fused train-mode BatchNorm2d statistics (model/utils.py:16-17): the raw-output conv epilogue accumulates the
+ * per-channel sum / sum of squares of what it stores, and the last CTA to finish turns them into
+ * scale = gamma*rsqrt(var+eps), shift = beta-mean*scale, updates the running statistics (momentum, unbiased
+ * variance) and num_batches_tracked.  sum, sumsq (fp32[Cout]) and counter (u32) must be zero on entry.      */
+typedef struct ryolo_bn_fuse {
+  float* sum; float* sumsq; unsigned int* counter;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* num_batches;     /* nullable */
+  float eps, momentum;
+  float* scale; float* shift;                                           /* outputs fp32[Cout] */
+  float* save_mean; float* save_invstd;                                 /* nullable outputs */
+} ryolo_bn_fuse;
+
 typedef struct ryolo_conv_desc {
   const void* x;          /* bf16 NHWC input view                                   */
   int N, H, W, Cin;       /* Cin = channels of the view (multiple of 8)             */
@@ -102,6 +115,7 @@ typedef struct ryolo_conv_desc {
   const void* residual;   /* optional bf16 NHWC view added after the activation     */
   long long res_cpitch;
   int head_na, head_ch;   /* mode 1: Cout == head_na*head_ch                        */
+  const ryolo_bn_fuse* bn;/* optional (HOST pointer): fused BN statistics, raw epilogue only */
 } ryolo_conv_desc;
 
 /* model/utils.py:6-32 Conv (Conv2d + eval-folded BN + activation) / raw conv for train-mode BN.

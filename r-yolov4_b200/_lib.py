@@ -40,12 +40,19 @@ SIGNATURES = {
 _f32p, _dbl, _ll = ctypes.POINTER(_f32), ctypes.c_double, ctypes.c_longlong
 
 
+class BnFuse(ctypes.Structure):
+    """struct ryolo_bn_fuse (include/ryolo_b200.h)."""
+    _fields_ = [("sum", _vp), ("sumsq", _vp), ("counter", _vp), ("gamma", _vp), ("beta", _vp), ("running_mean", _vp),
+                ("running_var", _vp), ("num_batches", _vp), ("eps", _f32), ("momentum", _f32), ("scale", _vp),
+                ("shift", _vp), ("save_mean", _vp), ("save_invstd", _vp)]
+
+
 class ConvDesc(ctypes.Structure):
     """struct ryolo_conv_desc (include/ryolo_b200.h)."""
     _fields_ = [("x", _vp), ("N", _i32), ("H", _i32), ("W", _i32), ("Cin", _i32), ("x_cpitch", _ll), ("w", _vp),
                 ("Cout", _i32), ("ksize", _i32), ("stride", _i32), ("out", _vp), ("out_mode", _i32),
                 ("out_cpitch", _ll), ("scale", _vp), ("shift", _vp), ("act", _i32), ("residual", _vp),
-                ("res_cpitch", _ll), ("head_na", _i32), ("head_ch", _i32)]
+                ("res_cpitch", _ll), ("head_na", _i32), ("head_ch", _i32), ("bn", ctypes.POINTER(BnFuse))]
 
 
 SIGNATURES.update({

@@ -144,6 +144,8 @@ struct ConvKernelParams {
   const __nv_bfloat16* residual;
   long long res_cpitch;
   int head_na, head_ch;
+  ryolo_bn_fuse bn;        // bn.sum != nullptr: fused train-mode BatchNorm statistics + finalize (EPI_RAW only)
+  double bn_count;         // N*Ho*Wo
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -179,6 +181,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int KB = taps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   __shared__ __align__(16) float s_aff[2 * 256];           // scale | shift of this CTA's n-tile (EPI_AFFINE / EPI_HEAD)
+  __shared__ float s_tr[4 * 32 * 33];                      // per-warp 32x32 transpose tile (BN statistics, head stores)
+  __shared__ int s_last;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
@@ -268,6 +272,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    const bool do_stats = (EPI == EPI_RAW) && (p.bn.sum != nullptr);
+    float st_s[8], st_q[8];                  // per-lane channel partial sums, one slot per 32-channel chunk
+#pragma unroll
+    for (int i = 0; i < 8; i++) { st_s[i] = 0.f; st_q[i] = 0.f; }
+    float* tw = s_tr + sub * (32 * 33);
     uint32_t it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
       const int nt = t % p.n_tiles;
@@ -283,69 +292,135 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * (uint32_t)BN + ((uint32_t)(sub * 32) << 16);
       const int nvalid = min(BN, p.Cout - n0);       // channels of this tile that exist
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(t_row + (uint32_t)c0, v);
-        tmem_ld_wait();
-        if (c0 + 32 >= BN) {                 // last chunk is in registers: hand the accumulator back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
-        }
-        if (!row_ok || c0 >= nvalid) continue;
-        if (EPI == EPI_HEAD) {   // out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k
-          float* o = (float*)p.out;
-          const int cmax = min(32, nvalid - c0);
-          int c = n0 + c0;
-          int a = c / p.head_ch, k = c - a * p.head_ch;
-          float* op = o + ((((long long)img * p.head_na + a) * p.Ho + ho) * p.Wo + wo) * p.head_ch + k;
-          const long long astride = (long long)p.Ho * p.Wo * p.head_ch;
-#pragma unroll 8
-          for (int j = 0; j < 32; j++) {
-            if (j < cmax) {
-              *op = __uint_as_float(v[j]) * s_aff[c0 + j] + s_aff[256 + c0 + j];
-              op++;
-              if (++k == p.head_ch) { k = 0; op += astride - p.head_ch; }
-            }
+      // head layout: row base (anchor 0) of this lane's pixel, broadcast by shuffle when storing
+      const long long head_row = (((long long)img * p.head_na * p.Ho + ho) * p.Wo + wo) * p.head_ch;
+      const unsigned ok_mask = __ballot_sync(0xffffffffu, row_ok);
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) {
+        const int c0 = ci * 32;
+        if (c0 < BN) {
+          uint32_t v[32];
+          tmem_ld32(t_row + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (c0 + 32 >= BN) {               // last chunk is in registers: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc_empty + 8 * buf);
           }
-        } else {
-          __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
-          const __nv_bfloat16* res = (EPI == EPI_AFFINE && p.residual) ? p.residual + pix * p.res_cpitch + n0 + c0
-                                                                       : nullptr;
-          const int ng = min(4, (nvalid - c0) >> 3);   // Cout is a multiple of 8
+          if (c0 < nvalid) {
+            if (EPI == EPI_HEAD) {
+              // out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k.  Transpose through smem so that
+              // the 32 lanes of a warp write 32 consecutive channels of one pixel (128-byte coalesced stores).
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            if (g < ng) {
-              float f[8];
+              for (int j = 0; j < 32; j++)
+                tw[lane * 33 + j] = __uint_as_float(v[j]) * s_aff[c0 + j] + s_aff[256 + c0 + j];
+              __syncwarp();
+              const int c = n0 + c0 + lane;
+              const int a = c / p.head_ch, k = c - a * p.head_ch;
+              const long long coff = (long long)a * p.Ho * p.Wo * p.head_ch + k;
+              const bool c_ok = (c0 + lane) < nvalid;
+              float* o = (float*)p.out;
+#pragma unroll 4
+              for (int rr = 0; rr < 32; rr++) {
+                const long long rb = __shfl_sync(0xffffffffu, head_row, rr);
+                if (((ok_mask >> rr) & 1u) && c_ok) o[rb + coff] = tw[rr * 33 + lane];
+              }
+              __syncwarp();
+            } else {
+              __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
+              const __nv_bfloat16* res = (EPI == EPI_AFFINE && p.residual)
+                                             ? p.residual + pix * p.res_cpitch + n0 + c0 : nullptr;
+              const int ng = min(4, (nvalid - c0) >> 3);   // Cout is a multiple of 8
 #pragma unroll
-              for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[8 * g + j]);
-              if (EPI == EPI_AFFINE) {
-                const float4 s0 = *reinterpret_cast<const float4*>(&s_aff[c0 + 8 * g]);
-                const float4 s1 = *reinterpret_cast<const float4*>(&s_aff[c0 + 8 * g + 4]);
-                const float4 b0 = *reinterpret_cast<const float4*>(&s_aff[256 + c0 + 8 * g]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&s_aff[256 + c0 + 8 * g + 4]);
-                f[0] = act_apply(f[0] * s0.x + b0.x, ACT); f[1] = act_apply(f[1] * s0.y + b0.y, ACT);
-                f[2] = act_apply(f[2] * s0.z + b0.z, ACT); f[3] = act_apply(f[3] * s0.w + b0.w, ACT);
-                f[4] = act_apply(f[4] * s1.x + b1.x, ACT); f[5] = act_apply(f[5] * s1.y + b1.y, ACT);
-                f[6] = act_apply(f[6] * s1.z + b1.z, ACT); f[7] = act_apply(f[7] * s1.w + b1.w, ACT);
-                if (res) {
-                  const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
-                  const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+              for (int g = 0; g < 4; g++) {
+                float f[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) f[j] = __uint_as_float(v[8 * g + j]);
+                if (EPI == EPI_AFFINE) {
+                  const float4 s0 = *reinterpret_cast<const float4*>(&s_aff[c0 + 8 * g]);
+                  const float4 s1 = *reinterpret_cast<const float4*>(&s_aff[c0 + 8 * g + 4]);
+                  const float4 b0 = *reinterpret_cast<const float4*>(&s_aff[256 + c0 + 8 * g]);
+                  const float4 b1 = *reinterpret_cast<const float4*>(&s_aff[256 + c0 + 8 * g + 4]);
+                  f[0] = act_apply(f[0] * s0.x + b0.x, ACT); f[1] = act_apply(f[1] * s0.y + b0.y, ACT);
+                  f[2] = act_apply(f[2] * s0.z + b0.z, ACT); f[3] = act_apply(f[3] * s0.w + b0.w, ACT);
+                  f[4] = act_apply(f[4] * s1.x + b1.x, ACT); f[5] = act_apply(f[5] * s1.y + b1.y, ACT);
+                  f[6] = act_apply(f[6] * s1.z + b1.z, ACT); f[7] = act_apply(f[7] * s1.w + b1.w, ACT);
+                  if (res && row_ok && g < ng) {
+                    const uint4 rv = *reinterpret_cast<const uint4*>(res + 8 * g);
+                    const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                      const float2 tt = __bfloat1622float2(rb[j]);
+                      f[2 * j] += tt.x;
+                      f[2 * j + 1] += tt.y;
+                    }
+                  }
+                }
+                uint4 pk;
+                __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+                if (row_ok && g < ng) *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+                if (do_stats) {              // statistics of the values as stored (bf16-rounded)
+                  const bool live = row_ok && g < ng;
 #pragma unroll
                   for (int j = 0; j < 4; j++) {
-                    const float2 tt = __bfloat1622float2(rb[j]);
-                    f[2 * j] += tt.x;
-                    f[2 * j + 1] += tt.y;
+                    const float2 tt = __bfloat1622float2(pb[j]);
+                    tw[lane * 33 + 8 * g + 2 * j] = live ? tt.x : 0.f;
+                    tw[lane * 33 + 8 * g + 2 * j + 1] = live ? tt.y : 0.f;
                   }
                 }
               }
-              uint4 pk;
-              __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-              for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+              if (do_stats) {
+                __syncwarp();
+                float a = 0.f, b = 0.f;
+#pragma unroll 8
+                for (int rr = 0; rr < 32; rr++) {
+                  const float x = tw[rr * 33 + lane];
+                  a += x;
+                  b += x * x;
+                }
+                st_s[ci] += a;
+                st_q[ci] += b;
+                __syncwarp();
+              }
             }
+          }
+        }
+      }
+    }
+    if (do_stats) {
+      // flush this CTA's partial sums; the last CTA to arrive turns them into scale/shift + running stats
+      const int n0c = (blockIdx.x % p.n_tiles) * BN;
+#pragma unroll
+      for (int ci = 0; ci < 8; ci++) {
+        const int c = n0c + ci * 32 + lane;
+        if (ci * 32 < BN && c < p.Cout) {
+          atomicAdd(p.bn.sum + c, st_s[ci]);
+          atomicAdd(p.bn.sumsq + c, st_q[ci]);
+        }
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et == 0) s_last = (atomicAdd(p.bn.counter, 1u) == gridDim.x - 1) ? 1 : 0;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (s_last) {
+        __threadfence();
+        if (et == 0 && p.bn.num_batches) *p.bn.num_batches += 1;
+        for (int c = et; c < p.Cout; c += 128) {
+          const double mean = (double)__ldcg(p.bn.sum + c) / p.bn_count;
+          double var = (double)__ldcg(p.bn.sumsq + c) / p.bn_count - mean * mean;
+          if (var < 0.0) var = 0.0;
+          const float invstd = (float)(1.0 / sqrt(var + (double)p.bn.eps));
+          const float sc = p.bn.gamma[c] * invstd;
+          p.bn.scale[c] = sc;
+          p.bn.shift[c] = p.bn.beta[c] - (float)mean * sc;
+          if (p.bn.save_mean) p.bn.save_mean[c] = (float)mean;
+          if (p.bn.save_invstd) p.bn.save_invstd[c] = invstd;
+          if (p.bn.running_mean) {
+            const double unbiased = p.bn_count > 1.0 ? var * p.bn_count / (p.bn_count - 1.0) : var;
+            p.bn.running_mean[c] = (1.f - p.bn.momentum) * p.bn.running_mean[c] + p.bn.momentum * (float)mean;
+            p.bn.running_var[c] = (1.f - p.bn.momentum) * p.bn.running_var[c] + p.bn.momentum * (float)unbiased;
           }
         }
       }
@@ -442,6 +517,13 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   p->scale = d->scale; p->shift = d->shift;
   p->residual = (const __nv_bfloat16*)d->residual; p->res_cpitch = d->res_cpitch;
   p->head_na = d->head_na; p->head_ch = d->head_ch;
+  if (d->bn) {
+    RY_CHECK_ARG(d->out_mode == RYOLO_OUT_NHWC_BF16 && !d->scale && !d->shift && d->act == RYOLO_ACT_LINEAR &&
+                     !d->residual, "conv: fused BatchNorm statistics need the raw (no scale/shift/act/residual) epilogue");
+    RY_CHECK_ARG(d->bn->sum && d->bn->sumsq && d->bn->counter && d->bn->gamma && d->bn->beta && d->bn->scale &&
+                     d->bn->shift, "conv: incomplete ryolo_bn_fuse");
+    p->bn = *d->bn;
+  }
   if (d->out_mode == RYOLO_OUT_NHWC_BF16) {
     RY_CHECK_ARG(d->Cout % 8 == 0 && d->out_cpitch % 8 == 0 && (((uintptr_t)d->out) & 15) == 0,
                  "conv: bf16 output needs Cout and channel pitch multiples of 8 and a 16-byte aligned pointer");
@@ -455,6 +537,7 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   pick_patch(p->Ho, p->Wo, d->stride, &p->TH, &p->TW);
   p->tiles_h = (p->Ho + p->TH - 1) / p->TH;
   p->tiles_w = (p->Wo + p->TW - 1) / p->TW;
+  p->bn_count = (double)p->N * p->Ho * p->Wo;
   return RYOLO_OK;
 }
 
@@ -469,7 +552,7 @@ int sm_count() {
   return n;
 }
 
-constexpr size_t kSmemBudget = 200 * 1024;
+constexpr size_t kSmemBudget = 200 * 1024;   // dynamic; + ~21 KB static (transpose tile, scale/shift, barriers)
 
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, cudaStream_t st) {
   const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;

@@ -101,42 +101,76 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sum, const float* _
 }
 
 // y = act(x*scale + shift) (+ x2*scale2 + shift2 before the activation) (+ residual after it)
+// Thread layout: (C/8 channel groups) x rows; a thread keeps the scale/shift of its 8 channels in registers and
+// walks pixels, four independent 128-bit loads in flight.
+template <int ACT, bool HAS_X2, bool HAS_RES>
 __global__ void __launch_bounds__(256)
 scale_shift_act_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
                        const float* __restrict__ shift, const __nv_bfloat16* __restrict__ x2, long long x2p,
-                       const float* __restrict__ scale2, const float* __restrict__ shift2, int act,
+                       const float* __restrict__ scale2, const float* __restrict__ shift2,
                        const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
                        long long P, int C) {
   const int groups = C >> 3;
-  const long long total = P * groups;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long pix = i / groups;
-    const int c = (int)(i - pix * groups) * 8;
-    float f[8];
-    unpack8(*reinterpret_cast<const uint4*>(x + pix * xp + c), f);
-    const float4 s0 = *reinterpret_cast<const float4*>(scale + c), s1 = *reinterpret_cast<const float4*>(scale + c + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(shift + c), b1 = *reinterpret_cast<const float4*>(shift + c + 4);
-    const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-    const float sh[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (r >= rows) return;
+  const int c = 8 * g;
+  float sc[8], sh[8], sc2[8], sh2[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) f[j] = f[j] * sc[j] + sh[j];
-    if (x2) {
-      float h[8];
-      unpack8(*reinterpret_cast<const uint4*>(x2 + pix * x2p + c), h);
-#pragma unroll
-      for (int j = 0; j < 8; j++) f[j] += h[j] * scale2[c + j] + shift2[c + j];
-    }
-#pragma unroll
-    for (int j = 0; j < 8; j++) f[j] = act_apply(f[j], act);
-    if (res) {
-      float h[8];
-      unpack8(*reinterpret_cast<const uint4*>(res + pix * rp + c), h);
-#pragma unroll
-      for (int j = 0; j < 8; j++) f[j] += h[j];
-    }
-    *reinterpret_cast<uint4*>(y + pix * yp + c) = pack8(f);
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c + j];
+    sh[j] = shift[c + j];
+    if (HAS_X2) { sc2[j] = scale2[c + j]; sh2[j] = shift2[c + j]; }
   }
+  const long long stride = (long long)gridDim.x * rows;
+  constexpr int U = 4;
+  for (long long pix0 = (long long)blockIdx.x * rows + r; pix0 < P; pix0 += U * stride) {
+    uint4 vx[U], v2[U], vr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long pix = pix0 + u * stride;
+      if (pix < P) {
+        vx[u] = *reinterpret_cast<const uint4*>(x + pix * xp + c);
+        if (HAS_X2) v2[u] = *reinterpret_cast<const uint4*>(x2 + pix * x2p + c);
+        if (HAS_RES) vr[u] = *reinterpret_cast<const uint4*>(res + pix * rp + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const long long pix = pix0 + u * stride;
+      if (pix < P) {
+        float f[8];
+        unpack8(vx[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = f[j] * sc[j] + sh[j];
+        if (HAS_X2) {
+          float h[8];
+          unpack8(v2[u], h);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] += h[j] * sc2[j] + sh2[j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = act_apply(f[j], ACT);
+        if (HAS_RES) {
+          float h[8];
+          unpack8(vr[u], h);
+#pragma unroll
+          for (int j = 0; j < 8; j++) f[j] += h[j];
+        }
+        *reinterpret_cast<uint4*>(y + pix * yp + c) = pack8(f);
+      }
+    }
+  }
+}
+
+typedef void (*SsaFn)(const __nv_bfloat16*, long long, const float*, const float*, const __nv_bfloat16*, long long,
+                      const float*, const float*, const __nv_bfloat16*, long long, __nv_bfloat16*, long long, long long,
+                      int);
+
+template <int ACT>
+SsaFn ssa_pick(bool x2, bool res) {
+  if (x2) return res ? scale_shift_act_kernel<ACT, true, true> : scale_shift_act_kernel<ACT, true, false>;
+  return res ? scale_shift_act_kernel<ACT, false, true> : scale_shift_act_kernel<ACT, false, false>;
 }
 
 // ------------------------------------------------------------------------------------ pooling / resize / copy
@@ -284,11 +318,25 @@ int ryolo_bn_finalize(const float* sum, const float* sumsq, double count, int C,
 int ryolo_scale_shift_act(const void* x, long long xp, const float* scale, const float* shift, const void* x2,
                           long long x2p, const float* scale2, const float* shift2, int act, const void* residual,
                           long long rp, void* y, long long yp, long long P, int C, void* stream) {
-  RY_CHECK_ARG(C % 8 == 0 && xp % 8 == 0 && yp % 8 == 0, "scale_shift_act: channels must be multiples of 8");
+  RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && xp % 8 == 0 && yp % 8 == 0,
+               "scale_shift_act: channels must be a multiple of 8 in [8, 2048]");
+  RY_CHECK_ARG(scale && shift && (!x2 || (scale2 && shift2)), "scale_shift_act: missing scale/shift");
   if (P == 0) return RYOLO_OK;
-  scale_shift_act_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, xp, scale, shift, (const __nv_bfloat16*)x2, x2p, scale2, shift2, act,
-      (const __nv_bfloat16*)residual, rp, (__nv_bfloat16*)y, yp, P, C);
+  SsaFn fn;
+  switch (act) {
+    case RYOLO_ACT_LEAKY: fn = ssa_pick<RYOLO_ACT_LEAKY>(x2 != nullptr, residual != nullptr); break;
+    case RYOLO_ACT_MISH: fn = ssa_pick<RYOLO_ACT_MISH>(x2 != nullptr, residual != nullptr); break;
+    case RYOLO_ACT_SWISH: fn = ssa_pick<RYOLO_ACT_SWISH>(x2 != nullptr, residual != nullptr); break;
+    default: fn = ssa_pick<RYOLO_ACT_LINEAR>(x2 != nullptr, residual != nullptr); break;
+  }
+  const int groups = C / 8;
+  const int threads = groups >= 256 ? groups : 256;
+  const int rows = threads / groups;
+  long long want = (P + (long long)rows * 4 - 1) / ((long long)rows * 4);
+  const int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  fn<<<blocks, threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, xp, scale, shift, (const __nv_bfloat16*)x2,
+                                                   x2p, scale2, shift2, (const __nv_bfloat16*)residual, rp,
+                                                   (__nv_bfloat16*)y, yp, P, C);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -27,7 +27,8 @@ class Ctx:
         self.tape = [] if training else None
         n = model._bn_channels
         self._stats = torch.zeros(2 * n, dtype=torch.float32, device=device) if training else None
-        self._stat_off = 0
+        self._counters = torch.zeros(model._bn_layers, dtype=torch.int32, device=device) if training else None
+        self._stat_off, self._ctr_off = 0, 0
 
     def new(self, N, H, W, C):
         return Act.empty(N, H, W, C, self.device)
@@ -36,7 +37,9 @@ class Ctx:
         s = self._stats[self._stat_off:self._stat_off + C]
         q = self._stats[self._stat_off + C:self._stat_off + 2 * C]
         self._stat_off += 2 * C
-        return s, q
+        ctr = self._counters[self._ctr_off:self._ctr_off + 1]
+        self._ctr_off += 1
+        return s, q, ctr
 
 
 class _Packed:
@@ -96,14 +99,11 @@ class Conv(nn.Module):
             scale, shift = _bn_eval_affine(bn, self._affine)
             return ops.conv2d(x, w, self.c2, k, self.s, out=out, scale=scale, shift=shift, act=self.act,
                               residual=residual)
-        raw = ops.conv2d(x, w, self.c2, k, self.s)
-        s, q = ctx.stat_slot(self.c2)
-        ops.bn_stats(raw, s, q)
+        s, q, ctr = ctx.stat_slot(self.c2)
         aff = torch.empty(4 * self.c2, dtype=torch.float32, device=ctx.device)
         scale, shift, mean, invstd = aff[:self.c2], aff[self.c2:2 * self.c2], aff[2 * self.c2:3 * self.c2], \
             aff[3 * self.c2:]
-        ops.bn_finalize(s, q, raw.P, bn.weight.data, bn.bias.data, bn.eps, bn.momentum, bn.running_mean,
-                        bn.running_var, bn.num_batches_tracked, scale, shift, mean, invstd)
+        raw = ops.conv2d(x, w, self.c2, k, self.s, bn=ops.bn_fuse(s, q, ctr, bn, scale, shift, mean, invstd))
         if out is None:
             out = ctx.new(raw.N, raw.H, raw.W, self.c2)
         ops.scale_shift_act(raw, scale, shift, self.act, out, residual=residual)
@@ -180,11 +180,13 @@ class SPP(nn.Module):
         cat = ctx.new(x.N, x.H, x.W, 4 * c_)                      # order m3, m2, m1, x  (model/utils.py:241)
         src = cat.slice(3 * c_, c_)
         self.cv3(ctx, self.cv2(ctx, self.cv1(ctx, x)), out=src)
-        for i, k in enumerate((13, 9, 5)):
+        # pool9 = pool5(pool5), pool13 = pool5(pool9): exact for max with -inf padding, 3.7x fewer loads
+        for i in (2, 1, 0):
             dst = cat.slice(i * c_, c_)
-            ops.maxpool(src, k, 1, k // 2, out=dst)
+            ops.maxpool(src, 5, 1, 2, out=dst)
             if ctx.tape is not None:
-                ctx.tape.append(("maxpool", src, dst, k, 1, k // 2))
+                ctx.tape.append(("maxpool", src, dst, 5, 1, 2))
+            src = dst
         return self.cv6(ctx, self.cv5(ctx, self.cv4(ctx, cat)), out=out)
 
 
@@ -207,11 +209,13 @@ class SPPCSPC(nn.Module):
         cat4 = ctx.new(x.N, x.H, x.W, 4 * c_)                     # order x1, m5, m9, m13 (model/utils.py:279)
         src = cat4.slice(0, c_)
         self.cv4(ctx, self.cv3(ctx, self.cv1(ctx, x)), out=src)
-        for i, k in enumerate(self.ks):
+        assert self.ks == (5, 9, 13)
+        for i in range(3):                                         # cascaded 5x5 pools (see SPP)
             dst = cat4.slice((i + 1) * c_, c_)
-            ops.maxpool(src, k, 1, k // 2, out=dst)
+            ops.maxpool(src, 5, 1, 2, out=dst)
             if ctx.tape is not None:
-                ctx.tape.append(("maxpool", src, dst, k, 1, k // 2))
+                ctx.tape.append(("maxpool", src, dst, 5, 1, 2))
+            src = dst
         cat2 = ctx.new(x.N, x.H, x.W, 2 * c_)
         self.cv6(ctx, self.cv5(ctx, cat4), out=cat2.slice(0, c_))
         self.cv2(ctx, x, out=cat2.slice(c_, c_))
@@ -319,20 +323,20 @@ class RepConv(nn.Module):
         wd, w1 = self._pd.get(self.rbr_dense[0].weight), self._p1.get(self.rbr_1x1[0].weight)
         if out is None:
             out = ctx.new(x.N, x.H, x.W, self.c2)
-        rd = ops.conv2d(x, wd, self.c2, self.k, self.s)
-        r1 = ops.conv2d(x, w1, self.c2, 1, self.s)
         if not ctx.training:
+            rd = ops.conv2d(x, wd, self.c2, self.k, self.s)
+            r1 = ops.conv2d(x, w1, self.c2, 1, self.s)
             sd, bd = _bn_eval_affine(self.rbr_dense[1], self._ad)
             s1, b1 = _bn_eval_affine(self.rbr_1x1[1], self._a1)
             return ops.scale_shift_act(rd, sd, bd, "swish", out, x2=r1, scale2=s1, shift2=b1)
-        affs = []
-        for raw, bn in ((rd, self.rbr_dense[1]), (r1, self.rbr_1x1[1])):
-            s, q = ctx.stat_slot(self.c2)
-            ops.bn_stats(raw, s, q)
+        affs, raws = [], []
+        for wgt, kk, bn in ((wd, self.k, self.rbr_dense[1]), (w1, 1, self.rbr_1x1[1])):
+            s, q, ctr = ctx.stat_slot(self.c2)
             aff = torch.empty(4, self.c2, dtype=torch.float32, device=ctx.device)
-            ops.bn_finalize(s, q, raw.P, bn.weight.data, bn.bias.data, bn.eps, bn.momentum, bn.running_mean,
-                            bn.running_var, bn.num_batches_tracked, aff[0], aff[1], aff[2], aff[3])
+            raws.append(ops.conv2d(x, wgt, self.c2, kk, self.s,
+                                   bn=ops.bn_fuse(s, q, ctr, bn, aff[0], aff[1], aff[2], aff[3])))
             affs.append(aff)
+        rd, r1 = raws
         ops.scale_shift_act(rd, affs[0][0], affs[0][1], "swish", out, x2=r1, scale2=affs[1][0], shift2=affs[1][1])
         ctx.tape.append(("repconv", self, x, rd, r1, out, affs))
         return out

@@ -34,6 +34,7 @@ class Yolo(nn.Module):
         self.neck = families[ver][1](self.na * self.ch)
         self.yolo = layer
         self._bn_channels = sum(m.num_features for m in self.modules() if isinstance(m, nn.BatchNorm2d))
+        self._bn_layers = sum(1 for m in self.modules() if isinstance(m, nn.BatchNorm2d))
         self.last_ctx = None
 
     def forward(self, i, training):

@@ -76,8 +76,22 @@ def out_hw(H, W, k, s):
     return (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
 
 
+def bn_fuse(sum_, sumsq, counter, bn, scale, shift, save_mean=None, save_invstd=None):
+    """ryolo_bn_fuse for an nn.BatchNorm2d `bn` (fused statistics + finalize in the conv epilogue)."""
+    f = L.BnFuse()
+    f.sum, f.sumsq, f.counter = sum_.data_ptr(), sumsq.data_ptr(), counter.data_ptr()
+    f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
+    f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
+    f.num_batches = bn.num_batches_tracked.data_ptr()
+    f.eps, f.momentum = bn.eps, bn.momentum
+    f.scale, f.shift = scale.data_ptr(), shift.data_ptr()
+    f.save_mean = save_mean.data_ptr() if save_mean is not None else None
+    f.save_invstd = save_invstd.data_ptr() if save_invstd is not None else None
+    return f
+
+
 def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear", residual=None, head=None,
-           reference=False):
+           reference=False, bn=None):
     """x: Act; w: packed bf16 [Cout, k*k*Cin]; out: Act (bf16 NHWC) or, with head=(na, ch), an fp32
     [N, na, Ho, Wo, ch] tensor.  Returns out."""
     Ho, Wo = out_hw(x.H, x.W, k, stride)
@@ -102,6 +116,8 @@ def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear"
     d.act = ACT[act]
     if residual is not None:
         d.residual, d.res_cpitch = residual.ptr, residual.pitch
+    if bn is not None:
+        d.bn = ctypes.pointer(bn)
     fn = L.lib().ryolo_conv2d_reference if reference else L.lib().ryolo_conv2d_forward
     if PROFILE is not None:
         _prof_begin()
