@@ -9,8 +9,9 @@
 //                  element strides.  No im2col buffer ever exists.
 //   operands       bf16, K-major, 128-byte swizzle (TMA writes it, the UMMA descriptor reads it)
 //   pipeline       persistent CTAs (one per SM); warp 0: TMA producer | warp 1: TMEM alloc + single-thread MMA
-//                  issue into two alternating TMEM accumulators | warps 2-5: epilogue (tcgen05.ld -> scale/shift/
-//                  activation/residual -> global) overlapping the next tile's main loop; mbarrier smem ring
+//                  issue into two alternating TMEM accumulators | warps 2-5 / 6-9: two epilogue groups, one per
+//                  accumulator (tcgen05.ld -> scale/shift/activation/residual/BN statistics -> global) overlapping
+//                  the following tiles' main loops; mbarrier smem ring
 //   epilogue       mode 0: bf16 NHWC into a channel slice of a (concat) buffer; per-channel scale/shift =
 //                  folded BatchNorm (eval) or identity (train: raw conv output, BN statistics follow);
 //                  mode 1: fp32 head written directly in the reference's [B, na, gs, gs, ch] layout
@@ -24,7 +25,7 @@ namespace {
 
 constexpr int kBM = 128;        // UMMA M (rows of the patch tile, TH*TW <= 128)
 constexpr int kBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
-constexpr int kThreads = 192;   // 6 warps
+constexpr int kThreads = 320;   // 10 warps: TMA, MMA, 2 x 4 epilogue
 constexpr int kMaxStages = 12;
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -181,7 +182,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int KB = taps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   __shared__ __align__(16) float s_aff[2 * 256];           // scale | shift of this CTA's n-tile (EPI_AFFINE / EPI_HEAD)
-  __shared__ float s_tr[4 * 32 * 33];                      // per-warp 32x32 transpose tile (BN statistics, head stores)
+  __shared__ float s_tr[8 * 32 * 17];                      // per-warp 32x16-word transpose tile (BN statistics, head stores)
   __shared__ int s_last;
 
   if (warp == 0 && lane == 0) {
@@ -261,24 +262,25 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int sub = warp & 3;               // TMEM lanes [32*sub, 32*sub+32) are accessible to this warp
     const int r = sub * 32 + lane;          // accumulator row = pixel of the patch
     const int hl = r / p.TW, wl = r - hl * p.TW;
-    const int et = threadIdx.x - 64;        // 0..127
+    const int et = threadIdx.x - 64;        // 0..255
+    const uint32_t eg = (uint32_t)(warp - 2) >> 2;   // epilogue group 0|1 owns TMEM accumulator 0|1 (tiles it%2 == eg)
     if (EPI != EPI_RAW) {
       // every tile of this CTA has the same n-tile when n_tiles divides gridDim.x (host guarantees it)
       const int n0c = (blockIdx.x % p.n_tiles) * BN;
-      for (int i = et; i < BN; i += 128) {
+      for (int i = et; i < BN; i += 256) {
         const int c = n0c + i;
         s_aff[i] = (p.scale && c < p.Cout) ? p.scale[c] : 1.f;
         s_aff[256 + i] = (p.shift && c < p.Cout) ? p.shift[c] : 0.f;
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     const bool do_stats = (EPI == EPI_RAW) && (p.bn.sum != nullptr);
     float st_s[8], st_q[8];                  // per-lane channel partial sums, one slot per 32-channel chunk
 #pragma unroll
     for (int i = 0; i < 8; i++) { st_s[i] = 0.f; st_q[i] = 0.f; }
-    float* tw = s_tr + sub * (32 * 33);
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+    float* tw = s_tr + (warp - 2) * (32 * 17);
+    uint32_t it = eg;
+    for (int t = blockIdx.x + (int)eg * (int)gridDim.x; t < total_tiles; t += 2 * gridDim.x, it += 2) {
       const int nt = t % p.n_tiles;
       int mt = t / p.n_tiles;
       const int pw = mt % p.tiles_w; mt /= p.tiles_w;
@@ -311,21 +313,27 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             if (EPI == EPI_HEAD) {
               // out[((img*na + a)*Ho + ho)*Wo + wo][k], channel c = a*ch + k.  Transpose through smem so that
               // the 32 lanes of a warp write 32 consecutive channels of one pixel (128-byte coalesced stores).
-#pragma unroll
-              for (int j = 0; j < 32; j++)
-                tw[lane * 33 + j] = __uint_as_float(v[j]) * s_aff[c0 + j] + s_aff[256 + c0 + j];
-              __syncwarp();
-              const int c = n0 + c0 + lane;
-              const int a = c / p.head_ch, k = c - a * p.head_ch;
-              const long long coff = (long long)a * p.Ho * p.Wo * p.head_ch + k;
-              const bool c_ok = (c0 + lane) < nvalid;
               float* o = (float*)p.out;
+#pragma unroll
+              for (int h = 0; h < 2; h++) {      // 16 channels per pass: two pixels per store instruction
+#pragma unroll
+                for (int j = 0; j < 16; j++)
+                  tw[lane * 17 + j] = __uint_as_float(v[16 * h + j]) * s_aff[c0 + 16 * h + j] +
+                                      s_aff[256 + c0 + 16 * h + j];
+                __syncwarp();
+                const int cl = c0 + 16 * h + (lane & 15);
+                const int c = n0 + cl;
+                const int a = c / p.head_ch, k = c - a * p.head_ch;
+                const long long coff = (long long)a * p.Ho * p.Wo * p.head_ch + k;
+                const bool c_ok = cl < nvalid;
 #pragma unroll 4
-              for (int rr = 0; rr < 32; rr++) {
-                const long long rb = __shfl_sync(0xffffffffu, head_row, rr);
-                if (((ok_mask >> rr) & 1u) && c_ok) o[rb + coff] = tw[rr * 33 + lane];
+                for (int q = 0; q < 16; q++) {
+                  const int rr = 2 * q + (lane >> 4);
+                  const long long rb = __shfl_sync(0xffffffffu, head_row, rr);
+                  if (((ok_mask >> rr) & 1u) && c_ok) o[rb + coff] = tw[rr * 17 + (lane & 15)];
+                }
+                __syncwarp();
               }
-              __syncwarp();
             } else {
               __nv_bfloat16* o = (__nv_bfloat16*)p.out + pix * p.out_cpitch + n0 + c0;
               const __nv_bfloat16* res = (EPI == EPI_AFFINE && p.residual)
@@ -361,14 +369,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
                 for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
                 if (row_ok && g < ng) *reinterpret_cast<uint4*>(o + 8 * g) = pk;
-                if (do_stats) {              // statistics of the values as stored (bf16-rounded)
+                if (do_stats) {              // statistics of the values as stored (bf16-rounded, packed pairs)
                   const bool live = row_ok && g < ng;
-#pragma unroll
-                  for (int j = 0; j < 4; j++) {
-                    const float2 tt = __bfloat1622float2(pb[j]);
-                    tw[lane * 33 + 8 * g + 2 * j] = live ? tt.x : 0.f;
-                    tw[lane * 33 + 8 * g + 2 * j + 1] = live ? tt.y : 0.f;
-                  }
+                  uint32_t* tw32 = reinterpret_cast<uint32_t*>(tw) + lane * 17 + 4 * g;
+                  tw32[0] = live ? pk.x : 0u;
+                  tw32[1] = live ? pk.y : 0u;
+                  tw32[2] = live ? pk.z : 0u;
+                  tw32[3] = live ? pk.w : 0u;
                 }
               }
               if (do_stats) {
@@ -376,7 +383,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 float a = 0.f, b = 0.f;
 #pragma unroll 8
                 for (int rr = 0; rr < 32; rr++) {
-                  const float x = tw[rr * 33 + lane];
+                  const uint32_t w2 = reinterpret_cast<const uint32_t*>(tw)[rr * 17 + (lane >> 1)];
+                  const float x = __uint_as_float((lane & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
                   a += x;
                   b += x * x;
                 }
@@ -401,13 +409,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       __threadfence();
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0) s_last = (atomicAdd(p.bn.counter, 1u) == gridDim.x - 1) ? 1 : 0;
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      asm volatile("bar.sync 1, 256;" ::: "memory");
       if (s_last) {
         __threadfence();
         if (et == 0 && p.bn.num_batches) *p.bn.num_batches += 1;
-        for (int c = et; c < p.Cout; c += 128) {
+        for (int c = et; c < p.Cout; c += 256) {
           const double mean = (double)__ldcg(p.bn.sum + c) / p.bn_count;
           double var = (double)__ldcg(p.bn.sumsq + c) / p.bn_count - mean * mean;
           if (var < 0.0) var = 0.0;
@@ -552,7 +560,7 @@ int sm_count() {
   return n;
 }
 
-constexpr size_t kSmemBudget = 200 * 1024;   // dynamic; + ~21 KB static (transpose tile, scale/shift, barriers)
+constexpr size_t kSmemBudget = 204 * 1024;   // dynamic; + ~20 KB static (transpose tile, scale/shift, barriers)
 
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, cudaStream_t st) {
   const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
