@@ -121,6 +121,10 @@ typedef struct ryolo_conv_desc {
 /* model/utils.py:6-32 Conv (Conv2d + eval-folded BN + activation) / raw conv for train-mode BN.
  * tcgen05 implicit GEMM (csrc/conv.cu).                                                           */
 int ryolo_conv2d_forward(const ryolo_conv_desc* d, void* stream);
+/* Backward-data of the same Conv2d (autograd's conv backward at train.py:198): dx[N,H,W,Cin] (+)= conv^T(dy, w).
+ * dy bf16 NHWC view [N,Ho,Wo,Cout]; wt bf16 [Cin][kh][kw][Cout] (ryolo_pack_weights, layout 2).           */
+int ryolo_conv2d_dgrad(const void* dy, long long dy_cpitch, int N, int H, int W, int Cin, int Cout, int ksize,
+                       int stride, const void* wt, void* dx, long long dx_cpitch, int accumulate, void* stream);
 /* same contract on CUDA cores: device-side checker for the tensor-core path, never a fallback     */
 int ryolo_conv2d_reference(const ryolo_conv_desc* d, void* stream);
 
@@ -146,8 +150,38 @@ int ryolo_resize_copy(const void* x, long long xp, int N, int H, int W, int C, i
                       void* stream);
 /* fp32 NCHW image [N,3,H,W] -> bf16 [N,H,W,64] 3x3 patches (27 taps + zero pad) for the stem conv       */
 int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stream);
-/* state-dict OIHW fp32 -> bf16 [Cout][kh][kw][Cin]; stem != 0 -> [Cout][64] in the im2col channel order  */
+/* state-dict OIHW fp32 -> bf16: layout 0 [Cout][kh][kw][Cin]; 1 (stem) [Cout][64] in the im2col channel
+ * order; 2 (dgrad) [Cin][kh][kw][Cout]                                                                     */
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream);
+
+/* ---- conv stack backward (autograd's backward of the reference, train.py:198) ------------------------------
+ * dw (fp32 OIHW [Cout][Cin][k][k]; stem != 0: [Cout][3][3][3] with x = the 64-channel im2col tensor) +=
+ * conv_backward_weight(x, dy).  x bf16 NHWC view [N,H,W,Cin]; dy bf16 NHWC view [N,Ho,Wo,Cdy], Cdy >= Cout.
+ * tcgen05 GEMM over pixels with MN-major operands, split-K across CTAs, fp32 atomics into dw (csrc/wgrad.cu). */
+int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
+                       long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, int stem, float* dw,
+                       void* stream);
+/* d raw = backward of act(BatchNorm2d_train(raw)) given d out; also d gamma, d beta (fp32[C], nullable).
+ * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.                   */
+int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long rp, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
+                     float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream);
+/* dst (+)= src on bf16 NHWC views (gradient fan-in: residuals, concat slices, multiple consumers)            */
+int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, long long P, int C, int accumulate,
+                   void* stream);
+/* nn.MaxPool2d backward: dx += route(dy) (first maximum of each window); dx must hold valid numbers          */
+int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp, int N, int H, int W, int C, int k,
+                      int stride, int pad, void* dx, long long dxp, void* stream);
+/* nearest x2 upsample backward: dx[N,H,W,C] (+)= 2x2 block sums of dy[N,2H,2W,C]                             */
+int ryolo_upsample2x_bwd(const void* dy, long long dyp, int N, int H, int W, int C, void* dx, long long dxp,
+                         int accumulate, void* stream);
+/* loss gradient fp32 [B,na,H,W,ch] -> bf16 NHWC [B,H,W,Cpad] (x mul[c] if given) + dbias[c] += column sums    */
+int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch, int Cpad, const float* mul, void* out,
+                         float* dbias, void* stream);
+/* torch.optim.SGD step (train.py:156: momentum, nesterov) on flat fp32 buffers:
+ *   g = grad + wd*p;  buf = first ? g : momentum*buf + g;  p -= lr * (nesterov ? g + momentum*buf : buf)      */
+int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, float lr, float momentum,
+                   float weight_decay, int nesterov, int first, void* stream);
 
 #ifdef __cplusplus
 }

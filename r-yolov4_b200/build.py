@@ -24,7 +24,7 @@ SOURCES = {
     "decode.cu": ["--fmad=false"],
     "loss.cu": ["--fmad=false"],
 }
-for _opt in ("conv.cu", "elementwise.cu", "optim.cu"):
+for _opt in ("conv.cu", "elementwise.cu", "wgrad.cu", "backward.cu"):
     if os.path.exists(os.path.join(CSRC, _opt)):
         SOURCES[_opt] = []
 

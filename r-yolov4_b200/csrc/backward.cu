@@ -1,0 +1,400 @@
+// HBM-bound backward companions of the conv stack on NHWC bf16 views (the BatchNorm / activation / pooling /
+// upsample / concat halves of autograd's backward at train.py:198):
+//   bn_act_bwd_reduce / bn_act_bwd_apply   d(act(BN_train(raw))) -> d raw, d gamma, d beta      model/utils.py:16-23
+//   add_into                               gradient accumulation across consumers (residuals, fan-out, concat)
+//   maxpool_bwd                            nn.MaxPool2d backward (first maximum in window scan order wins)
+//   upsample2x_bwd                         nearest x2 upsample backward (sum over the 2x2 block)
+//   head_grad_pack                         fp32 [B,na,gs,gs,ch] head gradient -> bf16 NHWC [B,gs,gs,Cpad] + bias grad
+#include "common.cuh"
+#include "ryolo_b200.h"
+#include <cuda_bf16.h>
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* b = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const float2 t = __bfloat1622float2(b[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return v;
+}
+
+// derivative of the activation at pre-activation value y
+template <int ACT>
+__device__ __forceinline__ float act_grad(float y) {
+  if (ACT == RYOLO_ACT_LEAKY) return y > 0.f ? 1.f : 0.1f;
+  if (ACT == RYOLO_ACT_MISH) {           // f = y*t, t = tanh(softplus(y)) = n/(n+2), n = e^y(e^y+2)
+    if (y > 20.f) return 1.f;
+    const float e = __expf(y);
+    const float n = e * (e + 2.f);
+    const float t = __fdividef(n, n + 2.f);
+    const float sg = __fdividef(e, 1.f + e);
+    return t + y * (1.f - t * t) * sg;
+  }
+  if (ACT == RYOLO_ACT_SWISH) {
+    const float sg = __fdividef(1.f, 1.f + __expf(-y));
+    return sg * (1.f + y * (1.f - sg));
+  }
+  return 1.f;
+}
+
+// Pass 1: per-channel  s1 = sum dY,  s2 = sum dY * xhat   with dY = dOut * act'(raw*scale+shift),
+// xhat = (raw - mean) * invstd.  sums = [s1 | s2] (fp32[2C], zeroed by the caller).
+template <int ACT>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                         long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
+                         float* __restrict__ sums) {
+  extern __shared__ float red[];   // [rows][C] x 2
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int c = 8 * g;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < rows) {
+    float sc[8], sh[8], mu[8], is[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j]; }
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long pix0 = (long long)blockIdx.x * rows + r; pix0 < P; pix0 += 2 * stride) {
+      uint4 vd[2], vr[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const long long pix = pix0 + u * stride;
+        if (pix < P) {
+          vd[u] = *reinterpret_cast<const uint4*>(dout + pix * dp + c);
+          vr[u] = *reinterpret_cast<const uint4*>(raw + pix * rp + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const long long pix = pix0 + u * stride;
+        if (pix < P) {
+          float d[8], x[8];
+          unpack8(vd[u], d);
+          unpack8(vr[u], x);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const float dy = d[j] * act_grad<ACT>(x[j] * sc[j] + sh[j]);
+            s1[j] += dy;
+            s2[j] += dy * (x[j] - mu[j]) * is[j];
+          }
+        }
+      }
+    }
+  }
+  float* r1 = red;
+  float* r2 = red + (size_t)rows * C;
+  if (r < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { r1[r * C + c + j] = s1[j]; r2[r * C + c + j] = s2[j]; }
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; rr++) { a += r1[rr * C + cc]; b += r2[rr * C + cc]; }
+    atomicAdd(sums + cc, a);
+    atomicAdd(sums + C + cc, b);
+  }
+}
+
+// Pass 2: d raw = scale * (dY - s1/P - xhat * s2/P);  block 0 also emits d gamma = s2, d beta = s1.
+template <int ACT>
+__global__ void __launch_bounds__(256)
+bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                        long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd,
+                        const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
+                        long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (blockIdx.x == 0) {
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      if (dbeta) dbeta[cc] = sums[cc];
+      if (dgamma) dgamma[cc] = sums[C + cc];
+    }
+  }
+  if (r >= rows) return;
+  const int c = 8 * g;
+  const float invP = 1.f / (float)P;
+  float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j];
+    m1[j] = sums[c + j] * invP; m2[j] = sums[C + c + j] * invP;
+  }
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long pix0 = (long long)blockIdx.x * rows + r; pix0 < P; pix0 += 2 * stride) {
+    uint4 vd[2], vr[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long pix = pix0 + u * stride;
+      if (pix < P) {
+        vd[u] = *reinterpret_cast<const uint4*>(dout + pix * dp + c);
+        vr[u] = *reinterpret_cast<const uint4*>(raw + pix * rp + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long pix = pix0 + u * stride;
+      if (pix < P) {
+        float d[8], x[8], o[8];
+        unpack8(vd[u], d);
+        unpack8(vr[u], x);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float dy = d[j] * act_grad<ACT>(x[j] * sc[j] + sh[j]);
+          const float xh = (x[j] - mu[j]) * is[j];
+          o[j] = sc[j] * (dy - m1[j] - xh * m2[j]);
+        }
+        *reinterpret_cast<uint4*>(draw + pix * op + c) = pack8(o);
+      }
+    }
+  }
+}
+
+// dst (+)= src over P pixels x C channels
+__global__ void __launch_bounds__(256)
+add_into_kernel(__nv_bfloat16* __restrict__ dst, long long dpitch, const __nv_bfloat16* __restrict__ src, long long sp,
+                long long P, int C, int accumulate) {
+  const int groups = C >> 3;
+  const long long total = P * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / groups;
+    const int c = (int)(i - pix * groups) * 8;
+    uint4 v = *reinterpret_cast<const uint4*>(src + pix * sp + c);
+    if (accumulate) {
+      float a[8], b[8];
+      unpack8(v, a);
+      unpack8(*reinterpret_cast<const uint4*>(dst + pix * dpitch + c), b);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] += b[j];
+      v = pack8(a);
+    }
+    *reinterpret_cast<uint4*>(dst + pix * dpitch + c) = v;
+  }
+}
+
+// MaxPool2d backward: every output routes its gradient to the first maximum of its window (row-major scan,
+// strict >).  Overlapping windows (stride < k) use bf16 atomics on dx (which must already hold valid numbers).
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv_bfloat16* __restrict__ dy,
+                   long long dyp, int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                   __nv_bfloat16* __restrict__ dx, long long dxp) {
+  const int groups = C >> 3;
+  const long long total = (long long)N * Ho * Wo * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    long long pix = i / groups;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float m[8];
+    int am[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { m[j] = -INFINITY; am[j] = -1; }
+    for (int dh = 0; dh < k; dh++) {
+      const int hi = ho * stride + dh - pad;
+      if (hi < 0 || hi >= H) continue;
+      for (int dw = 0; dw < k; dw++) {
+        const int wi = wo * stride + dw - pad;
+        if (wi < 0 || wi >= W) continue;
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * H + hi) * W + wi) * xp + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (f[j] > m[j] || am[j] < 0) { m[j] = f[j]; am[j] = hi * W + wi; }
+      }
+    }
+    float g[8];
+    unpack8(*reinterpret_cast<const uint4*>(dy + pix * dyp + c), g);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (am[j] >= 0) atomicAdd(dx + ((long long)n * H * W + am[j]) * dxp + c + j, __float2bfloat16_rn(g[j]));
+  }
+}
+
+// dx (+)= sum of the 2x2 block of dy  (nearest x2 upsample backward)
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dyp, int N, int H, int W, int C,
+                      __nv_bfloat16* __restrict__ dx, long long dxp, int accumulate) {
+  const int groups = C >> 3;
+  const long long total = (long long)N * H * W * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    long long pix = i / groups;
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int dh = 0; dh < 2; dh++)
+#pragma unroll
+      for (int dw = 0; dw < 2; dw++) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(dy + (((long long)n * 2 * H + 2 * h + dh) * 2 * W + 2 * w + dw) * dyp + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] += f[j];
+      }
+    if (accumulate) {
+      float b[8];
+      unpack8(*reinterpret_cast<const uint4*>(dx + pix * dxp + c), b);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] += b[j];
+    }
+    *reinterpret_cast<uint4*>(dx + pix * dxp + c) = pack8(a);
+  }
+}
+
+// glev fp32 [B, na, H, W, ch] -> out bf16 [B, H, W, Cpad] (channel c = a*ch + k, zero for c >= na*ch), multiplied by
+// mul[c] when given (ImplicitM); dbias[c] += sum over pixels of the packed value.  One warp per pixel.
+__global__ void __launch_bounds__(256)
+head_grad_pack_kernel(const float* __restrict__ glev, int B, int na, int H, int W, int ch, int Cpad,
+                      const float* __restrict__ mul, __nv_bfloat16* __restrict__ out, float* __restrict__ dbias) {
+  extern __shared__ float sb[];    // [Cpad] block-level bias partials
+  const int C = na * ch;
+  for (int c = threadIdx.x; c < Cpad; c += blockDim.x) sb[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * wpb) {
+    const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
+    for (int c = lane; c < Cpad; c += 32) {
+      float v = 0.f;
+      if (c < C) {
+        const int a = c / ch, k = c - a * ch;
+        v = glev[((((long long)b * na + a) * H + h) * W + w) * ch + k];
+        if (mul) v *= mul[c];
+        atomicAdd(&sb[c], v);
+      }
+      out[pix * Cpad + c] = __float2bfloat16_rn(v);
+    }
+  }
+  __syncthreads();
+  if (dbias)
+    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, sb[c]);
+}
+
+__global__ void __launch_bounds__(256)
+sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n, float lr,
+           float momentum, float wd, int nesterov, int first) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] + wd * p[i];
+    float b = first ? gi : momentum * buf[i] + gi;
+    buf[i] = b;
+    p[i] -= lr * (nesterov ? gi + momentum * b : b);
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148ll * 32;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+extern "C" {
+
+// Backward of act(BatchNorm2d_train(raw)) (+ gradient already flowing to a residual is the caller's business).
+//   dout, raw: bf16 NHWC views over P pixels x C channels; scale/shift/mean/invstd: fp32[C] saved by the forward pass
+//   sums: fp32[2C] scratch, zeroed;  draw: bf16 view;  dgamma / dbeta: fp32[C] outputs (nullable)
+int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long rp, const float* scale,
+                     const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
+                     float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && dp % 8 == 0 && rp % 8 == 0 && op % 8 == 0,
+               "bn_act_bwd: channels must be a multiple of 8 in [8, 2048]");
+  if (P == 0) return RYOLO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int groups = C / 8;
+  const int threads = groups >= 256 ? groups : 256;
+  const int rows = threads / groups;
+  const size_t smem = (size_t)2 * rows * C * sizeof(float);
+  long long want = (P + 2ll * rows - 1) / (2ll * rows);
+  const int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+  const __nv_bfloat16* d = (const __nv_bfloat16*)dout;
+  const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
+  __nv_bfloat16* o = (__nv_bfloat16*)draw;
+#define RY_BWD(ACT)                                                                                                  \
+  bn_act_bwd_reduce_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C, sums); \
+  bn_act_bwd_apply_kernel<ACT><<<blocks * 2, threads, 0, st>>>(d, dp, r, rp, scale, shift, mean, invstd, sums, P, C, o, \
+                                                              op, dgamma, dbeta);
+  switch (act) {
+    case RYOLO_ACT_LEAKY: RY_BWD(RYOLO_ACT_LEAKY) break;
+    case RYOLO_ACT_MISH: RY_BWD(RYOLO_ACT_MISH) break;
+    case RYOLO_ACT_SWISH: RY_BWD(RYOLO_ACT_SWISH) break;
+    default: RY_BWD(RYOLO_ACT_LINEAR) break;
+  }
+#undef RY_BWD
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, long long P, int C, int accumulate,
+                   void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && dpitch % 8 == 0 && sp % 8 == 0, "add_into: channels must be multiples of 8");
+  if (P == 0) return RYOLO_OK;
+  add_into_kernel<<<grid_for(P * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((__nv_bfloat16*)dst, dpitch,
+                                                                                (const __nv_bfloat16*)src, sp, P, C,
+                                                                                accumulate);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+// dx must hold valid numbers on entry (zeros or a running gradient): the routed gradients are ADDED to it.
+int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp, int N, int H, int W, int C, int k,
+                      int stride, int pad, void* dx, long long dxp, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && k >= 1 && stride >= 1, "maxpool_bwd: bad arguments");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (C / 8);
+  if (total == 0) return RYOLO_OK;
+  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, N, H, W, C, k, stride, pad, Ho, Wo,
+      (__nv_bfloat16*)dx, dxp);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_upsample2x_bwd(const void* dy, long long dyp, int N, int H, int W, int C, void* dx, long long dxp,
+                         int accumulate, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0, "upsample2x_bwd: channels must be a multiple of 8");
+  const long long total = (long long)N * H * W * (C / 8);
+  if (total == 0) return RYOLO_OK;
+  upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, dyp, N, H, W,
+                                                                                C, (__nv_bfloat16*)dx, dxp, accumulate);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, float lr, float momentum,
+                   float weight_decay, int nesterov, int first, void* stream) {
+  if (n <= 0) return RYOLO_OK;
+  sgd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, buf, n, lr, momentum, weight_decay,
+                                                                nesterov, first);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch, int Cpad, const float* mul, void* out,
+                         float* dbias, void* stream) {
+  RY_CHECK_ARG(Cpad % 8 == 0 && Cpad >= na * ch && Cpad <= 4096, "head_grad_pack: bad padded channel count");
+  const long long npix = (long long)B * H * W;
+  if (npix == 0) return RYOLO_OK;
+  const int blocks = (int)(npix / 8 + 1 > 148 * 4 ? 148 * 4 : npix / 8 + 1);
+  head_grad_pack_kernel<<<blocks, 256, (size_t)Cpad * sizeof(float), (cudaStream_t)stream>>>(
+      glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+}  // extern "C"

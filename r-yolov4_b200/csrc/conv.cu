@@ -137,6 +137,10 @@ struct ConvKernelParams {
   int BN, stages;
   uint32_t tmem_cols;
   int ksize, stride, pad, kb_per_tap;
+  int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
+  signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
+  unsigned char tap_k[9];          // weight K-block index of each tap
+  int out_s, out_oh, out_ow, OutH, OutW;   // output lattice: pixel (ho*out_s + out_oh, wo*out_s + out_ow) of an OutH x OutW map
   int mode, act;
   void* out;
   long long out_cpitch;
@@ -178,8 +182,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
                  bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + 2]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int taps = p.ksize * p.ksize;
-  const int KB = taps * p.kb_per_tap;
+  const int KB = p.ntaps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   __shared__ __align__(16) float s_aff[2 * 256];           // scale | shift of this CTA's n-tile (EPI_AFFINE / EPI_HEAD)
   __shared__ float s_tr[8 * 32 * 17];                      // per-warp 32x16-word transpose tile (BN statistics, head stores)
@@ -219,14 +222,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int pw = mt % p.tiles_w; mt /= p.tiles_w;
         const int ph = mt % p.tiles_h;
         const int img = mt / p.tiles_h;
-        const int hs = ph * p.TH * p.stride - p.pad, ws = pw * p.TW * p.stride - p.pad, n0 = nt * BN;
+        const int hs = ph * p.TH * p.stride, ws = pw * p.TW * p.stride, n0 = nt * BN;
         for (int kb = 0; kb < KB; kb++) {
           const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-          const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
           mbar_wait(bar_empty + 8 * s, phase ^ 1u);
           mbar_expect_tx(bar_full + 8 * s, a_bytes + kBBytes);
-          tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, ws + kw, hs + kh, img);
-          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, tap * p.Cin + cb * kBK, n0);
+          tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
+          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * kBK, n0);
           if (++s == STAGES) { s = 0; phase ^= 1u; }
         }
       }
@@ -288,7 +290,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int img = mt / p.tiles_h;
       const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
       const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo);
-      const long long pix = ((long long)img * p.Ho + ho) * p.Wo + wo;
+      const long long pix = ((long long)img * p.OutH + ho * p.out_s + p.out_oh) * p.OutW + wo * p.out_s + p.out_ow;
       const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
       mbar_wait(bar_acc_full + 8 * buf, aphase);
       tc_fence_after();
@@ -520,6 +522,13 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   p->Ho = (d->H + 2 * p->pad - d->ksize) / d->stride + 1;
   p->Wo = (d->W + 2 * p->pad - d->ksize) / d->stride + 1;
   p->kb_per_tap = (d->Cin + kBK - 1) / kBK;
+  p->ntaps = d->ksize * d->ksize; p->Ktap = d->Cin;
+  for (int t = 0; t < p->ntaps; t++) {
+    p->tap_dh[t] = (signed char)(t / d->ksize - p->pad);
+    p->tap_dw[t] = (signed char)(t % d->ksize - p->pad);
+    p->tap_k[t] = (unsigned char)t;
+  }
+  p->out_s = 1; p->out_oh = 0; p->out_ow = 0; p->OutH = p->Ho; p->OutW = p->Wo;
   p->mode = d->out_mode; p->act = d->act;
   p->out = d->out; p->out_cpitch = d->out_cpitch;
   p->scale = d->scale; p->shift = d->shift;
@@ -615,6 +624,35 @@ int pick_bn(int Cout) {
   return best;
 }
 
+// Encodes the activation (4-D, box = one patch, element stride = conv stride) and weight (2-D) tensor maps and launches.
+int encode_and_launch(const void* x, int N, int H, int W, int C, long long cpitch, int estride, const void* w,
+                      int Ktot, int wrows, ConvKernelParams& p, cudaStream_t st) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
+  CUtensorMap tmA, tmB;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * W, (cuuint64_t)cpitch * 2 * W * H};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(p.TW * estride), (cuuint32_t)(p.TH * estride), 1};
+    cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the activation operand"); return RYOLO_ERR_CUDA; }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)wrows};
+    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)p.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the weight operand"); return RYOLO_ERR_CUDA; }
+  }
+  return launch(tmA, tmB, p, st);
+}
+
 }  // namespace
 
 extern "C" {
@@ -624,38 +662,67 @@ int ryolo_conv2d_forward(const ryolo_conv_desc* d, void* stream) {
   ConvKernelParams p{};
   int rc = fill_params(d, &p);
   if (rc) return rc;
-  EncodeTiledFn enc = get_encode();
-  if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
   if (d->N == 0) return RYOLO_OK;
+  p.BN = pick_bn(d->Cout);
+  return encode_and_launch(d->x, d->N, d->H, d->W, d->Cin, d->x_cpitch, d->stride, d->w,
+                           d->ksize * d->ksize * d->Cin, d->Cout, p, (cudaStream_t)stream);
+}
 
-  const int BN = pick_bn(d->Cout);
-  p.BN = BN;
-
-  CUtensorMap tmA, tmB;
-  {
-    cuuint64_t dims[4] = {(cuuint64_t)d->Cin, (cuuint64_t)d->W, (cuuint64_t)d->H, (cuuint64_t)d->N};
-    cuuint64_t strides[3] = {(cuuint64_t)d->x_cpitch * 2, (cuuint64_t)d->x_cpitch * 2 * d->W,
-                             (cuuint64_t)d->x_cpitch * 2 * d->W * d->H};
-    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(p.TW * d->stride), (cuuint32_t)(p.TH * d->stride), 1};
-    cuuint32_t estr[4] = {1, (cuuint32_t)d->stride, (cuuint32_t)d->stride, 1};
-    CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)d->x, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the activation operand"); return RYOLO_ERR_CUDA; }
+// Gradient wrt the input of Conv2d(Cin -> Cout, ksize, stride, pad=(ksize-1)/2):  dx[N,H,W,Cin] (+)= conv^T(dy, w).
+//   dy  bf16 NHWC view [N,Ho,Wo,Cout];  wt  bf16 [Cin][kh][kw][Cout] (ryolo_pack_weights with transpose=1)
+// Runs on the same tcgen05 kernel: the taps are mirrored, and a stride-s conv splits into s*s output-parity
+// classes, each an ordinary stride-1 implicit GEMM over dy writing an s-strided lattice of dx.
+int ryolo_conv2d_dgrad(const void* dy, long long dy_cpitch, int N, int H, int W, int Cin, int Cout, int ksize,
+                       int stride, const void* wt, void* dx, long long dx_cpitch, int accumulate, void* stream) {
+  RY_CHECK_ARG(ksize == 1 || ksize == 3, "dgrad: ksize must be 1 or 3");
+  RY_CHECK_ARG(stride == 1 || stride == 2, "dgrad: stride must be 1 or 2");
+  RY_CHECK_ARG(Cin % 8 == 0 && Cout % 8 == 0 && dy_cpitch % 8 == 0 && dx_cpitch % 8 == 0,
+               "dgrad: channel counts and pitches must be multiples of 8");
+  RY_CHECK_ARG((((uintptr_t)dy) & 15) == 0 && (((uintptr_t)dx) & 15) == 0 && (((uintptr_t)wt) & 15) == 0,
+               "dgrad: operands must be 16-byte aligned");
+  if (N == 0) return RYOLO_OK;
+  const int pad = (ksize - 1) / 2;
+  const int Ho = (H + 2 * pad - ksize) / stride + 1, Wo = (W + 2 * pad - ksize) / stride + 1;
+  for (int ph = 0; ph < stride; ph++) {
+    for (int pw = 0; pw < stride; pw++) {
+      const int Hl = (H - ph + stride - 1) / stride, Wl = (W - pw + stride - 1) / stride;
+      if (Hl <= 0 || Wl <= 0) continue;
+      ConvKernelParams p{};
+      p.N = N; p.Ho = Hl; p.Wo = Wl; p.Cout = Cin; p.Cin = Cout; p.Ktap = Cout;
+      p.ksize = ksize; p.stride = 1; p.pad = pad;
+      p.kb_per_tap = (Cout + kBK - 1) / kBK;
+      p.ntaps = 0;
+      for (int kh = 0; kh < ksize; kh++) {
+        const int vh = ph + pad - kh;
+        if (((vh % stride) + stride) % stride) continue;
+        for (int kw = 0; kw < ksize; kw++) {
+          const int vw = pw + pad - kw;
+          if (((vw % stride) + stride) % stride) continue;
+          p.tap_dh[p.ntaps] = (signed char)(vh >= 0 ? vh / stride : -((-vh) / stride));
+          p.tap_dw[p.ntaps] = (signed char)(vw >= 0 ? vw / stride : -((-vw) / stride));
+          p.tap_k[p.ntaps] = (unsigned char)(kh * ksize + kw);
+          p.ntaps++;
+        }
+      }
+      p.mode = RYOLO_OUT_NHWC_BF16; p.act = RYOLO_ACT_LINEAR;
+      p.out = dx; p.out_cpitch = dx_cpitch;
+      p.out_s = stride; p.out_oh = ph; p.out_ow = pw; p.OutH = H; p.OutW = W;
+      if (accumulate) { p.residual = (const __nv_bfloat16*)dx; p.res_cpitch = dx_cpitch; }
+      p.TH = 1; p.TW = 1;
+      pick_patch(Hl, Wl, 1, &p.TH, &p.TW);
+      p.tiles_h = (Hl + p.TH - 1) / p.TH;
+      p.tiles_w = (Wl + p.TW - 1) / p.TW;
+      p.BN = pick_bn(Cin);
+      if (p.ntaps == 0) {      // no contribution for this parity class (cannot happen for k=3/s=2, k=1/s=1)
+        ryolo_set_error("dgrad: empty tap set");
+        return RYOLO_ERR_INVALID;
+      }
+      int rc = encode_and_launch(dy, N, Ho, Wo, Cout, dy_cpitch, 1, wt, ksize * ksize * Cout, Cin, p,
+                                 (cudaStream_t)stream);
+      if (rc) return rc;
+    }
   }
-  {
-    const int Ktot = d->ksize * d->ksize * d->Cin;
-    cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)d->Cout};
-    cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)BN};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d->w, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the weight operand"); return RYOLO_ERR_CUDA; }
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  return launch(tmA, tmB, p, st);
+  return RYOLO_OK;
 }
 
 // Same contract as ryolo_conv2d_forward, computed by a plain CUDA-core kernel (device-side checker).

@@ -258,16 +258,28 @@ stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bflo
 }
 
 // ------------------------------------------------------------------------------------ weight packing
-// OIHW fp32 -> [Cout][kh][kw][Cin] bf16.  stem != 0: [Cout,3,3,3] -> [Cout][64] in the im2col channel order.
+// OIHW fp32 -> [Cout][kh][kw][Cin] bf16.  stem == 1: [Cout,3,3,3] -> [Cout][64] in the im2col channel order.
+// stem == 2 (transpose, for dgrad): -> [Cin][kh][kw][Cout].
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int stem,
                                     __nv_bfloat16* __restrict__ out) {
-  const int Kp = stem ? 64 : k * k * Cin;
+  if (stem == 2) {
+    const long long total = (long long)Cin * k * k * Cout;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+      const int co = (int)(i % Cout);
+      const int tap = (int)((i / Cout) % (k * k));
+      const int ci = (int)(i / ((long long)Cout * k * k));
+      out[i] = __float2bfloat16_rn(w[((long long)co * Cin + ci) * k * k + tap]);
+    }
+    return;
+  }
+  const int Kp = stem == 1 ? 64 : k * k * Cin;
   const long long total = (long long)Cout * Kp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i / Kp), kk = (int)(i % Kp);
     float v = 0.f;
-    if (stem) {
+    if (stem == 1) {
       if (kk < 27) {
         const int tap = kk / 3, ci = kk % 3;
         v = w[((long long)co * 3 + ci) * 9 + tap];
@@ -374,8 +386,8 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stre
 
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream) {
   RY_CHECK_ARG(Cout > 0 && Cin > 0 && k > 0, "pack_weights: bad shape");
-  RY_CHECK_ARG(!stem || (Cin == 3 && k == 3), "pack_weights: the stem layout is for 3-channel 3x3 convs");
-  const long long total = (long long)Cout * (stem ? 64 : k * k * Cin);
+  RY_CHECK_ARG(stem != 1 || (Cin == 3 && k == 3), "pack_weights: the stem layout is for 3-channel 3x3 convs");
+  const long long total = (long long)Cout * (stem == 1 ? 64 : k * k * Cin);
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, k, stem,
                                                                              (__nv_bfloat16*)out);
   RY_CHECK_LAUNCH();

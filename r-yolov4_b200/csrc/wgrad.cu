@@ -1,0 +1,388 @@
+// Weight gradient of Conv2d on the tcgen05 tensor cores (K3 in SURVEY.md §2.1): the conv_backward-weight half of
+// autograd's backward at train.py:198.
+//
+//   dW[co, tap, ci] = sum over pixels p of  dY[p, co] * X[p shifted by tap, ci]
+//
+// GEMM view: M = 128 output channels, N = 64*nb input channels, K = pixels.  Both operands are NHWC bf16, i.e.
+// "MN-major" for this GEMM (the channel dimension is contiguous, the reduction dimension strides by one pixel),
+// which UMMA consumes directly through MN-major SWIZZLE_128B descriptors: a [pixels x 64 channels] TMA box is
+// exactly one canonical MN-major atom column.  The K block is one TH x TW patch (<= 128 pixels); rows past
+// TH*TW are zeroed once (TMA never touches them), out-of-image rows are zero-filled by TMA, and the shifted X box
+// of every tap reuses the same tensor map as the forward pass (element strides = conv stride, OOB = padding).
+//
+//   work item   (128-channel Cout tile) x (64*nb-channel Cin tile) x (group of taps that fits TMEM: tg*64*nb <= 512)
+//   split-K     the patches of an item are dealt round-robin to `ksplit` CTAs; every CTA keeps its partial dW in TMEM
+//               for its whole life and adds it to the fp32 OIHW gradient with atomics once at the end
+//   pipeline    warp 0 TMA producer (dY ring of 2, X ring of b_stages) | warp 1 MMA issuer | warps 2-5 epilogue
+#include "common.cuh"
+#include "ryolo_b200.h"
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int kBoxBytes = 128 * 128;     // one [128 pixels x 64 channels] bf16 box
+constexpr int kMaxBStages = 8;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// MN-major SWIZZLE_128B descriptor: 64-element (128-byte) rows along MN, one row per K index, 8-row (1024-byte)
+// K groups (SBO); the next 64 MN elements live `lbo_bytes` further (LBO).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// D fp32, A/B bf16, both MN-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+
+struct WgradParams {
+  int N, Ho, Wo, Cin, Cout;
+  int TH, TW, tiles_h, tiles_w;
+  int ksize, stride, pad, ntaps;
+  int nb, tg;                               // X boxes per item (N = 64*nb), taps per item
+  int n_co_tiles, n_ci_tiles, n_tap_groups, ksplit;
+  int b_stages;
+  uint32_t tmem_cols;
+  float* dw;                                // fp32 OIHW [Cout][Cin][k][k] (stem: [Cout][3][3][3] from the 64-ch im2col)
+  int stem;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                  const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;                                   // 2 slots x 2 boxes (dY, 128 channels)
+  const uint32_t sB = smem_base + 4 * kBoxBytes;                   // b_stages slots x nb boxes (X)
+  __shared__ __align__(8) uint64_t bars[2 * kMaxBStages + 5];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar_bfull = smem_u32(&bars[0]), bar_bempty = smem_u32(&bars[kMaxBStages]),
+                 bar_afull = smem_u32(&bars[2 * kMaxBStages]), bar_aempty = smem_u32(&bars[2 * kMaxBStages + 2]),
+                 bar_acc = smem_u32(&bars[2 * kMaxBStages + 4]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int split = blockIdx.x % p.ksplit;
+  int item = blockIdx.x / p.ksplit;
+  const int tgi = item % p.n_tap_groups; item /= p.n_tap_groups;
+  const int cit = item % p.n_ci_tiles;
+  const int cot = item / p.n_ci_tiles;
+  const int tap0 = tgi * p.tg, ntap = min(p.tg, p.ntaps - tap0);
+  const int co0 = cot * 128, ci0 = cit * 64 * p.nb;
+  const int CIT = 64 * p.nb;
+  const int n_patches = p.N * p.tiles_h * p.tiles_w;
+  const int rows = p.TH * p.TW;
+  const uint32_t box_bytes = (uint32_t)rows * 128u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmG);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < p.b_stages; s++) {
+      mbar_init(bar_bfull + 8 * s, 1);
+      mbar_init(bar_bempty + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(bar_afull + 8 * s, 1);
+      mbar_init(bar_aempty + 8 * s, 1);
+    }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  if (rows < 128) {   // rows the TMA boxes never write must read as zeros (K padding of the GEMM)
+    const int nbox = 4 + p.b_stages * p.nb;
+    const int tail16 = (128 - rows) * 8;                           // 16-byte words per box tail
+    uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
+    for (int i = threadIdx.x; i < nbox * tail16; i += kThreads) {
+      const int b = i / tail16, w = i - b * tail16;
+      *reinterpret_cast<uint4*>(base + (size_t)b * kBoxBytes + (size_t)rows * 128 + (size_t)w * 16) =
+          make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+  const bool has_work = split < n_patches;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t bphase = 0, pit = 0;
+      for (int patch = split; patch < n_patches; patch += p.ksplit, pit++) {
+        const int pw = patch % p.tiles_w;
+        const int ph = (patch / p.tiles_w) % p.tiles_h;
+        const int img = patch / (p.tiles_w * p.tiles_h);
+        const int h0 = ph * p.TH, w0 = pw * p.TW;
+        const uint32_t ab = pit & 1u, aphase = (pit >> 1) & 1u;
+        mbar_wait(bar_aempty + 8 * ab, aphase ^ 1u);
+        mbar_expect_tx(bar_afull + 8 * ab, 2 * box_bytes);
+        tma_load_4d(sA + (ab * 2 + 0) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0, w0, h0, img);
+        tma_load_4d(sA + (ab * 2 + 1) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0 + 64, w0, h0, img);
+        for (int ti = 0; ti < ntap; ti++) {
+          const int tap = tap0 + ti;
+          const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+          mbar_wait(bar_bempty + 8 * s, bphase ^ 1u);
+          mbar_expect_tx(bar_bfull + 8 * s, (uint32_t)p.nb * box_bytes);
+          for (int j = 0; j < p.nb; j++)
+            tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + 64 * j,
+                        w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
+          if (++s == p.b_stages) { s = 0; bphase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16_mn(CIT);
+      const int ksteps = (rows + 15) / 16;
+      int s = 0;
+      uint32_t bphase = 0, pit = 0;
+      for (int patch = split; patch < n_patches; patch += p.ksplit, pit++) {
+        const uint32_t ab = pit & 1u, aphase = (pit >> 1) & 1u;
+        mbar_wait(bar_afull + 8 * ab, aphase);
+        tc_fence_after();
+        const uint32_t a0 = sA + ab * 2 * kBoxBytes;
+        for (int ti = 0; ti < ntap; ti++) {
+          mbar_wait(bar_bfull + 8 * s, bphase);
+          tc_fence_after();
+          const uint32_t b0 = sB + (uint32_t)(s * p.nb) * kBoxBytes;
+          for (int kk = 0; kk < ksteps; kk++) {
+            umma_bf16(tmem_base + (uint32_t)(ti * CIT), umma_desc_mn_sw128(a0 + kk * 2048, kBoxBytes),
+                      umma_desc_mn_sw128(b0 + kk * 2048, kBoxBytes), idesc, (pit | (uint32_t)kk) ? 1u : 0u);
+          }
+          umma_commit(bar_bempty + 8 * s);
+          if (++s == p.b_stages) { s = 0; bphase ^= 1u; }
+        }
+        umma_commit(bar_aempty + 8 * ab);
+      }
+      umma_commit(bar_acc);
+    }
+  } else if (has_work) {
+    const int sub = warp & 3;
+    const int co = co0 + sub * 32 + lane;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int kk2 = p.ksize * p.ksize;
+    for (int ti = 0; ti < ntap; ti++) {
+      const int tap = tap0 + ti;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CIT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(ti * CIT + c0), v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int ci = ci0 + c0 + j;
+            if (p.stem) {   // im2col channel ci = (kh*3+kw)*3 + c  ->  OIHW [co][c][kh][kw]
+              if (ci < 27) atomicAdd(p.dw + ((long long)co * 3 + ci % 3) * 9 + ci / 3, __uint_as_float(v[j]));
+            } else if (ci < p.Cin) {
+              atomicAdd(p.dw + ((long long)co * p.Cin + ci) * kk2 + tap, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+void pick_patch(int Ho, int Wo, int* TH, int* TW) {
+  double best = -1.0;
+  for (int tw = 1; tw <= 128 && tw <= Wo; tw++) {
+    int th = 128 / tw;
+    if (th > Ho) th = Ho;
+    const double tiles = (double)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
+    const double eff = (double)Ho * Wo / (tiles * 128.0);
+    if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > *TW)) { best = eff; *TH = th; *TW = tw; }
+  }
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int encode_nhwc(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, long long cpitch,
+                int TH, int TW, int estride) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * W, (cuuint64_t)cpitch * 2 * W * H};
+  cuuint32_t box[4] = {64, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+// dw (fp32 OIHW [Cout][Cin][k][k], or [Cout][3][3][3] when stem != 0 and x is the 64-channel im2col tensor) +=
+// conv_backward_weight(x, dy).   x: bf16 NHWC view [N,H,W,Cin]; dy: bf16 NHWC view [N,Ho,Wo,Cdy] with Cdy >= Cout
+// channels readable (extra channels are ignored).  dw must be zeroed (or hold a running sum) on entry.
+int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
+                       long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, int stem, float* dw,
+                       void* stream) {
+  RY_CHECK_ARG(ksize == 1 || ksize == 3, "wgrad: ksize must be 1 or 3");
+  RY_CHECK_ARG(stride == 1 || stride == 2, "wgrad: stride must be 1 or 2");
+  RY_CHECK_ARG(Cin % 8 == 0 && Cdy % 8 == 0 && x_cpitch % 8 == 0 && dy_cpitch % 8 == 0 && Cdy >= Cout,
+               "wgrad: channel counts and pitches must be multiples of 8");
+  RY_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)dy) & 15) == 0, "wgrad: operands must be 16-byte aligned");
+  RY_CHECK_ARG(!stem || (Cin == 64 && ksize == 1), "wgrad: the stem path expects the 64-channel im2col input");
+  if (N == 0) return RYOLO_OK;
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
+  WgradParams p{};
+  p.N = N; p.Cin = Cin; p.Cout = Cout; p.ksize = ksize; p.stride = stride; p.pad = (ksize - 1) / 2;
+  p.Ho = (H + 2 * p.pad - ksize) / stride + 1;
+  p.Wo = (W + 2 * p.pad - ksize) / stride + 1;
+  p.ntaps = ksize * ksize;
+  p.TH = 1; p.TW = 1;
+  pick_patch(p.Ho, p.Wo, &p.TH, &p.TW);
+  if (p.TW * stride > 256) { p.TW = 256 / stride; p.TH = 128 / p.TW; if (p.TH > p.Ho) p.TH = p.Ho; }
+  p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
+  p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
+  p.nb = (Cin + 63) / 64;
+  if (p.nb > 4) p.nb = 4;
+  const int CIT = 64 * p.nb;
+  p.n_ci_tiles = (Cin + CIT - 1) / CIT;
+  p.n_co_tiles = (Cout + 127) / 128;
+  p.tg = 512 / CIT;
+  if (p.tg > p.ntaps) p.tg = p.ntaps;
+  p.n_tap_groups = (p.ntaps + p.tg - 1) / p.tg;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.tg * CIT)) cols <<= 1;
+  p.tmem_cols = cols;
+  const int items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
+  const long long n_patches = (long long)N * p.tiles_h * p.tiles_w;
+  RY_CHECK_ARG(n_patches < (1ll << 31), "wgrad: too many patches");
+  int ksplit = sm_count() / items;
+  if (ksplit < 1) ksplit = 1;
+  if (ksplit > n_patches) ksplit = (int)n_patches;
+  p.ksplit = ksplit;
+  const size_t budget = 200 * 1024;
+  int bst = (int)((budget - 1024 - 4 * (size_t)kBoxBytes) / ((size_t)p.nb * kBoxBytes));
+  if (bst > kMaxBStages) bst = kMaxBStages;
+  RY_CHECK_ARG(bst >= 2, "wgrad: shared memory budget too small");
+  p.b_stages = bst;
+  const size_t smem = 1024 + 4 * (size_t)kBoxBytes + (size_t)bst * p.nb * kBoxBytes;
+  p.dw = dw; p.stem = stem;
+  CUtensorMap tmG, tmX;
+  if (encode_nhwc(enc, &tmG, dy, N, p.Ho, p.Wo, Cdy, dy_cpitch, p.TH, p.TW, 1) ||
+      encode_nhwc(enc, &tmX, x, N, H, W, Cin, x_cpitch, p.TH, p.TW, stride)) {
+    ryolo_set_error("cuTensorMapEncodeTiled failed in wgrad");
+    return RYOLO_ERR_CUDA;
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
+    configured = true;
+  }
+  conv_wgrad_kernel<<<items * ksplit, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+}  // extern "C"

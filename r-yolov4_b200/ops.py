@@ -128,12 +128,15 @@ def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear"
     return out
 
 
-def pack_weights(w_oihw, stem=False):
-    """fp32 OIHW (state-dict layout) -> bf16 [Cout, kh*kw*Cin] ([Cout, 64] for the stem)."""
+def pack_weights(w_oihw, stem=False, transpose=False):
+    """fp32 OIHW (state-dict layout) -> bf16 [Cout, kh*kw*Cin] ([Cout, 64] for the stem;
+    [Cin, kh*kw*Cout] with transpose=True, the dgrad operand)."""
     w = w_oihw.detach().contiguous().float()
     Cout, Cin, k, _ = w.shape
-    out = torch.empty((Cout, 64 if stem else k * k * Cin), dtype=torch.bfloat16, device=w.device)
-    L.check(L.lib().ryolo_pack_weights(_tp(w), Cout, Cin, k, 1 if stem else 0, _tp(out), L.stream()))
+    shape = (Cin, k * k * Cout) if transpose else (Cout, 64 if stem else k * k * Cin)
+    out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
+    L.check(L.lib().ryolo_pack_weights(_tp(w), Cout, Cin, k, 2 if transpose else (1 if stem else 0), _tp(out),
+                                       L.stream()))
     L.count(1)
     return out
 
@@ -189,3 +192,60 @@ def resize_copy(x, factor, out=None):
                                       L.stream()))
     L.count(1)
     return out
+
+
+# ------------------------------------------------------------------------------------ backward wrappers
+def conv2d_dgrad(dy, wt, Cin, k, stride, dx, accumulate):
+    """dx (Act [N,H,W,Cin]) (+)= conv^T(dy, w);  wt = pack_weights(w, transpose=True) with Cout == dy.C."""
+    assert wt.dtype == torch.bfloat16 and wt.numel() == Cin * k * k * dy.C
+    L.check(L.lib().ryolo_conv2d_dgrad(_vp(dy.ptr), dy.pitch, dx.N, dx.H, dx.W, Cin, dy.C, k, stride, _tp(wt),
+                                       _vp(dx.ptr), dx.pitch, 1 if accumulate else 0, L.stream()))
+    L.count(stride * stride)
+
+
+def conv2d_wgrad(x, dy, Cout, k, stride, dw, stem=False):
+    """dw (fp32, OIHW) += conv_backward_weight(x, dy)."""
+    assert dw.dtype == torch.float32 and dw.is_contiguous()
+    L.check(L.lib().ryolo_conv2d_wgrad(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, _vp(dy.ptr), dy.pitch, dy.C, Cout, k,
+                                       stride, 1 if stem else 0, _tp(dw), L.stream()))
+    L.count(1)
+
+
+def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, dbeta):
+    L.check(L.lib().ryolo_bn_act_bwd(_vp(dout.ptr), dout.pitch, _vp(raw.ptr), raw.pitch, _tp(scale), _tp(shift),
+                                     _tp(mean), _tp(invstd), ACT[act], raw.P, raw.C, _tp(sums), _vp(draw.ptr),
+                                     draw.pitch, _tp(dgamma), _tp(dbeta), L.stream()))
+    L.count(2)
+
+
+def add_into(dst, src, accumulate):
+    L.check(L.lib().ryolo_add_into(_vp(dst.ptr), dst.pitch, _vp(src.ptr), src.pitch, src.P, src.C,
+                                   1 if accumulate else 0, L.stream()))
+    L.count(1)
+
+
+def maxpool_bwd(x, dy, k, stride, pad, dx):
+    L.check(L.lib().ryolo_maxpool_bwd(_vp(x.ptr), x.pitch, _vp(dy.ptr), dy.pitch, x.N, x.H, x.W, x.C, k, stride, pad,
+                                      _vp(dx.ptr), dx.pitch, L.stream()))
+    L.count(1)
+
+
+def upsample2x_bwd(dy, dx, accumulate):
+    L.check(L.lib().ryolo_upsample2x_bwd(_vp(dy.ptr), dy.pitch, dx.N, dx.H, dx.W, dx.C, _vp(dx.ptr), dx.pitch,
+                                         1 if accumulate else 0, L.stream()))
+    L.count(1)
+
+
+def head_grad_pack(glev, Cpad, mul, dbias):
+    B, na, H, W, ch = glev.shape
+    out = Act.empty(B, H, W, Cpad, glev.device)
+    L.check(L.lib().ryolo_head_grad_pack(_tp(glev.contiguous()), B, na, H, W, ch, Cpad, _tp(mul), _vp(out.ptr),
+                                         _tp(dbias), L.stream()))
+    L.count(1)
+    return out
+
+
+def sgd_step(param, grad, buf, lr, momentum, weight_decay, nesterov, first):
+    L.check(L.lib().ryolo_sgd_step(_tp(param), _tp(grad), _tp(buf), param.numel(), float(lr), float(momentum),
+                                   float(weight_decay), 1 if nesterov else 0, 1 if first else 0, L.stream()))
+    L.count(1)

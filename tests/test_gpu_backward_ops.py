@@ -1,0 +1,178 @@
+"""GPU parity of the backward kernels (dgrad on the conv kernel, tcgen05 wgrad, BN/act/pool/upsample backward)
+against torch CPU autograd on the same bf16-rounded operands."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [  # N, H, W, Cin, Cout, k, stride
+    (2, 25, 25, 64, 128, 3, 1),
+    (2, 16, 16, 64, 64, 1, 1),
+    (2, 50, 50, 128, 256, 3, 2),
+    (2, 13, 13, 256, 512, 3, 1),
+    (1, 52, 52, 32, 64, 3, 2),
+    (1, 40, 40, 32, 32, 3, 1),
+    (2, 9, 7, 192, 96, 3, 1),
+    (1, 25, 25, 1024, 512, 1, 1),
+    (1, 25, 25, 512, 1024, 3, 1),
+    (1, 27, 27, 64, 128, 3, 2),      # odd size, stride 2
+]
+
+
+def _case(shape, seed=0):
+    N, H, W, Cin, Cout, k, s = shape
+    gen = torch.Generator().manual_seed(seed + sum(shape))
+    x = torch.randn(N, H, W, Cin, generator=gen).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=gen) * (2.0 / (Cin * k * k)) ** 0.5)
+    Ho, Wo = (H + 2 * ((k - 1) // 2) - k) // s + 1, (W + 2 * ((k - 1) // 2) - k) // s + 1
+    dy = torch.randn(N, Ho, Wo, Cout, generator=gen).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.bfloat16().float().requires_grad_(True)
+    y = F.conv2d(xr, wr, None, s, (k - 1) // 2)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    return x, w, dy, xr.grad.permute(0, 2, 3, 1).contiguous(), wr.grad
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_dgrad(shape):
+    from ryolo_b200 import ops
+    N, H, W, Cin, Cout, k, s = shape
+    x, w, dy, dx_ref, _ = _case(shape)
+    wt = ops.pack_weights(w.cuda(), transpose=True)
+    dx = ops.Act(torch.full((N, H, W, Cin), 3.0).bfloat16().cuda())
+    ops.conv2d_dgrad(ops.Act(dy.cuda()), wt, Cin, k, s, dx, accumulate=False)
+    got = dx.torch().float().cpu()
+    tol = 2e-2 * dx_ref.abs().max()
+    assert (got - dx_ref).abs().max() < tol
+    ops.conv2d_dgrad(ops.Act(dy.cuda()), wt, Cin, k, s, dx, accumulate=True)      # dx += same thing
+    assert (dx.torch().float().cpu() - 2 * dx_ref).abs().max() < 2 * tol
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_wgrad(shape):
+    from ryolo_b200 import ops
+    N, H, W, Cin, Cout, k, s = shape
+    x, w, dy, _, dw_ref = _case(shape, seed=1)
+    dw = torch.zeros(Cout, Cin, k, k, device="cuda")
+    ops.conv2d_wgrad(ops.Act(x.cuda()), ops.Act(dy.cuda()), Cout, k, s, dw)
+    got = dw.cpu()
+    assert (got - dw_ref).abs().max() < 1e-2 * dw_ref.abs().max(), (got - dw_ref).abs().max() / dw_ref.abs().max()
+    ops.conv2d_wgrad(ops.Act(x.cuda()), ops.Act(dy.cuda()), Cout, k, s, dw)      # accumulates
+    assert (dw.cpu() - 2 * dw_ref).abs().max() < 2e-2 * dw_ref.abs().max()
+
+
+def test_wgrad_channel_slices_and_padded_dy():
+    """x and dy are slices of wider buffers; dy carries padded channels beyond Cout (head case)."""
+    from ryolo_b200 import ops
+    shape = (2, 20, 20, 64, 40, 1, 1)
+    x, w, dy, _, dw_ref = _case(shape, seed=2)
+    xb = torch.randn(2, 20, 20, 160).bfloat16()
+    xb[..., 32:96] = x
+    dyb = torch.zeros(2, 20, 20, 48).bfloat16()
+    dyb[..., :40] = dy
+    dyb[..., 40:] = 5.0          # garbage in the padding must not leak into rows < Cout
+    dw = torch.zeros(40, 64, 1, 1, device="cuda")
+    ops.conv2d_wgrad(ops.Act(xb.cuda(), 64, 32), ops.Act(dyb.cuda()), 40, 1, 1, dw)
+    assert (dw.cpu() - dw_ref).abs().max() < 1e-2 * dw_ref.abs().max()
+
+
+def test_wgrad_stem():
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(3)
+    img = torch.rand(2, 3, 40, 36, generator=gen)
+    dy = torch.randn(2, 40, 36, 32, generator=gen).bfloat16()
+    w = torch.zeros(32, 3, 3, 3, requires_grad=True)
+    y = F.conv2d(img.bfloat16().float(), w, None, 1, 1)
+    y.backward(dy.float().permute(0, 3, 1, 2))
+    dw = torch.zeros(32, 3, 3, 3, device="cuda")
+    ops.conv2d_wgrad(ops.stem_im2col(img.cuda()), ops.Act(dy.cuda()), 32, 1, 1, dw, stem=True)
+    assert (dw.cpu() - w.grad).abs().max() < 1e-2 * w.grad.abs().max()
+
+
+@pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
+def test_bn_act_backward(act):
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(4)
+    N, H, W, C = 3, 20, 20, 96
+    raw = (torch.randn(N, H, W, C, generator=gen) * 1.5 + 0.3).bfloat16()
+    dout = torch.randn(N, H, W, C, generator=gen).bfloat16()
+    gamma = (torch.rand(C, generator=gen) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, generator=gen).requires_grad_(True)
+    xr = raw.float().permute(0, 3, 1, 2).requires_grad_(True)
+    y = F.batch_norm(xr, None, None, gamma, beta, True, 0.1, 1e-5)
+    z = {"linear": y, "leaky": F.leaky_relu(y, 0.1), "mish": F.mish(y), "swish": F.silu(y)}[act]
+    z.backward(dout.float().permute(0, 3, 1, 2))
+    mean = raw.float().mean((0, 1, 2))
+    var = raw.float().var((0, 1, 2), unbiased=False)
+    invstd = torch.rsqrt(var + 1e-5)
+    scale = gamma.detach() * invstd
+    shift = beta.detach() - mean * scale
+    sums = torch.zeros(2 * C, device="cuda")
+    draw = ops.Act.empty(N, H, W, C, "cuda")
+    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    ops.bn_act_bwd(ops.Act(dout.cuda()), ops.Act(raw.cuda()), scale.cuda(), shift.cuda(), mean.cuda(), invstd.cuda(), act,
+                   sums, draw, dg, db)
+    ref = xr.grad.permute(0, 2, 3, 1)
+    assert (draw.torch().float().cpu() - ref).abs().max() < 2e-2 * ref.abs().max()
+    assert (dg.cpu() - gamma.grad).abs().max() < 5e-3 * gamma.grad.abs().max()
+    assert (db.cpu() - beta.grad).abs().max() < 5e-3 * beta.grad.abs().max()
+
+
+def test_pool_upsample_add_headpack_backward():
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 25, 25, 64, generator=gen).bfloat16()
+    xn = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    dy = torch.randn(2, 25, 25, 64, generator=gen).bfloat16()
+    F.max_pool2d(xn, 5, 1, 2).backward(dy.float().permute(0, 3, 1, 2))
+    dx = ops.Act(torch.zeros(2, 25, 25, 64).bfloat16().cuda())
+    ops.maxpool_bwd(ops.Act(x.cuda()), ops.Act(dy.cuda()), 5, 1, 2, dx)
+    ref = xn.grad.permute(0, 2, 3, 1)
+    assert (dx.torch().float().cpu() - ref).abs().max() < 3e-2 * ref.abs().max()      # bf16 atomics
+    # 2x2 / stride 2
+    x2 = x[:, :24, :24].contiguous()
+    xn = x2.float().permute(0, 3, 1, 2).requires_grad_(True)
+    dy2 = torch.randn(2, 12, 12, 64, generator=gen).bfloat16()
+    F.max_pool2d(xn, 2, 2).backward(dy2.float().permute(0, 3, 1, 2))
+    dx = ops.Act(torch.zeros(2, 24, 24, 64).bfloat16().cuda())
+    ops.maxpool_bwd(ops.Act(x2.cuda()), ops.Act(dy2.cuda()), 2, 2, 0, dx)
+    assert torch.equal(dx.torch().float().cpu(), xn.grad.permute(0, 2, 3, 1))
+    # upsample x2
+    g = torch.randn(2, 20, 20, 32, generator=gen).bfloat16()
+    ref = g.float().view(2, 10, 2, 10, 2, 32).sum((2, 4))
+    dx = ops.Act(torch.ones(2, 10, 10, 32).bfloat16().cuda())
+    ops.upsample2x_bwd(ops.Act(g.cuda()), dx, accumulate=True)
+    assert (dx.torch().float().cpu() - (ref + 1)).abs().max() < 2e-2 * ref.abs().max()
+    # add_into on slices
+    a = torch.randn(2, 6, 6, 64, generator=gen).bfloat16()
+    b = torch.randn(2, 6, 6, 32, generator=gen).bfloat16()
+    A = ops.Act(a.clone().cuda(), 32, 16)
+    ops.add_into(A, ops.Act(b.cuda()), accumulate=True)
+    out = A.buf.float().cpu()
+    assert (out[..., 16:48] - (a[..., 16:48].float() + b.float())).abs().max() < 2e-2
+    assert torch.equal(out[..., :16], a[..., :16].float()) and torch.equal(out[..., 48:], a[..., 48:].float())
+    # head gradient pack
+    gl = torch.randn(2, 3, 7, 7, 187, generator=gen)
+    mul = torch.rand(561, generator=gen) + 0.5
+    dbias = torch.zeros(561, device="cuda")
+    packed = ops.head_grad_pack(gl.cuda(), 568, mul.cuda(), dbias)
+    ref = (gl.permute(0, 2, 3, 1, 4).reshape(2, 7, 7, 561) * mul)
+    got = packed.torch().float().cpu()
+    assert (got[..., :561] - ref).abs().max() < 1e-2 * ref.abs().max() and (got[..., 561:] == 0).all()
+    assert (dbias.cpu() - ref.sum((0, 1, 2))).abs().max() < 1e-3 * ref.sum((0, 1, 2)).abs().max()
+
+
+def test_sgd_step():
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(6)
+    p0 = torch.randn(10007, generator=gen)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.SGD([ref], lr=0.01, momentum=0.937, nesterov=True, weight_decay=5e-4)
+    p, buf = p0.clone().cuda(), torch.zeros(10007, device="cuda")
+    for it in range(3):
+        g = torch.randn(10007, generator=gen)
+        ref.grad = g.clone()
+        opt.step()
+        ops.sgd_step(p, g.cuda(), buf, 0.01, 0.937, 5e-4, True, it == 0)
+    assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
