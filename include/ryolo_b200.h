@@ -166,6 +166,10 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
 int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
                      float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream);
+/* ds = dout * act'(x1*s1+b1 + x2*s2+b2): backward through RepConv's SiLU of two summed BN branches          */
+int ryolo_act_bwd2(const void* dout, long long dp, const void* x1, long long p1, const float* s1, const float* b1,
+                   const void* x2, long long p2, const float* s2, const float* b2, int act, void* ds, long long op,
+                   long long P, int C, void* stream);
 /* dst (+)= src on bf16 NHWC views (gradient fan-in: residuals, concat slices, multiple consumers)            */
 int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, long long P, int C, int accumulate,
                    void* stream);

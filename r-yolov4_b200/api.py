@@ -5,6 +5,7 @@ from .lib.general import (nms_rotated, non_max_suppression, norm_angle, pairwise
                           post_process_device)
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
+from .train_step import TrainStep
 
 try:  # the conv stack is built on top of the kernels above
     from .model.yolo import Yolo
@@ -20,4 +21,4 @@ def compute_loss(model, hyp, mode="csl"):
 
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
-           "YoloCSLLayer", "YoloKFIoULayer", "RyoloError", "SO_PATH", "lib"]
+           "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "RyoloError", "SO_PATH", "lib"]

@@ -164,6 +164,30 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, co
   }
 }
 
+// ds = dout * act'(x1*s1+b1 + x2*s2+b2)   (two-branch pre-activation, RepConv)
+template <int ACT>
+__global__ void __launch_bounds__(256)
+act_bwd2_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ x1,
+                long long p1, const float* __restrict__ s1, const float* __restrict__ b1,
+                const __nv_bfloat16* __restrict__ x2, long long p2, const float* __restrict__ s2,
+                const float* __restrict__ b2, __nv_bfloat16* __restrict__ ds, long long op, long long P, int C) {
+  const int groups = C >> 3;
+  const long long total = P * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / groups;
+    const int c = (int)(i - pix * groups) * 8;
+    float d[8], a[8], b[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(dout + pix * dp + c), d);
+    unpack8(*reinterpret_cast<const uint4*>(x1 + pix * p1 + c), a);
+    unpack8(*reinterpret_cast<const uint4*>(x2 + pix * p2 + c), b);
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      o[j] = d[j] * act_grad<ACT>(a[j] * s1[c + j] + b1[c + j] + b[j] * s2[c + j] + b2[c + j]);
+    *reinterpret_cast<uint4*>(ds + pix * op + c) = pack8(o);
+  }
+}
+
 // dst (+)= src over P pixels x C channels
 __global__ void __launch_bounds__(256)
 add_into_kernel(__nv_bfloat16* __restrict__ dst, long long dpitch, const __nv_bfloat16* __restrict__ src, long long sp,
@@ -336,6 +360,27 @@ int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long 
     default: RY_BWD(RYOLO_ACT_LINEAR) break;
   }
 #undef RY_BWD
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_act_bwd2(const void* dout, long long dp, const void* x1, long long p1, const float* s1, const float* b1,
+                   const void* x2, long long p2, const float* s2, const float* b2, int act, void* ds, long long op,
+                   long long P, int C, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0, "act_bwd2: channels must be a multiple of 8");
+  if (P == 0) return RYOLO_OK;
+  const int g = grid_for(P * (C / 8), 256);
+  cudaStream_t st = (cudaStream_t)stream;
+#define RY_A2(ACT)                                                                                               \
+  act_bwd2_kernel<ACT><<<g, 256, 0, st>>>((const __nv_bfloat16*)dout, dp, (const __nv_bfloat16*)x1, p1, s1, b1,  \
+                                          (const __nv_bfloat16*)x2, p2, s2, b2, (__nv_bfloat16*)ds, op, P, C);
+  switch (act) {
+    case RYOLO_ACT_LEAKY: RY_A2(RYOLO_ACT_LEAKY) break;
+    case RYOLO_ACT_MISH: RY_A2(RYOLO_ACT_MISH) break;
+    case RYOLO_ACT_SWISH: RY_A2(RYOLO_ACT_SWISH) break;
+    default: RY_A2(RYOLO_ACT_LINEAR) break;
+  }
+#undef RY_A2
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

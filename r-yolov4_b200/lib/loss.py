@@ -20,27 +20,32 @@ def _grid_hw(levels):
     return arr
 
 
+def _run_loss(cfg, targets, levels, need_grad):
+    """One fused pass: returns (items fp32[8] on device, list of d loss / d level or None)."""
+    mode, na, nc, anchors, hyp = cfg
+    lib = L.lib()
+    dev = levels[0].device
+    lv = [p.detach().contiguous() for p in levels]
+    B = lv[0].shape[0]
+    T = targets.shape[0]
+    tg = targets.detach().contiguous().float() if T else torch.zeros((0, 187 if mode == 0 else 7), device=dev)
+    ghw = _grid_hw(lv)
+    nb = lib.ryolo_loss_workspace(B, na, ghw, T)
+    ws = L.workspace(nb, dev, "loss")
+    grads = [torch.empty_like(p) for p in lv] if need_grad else None
+    items = torch.empty(8, dtype=torch.float32, device=dev)
+    lp = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in lv])
+    gp = (ctypes.c_void_p * 3)(*[g.data_ptr() for g in grads]) if need_grad else None
+    L.check(lib.ryolo_loss(mode, lp, gp, B, na, nc, ghw, L.ptr(tg), T, tg.shape[1], L.ptr(anchors), hyp,
+                           L.ptr(items), L.ptr(ws), nb, L.stream()))
+    L.count(10 if T else 4)
+    return items, grads
+
+
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, targets, *levels):
-        mode, na, nc, anchors, hyp = cfg
-        need_grad = any(ctx.needs_input_grad[2:])
-        lib = L.lib()
-        dev = levels[0].device
-        lv = [p.detach().contiguous() for p in levels]
-        B = lv[0].shape[0]
-        T = targets.shape[0]
-        tg = targets.detach().contiguous().float() if T else torch.zeros((0, 187 if mode == 0 else 7), device=dev)
-        ghw = _grid_hw(lv)
-        nb = lib.ryolo_loss_workspace(B, na, ghw, T)
-        ws = L.workspace(nb, dev, "loss")
-        grads = [torch.empty_like(p) for p in lv] if need_grad else None
-        items = torch.empty(8, dtype=torch.float32, device=dev)
-        lp = (ctypes.c_void_p * 3)(*[p.data_ptr() for p in lv])
-        gp = (ctypes.c_void_p * 3)(*[g.data_ptr() for g in grads]) if need_grad else None
-        L.check(lib.ryolo_loss(mode, lp, gp, B, na, nc, ghw, L.ptr(tg), T, tg.shape[1], L.ptr(anchors), hyp,
-                               L.ptr(items), L.ptr(ws), nb, L.stream()))
-        L.count(10 if T else 4)
+        items, grads = _run_loss(cfg, targets, levels, any(ctx.needs_input_grad[2:]))
         ctx.grads = grads
         ctx.mark_non_differentiable(items)
         return items[4:5].clone(), items
@@ -88,6 +93,14 @@ class _ComputeLoss:
             vals = dict(reg_loss=v[0], theta_loss=v[1], conf_loss=v[2], cls_loss=v[3], total_loss=v[4])
             self.loss_items.update({k: vals[k] for k in self.KEYS})
         return loss, self.loss_items
+
+    def value_and_grad(self, outputs, target):
+        """Native path (no autograd): (items fp32[8] on device = reg, theta, conf, cls, total, n_pos x3;
+        [d loss / d level] x 3)."""
+        cfg = (self.MODE, self.na, self.nc, self._anchors3, self._hyp)
+        items, grads = _run_loss(cfg, target, outputs, True)
+        self.last_items_device = items
+        return items, grads
 
     def build_targets(self, p, targets):
         """Reference-format assignment tuples (bit-exact indices, reference emission order)."""

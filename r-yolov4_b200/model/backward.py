@@ -1,0 +1,157 @@
+"""Backward pass of the conv stack: walks the tape recorded by the training forward (model/blocks.py)
+in reverse and drives the dgrad / wgrad / BN-activation / pooling / upsample backward kernels.
+This is what autograd does for the reference at train.py:198; here nothing goes through torch autograd.
+
+Gradients of activations live in bf16 NHWC buffers that mirror the forward buffers (so a slice of a
+concat buffer has its gradient in the same slice of the mirrored buffer); weight gradients are fp32 and
+are ACCUMULATED into the tensors handed in by `param_grads` (zeroed by the caller).
+"""
+import torch
+
+from .. import ops
+from ..ops import Act
+
+
+class GradStore:
+    """bf16 gradient buffers mirroring forward activation buffers, with per-channel-range init tracking."""
+
+    def __init__(self):
+        self.bufs = {}       # buf.data_ptr() -> (grad tensor, list of initialised (lo, hi))
+
+    def _entry(self, act):
+        key = act.buf.data_ptr()
+        e = self.bufs.get(key)
+        if e is None:
+            e = (torch.empty_like(act.buf), [])
+            self.bufs[key] = e
+        return e
+
+    def view(self, act):
+        g, _ = self._entry(act)
+        return Act(g, act.C, act.coff)
+
+    def is_init(self, act):
+        _, rng = self._entry(act)
+        lo, hi = act.coff, act.coff + act.C
+        covered = lo
+        for a, b in sorted(rng):
+            if a <= covered < b:
+                covered = b
+        return covered >= hi
+
+    def mark(self, act):
+        self._entry(act)[1].append((act.coff, act.coff + act.C))
+
+    def writable(self, act):
+        """(grad view, accumulate flag) for an op that can either overwrite or add."""
+        gv = self.view(act)
+        acc = self.is_init(act)
+        if not acc:
+            _, rng = self._entry(act)
+            lo, hi = act.coff, act.coff + act.C
+            if any(a < hi and lo < b for a, b in rng):       # partial overlap: fall back to zero + accumulate
+                self.zero(act)
+                acc = True
+        return gv, acc
+
+    def zero(self, act):
+        gv = self.view(act)
+        gv.torch().zero_()
+        self.mark(act)
+        return gv
+
+    def add_only(self, act):
+        """grad view that holds valid numbers (zeros if nothing was written yet): for atomically-added gradients."""
+        if not self.is_init(act):
+            return self.zero(act)
+        return self.view(act)
+
+
+def _accumulate(G, act, src):
+    gv, acc = G.writable(act)
+    ops.add_into(gv, src, acc)
+    G.mark(act)
+
+
+def run_backward(model, ctx, dlevels, param_grads, seed=()):
+    """dlevels: 3 fp32 tensors [B, na, gs, gs, ch] (d loss / d level, strides 8, 16, 32).
+    param_grads: dict id(parameter) -> fp32 tensor (same shape) that receives += d loss / d parameter.
+    seed: optional [(activation, gradient Act)] pairs that pre-load output gradients (block-level tests)."""
+    from .blocks import Conv
+    tape = ctx.tape
+    assert tape is not None, "backward needs a training-mode forward"
+    dev = ctx.device
+    G = GradStore()
+    for act, g in seed:
+        ops.add_into(G.view(act), g, False)
+        G.mark(act)
+    sums = torch.zeros(2 * model._bn_channels + 16, dtype=torch.float32, device=dev)
+    soff = 0
+    head_i = 2
+    na, ch = model.na, model.ch
+
+    def pg(p):
+        return param_grads[id(p)]
+
+    for e in reversed(tape):
+        kind = e[0]
+        if kind == "head":
+            _, mod, x, y, mul = e
+            gl = dlevels[head_i]
+            head_i -= 1
+            conv = mod.conv[0]
+            Cout = na * ch
+            Cpad = (Cout + 7) // 8 * 8
+            if mul is not None:        # yolov7: y = im * (conv(x + ia) + b)   (model/neck.py:201,208,215)
+                model._implicit_head_grads(mod, gl, y, mul, param_grads)
+            dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias))
+            ops.conv2d_wgrad(x, dpre, Cout, 1, 1, pg(conv.weight))
+            w = conv.weight.data
+            if Cpad != Cout:
+                w = torch.cat((w, w.new_zeros(Cpad - Cout, *w.shape[1:])), 0)
+            wt = ops.pack_weights(w, transpose=True)
+            gx, acc = G.writable(x)
+            ops.conv2d_dgrad(dpre, wt, x.C, 1, 1, gx, acc)
+            G.mark(x)
+        elif kind == "conv":
+            _, mod, x, raw, out, residual, scale, shift, mean, invstd = e
+            if not G.is_init(out):
+                continue                                   # output never used downstream (cannot happen in these nets)
+            dout = G.view(out)
+            if residual is not None:                       # out = residual + act(bn(raw)): identity path
+                _accumulate(G, residual, dout)
+            bn = mod.conv[1]
+            C = mod.c2
+            ops.bn_act_bwd(dout, raw, scale, shift, mean, invstd, mod.act, sums[soff:soff + 2 * C], raw,
+                           pg(bn.weight), pg(bn.bias))     # d raw overwrites raw in place
+            soff += 2 * C
+            k = 1 if mod.stem else mod.k
+            ops.conv2d_wgrad(x, raw, C, k, mod.s, pg(mod.conv[0].weight), stem=mod.stem)
+            if not mod.stem:
+                gx, acc = G.writable(x)
+                ops.conv2d_dgrad(raw, mod.weight_t(), x.C, mod.k, mod.s, gx, acc)
+                G.mark(x)
+        elif kind == "repconv":
+            _, mod, x, rd, r1, out, affs = e
+            dout = G.view(out)
+            model._repconv_backward(mod, x, rd, r1, dout, affs, G, sums[soff:soff + 4 * mod.c2], param_grads)
+            soff += 4 * mod.c2
+        elif kind == "maxpool":
+            _, src, dst, k, s, p = e
+            if not G.is_init(dst):
+                continue
+            ops.maxpool_bwd(src, G.view(dst), k, s, p, G.add_only(src))
+        elif kind == "resize":
+            _, src, dst, factor = e
+            if not G.is_init(dst):
+                continue
+            gs, acc = G.writable(src)
+            if factor == 2:
+                ops.upsample2x_bwd(G.view(dst), gs, acc)
+            else:
+                ops.add_into(gs, G.view(dst), acc)
+            G.mark(src)
+        else:
+            raise RuntimeError(f"unknown tape entry {kind}")
+    ctx.tape = None            # the tape's raw buffers now hold gradients: a second backward would be wrong
+    return G

@@ -42,23 +42,26 @@ class Ctx:
         return s, q, ctr
 
 
+WEIGHT_EPOCH = [0]     # bumped by whoever rewrites parameters through raw pointers (TrainStep's SGD kernel)
+
+
 class _Packed:
     """bf16 [Cout][kh][kw][Cin] copy of an fp32 OIHW parameter, refreshed when the parameter changes."""
 
     def __init__(self):
         self.key, self.w = None, None
 
-    def get(self, p, stem=False):
-        key = (p.data_ptr(), p._version, p.device)
+    def get(self, p, stem=False, transpose=False):
+        key = (p.data_ptr(), p._version, p.device, WEIGHT_EPOCH[0])
         if key != self.key:
-            self.w = ops.pack_weights(p.data, stem=stem)
+            self.w = ops.pack_weights(p.data, stem=stem, transpose=transpose)
             self.key = key
         return self.w
 
 
 def _bn_eval_affine(bn, cache):
     key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-           bn.weight.data_ptr())
+           bn.weight.data_ptr(), WEIGHT_EPOCH[0], bn.num_batches_tracked.data_ptr())
     if cache.get("key") != key:
         scale = bn.weight.data.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
         cache["scale"], cache["shift"] = scale.contiguous(), (bn.bias.data.float() - bn.running_mean.float() * scale)
@@ -81,10 +84,14 @@ class Conv(nn.Module):
         self.conv = nn.ModuleList(layers)
         self.c1, self.c2, self.k, self.s, self.act, self.has_bn = c1, c2, k, s, activation, bn
         self.stem = (c1 == 3)
-        self._packed, self._affine = _Packed(), {}
+        self._packed, self._packed_t, self._affine = _Packed(), _Packed(), {}
 
     def weight(self):
         return self._packed.get(self.conv[0].weight, stem=self.stem)
+
+    def weight_t(self):
+        """[Cin][kh][kw][Cout] bf16 copy for dgrad."""
+        return self._packed_t.get(self.conv[0].weight, transpose=True)
 
     def forward(self, ctx, x, out=None, residual=None, head=None, head_scale=None, head_shift=None):
         w = self.weight()
@@ -92,7 +99,7 @@ class Conv(nn.Module):
         if head is not None:                       # biased linear 1x1 -> fp32 [B,na,gs,gs,ch]
             y = ops.conv2d(x, w, self.c2, k, self.s, scale=head_scale, shift=head_shift, act="linear", head=head)
             if ctx.tape is not None:
-                ctx.tape.append(("head", self, x, y))
+                ctx.tape.append(("head", self, x, y, head_scale))
             return y
         bn = self.conv[1]
         if not ctx.training:
@@ -316,6 +323,7 @@ class RepConv(nn.Module):
         self.rbr_1x1 = nn.Sequential(nn.Conv2d(c1, c2, 1, s, 0, bias=False), nn.BatchNorm2d(num_features=c2))
         self.c1, self.c2, self.k, self.s = c1, c2, k, s
         self._pd, self._p1, self._ad, self._a1 = _Packed(), _Packed(), {}, {}
+        self._pdt, self._p1t = _Packed(), _Packed()
 
     def forward(self, ctx, x, out=None):
         if self.rbr_identity is not None:

@@ -218,6 +218,13 @@ def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, d
     L.count(2)
 
 
+def act_bwd2(dout, x1, s1, b1, x2, s2, b2, act, ds):
+    L.check(L.lib().ryolo_act_bwd2(_vp(dout.ptr), dout.pitch, _vp(x1.ptr), x1.pitch, _tp(s1), _tp(b1), _vp(x2.ptr),
+                                   x2.pitch, _tp(s2), _tp(b2), ACT[act], _vp(ds.ptr), ds.pitch, x1.P, x1.C,
+                                   L.stream()))
+    L.count(1)
+
+
 def add_into(dst, src, accumulate):
     L.check(L.lib().ryolo_add_into(_vp(dst.ptr), dst.pitch, _vp(src.ptr), src.pitch, src.P, src.C,
                                    1 if accumulate else 0, L.stream()))
