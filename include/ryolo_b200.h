@@ -173,9 +173,9 @@ int ryolo_act_bwd2(const void* dout, long long dp, const void* x1, long long p1,
 /* dst (+)= src on bf16 NHWC views (gradient fan-in: residuals, concat slices, multiple consumers)            */
 int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, long long P, int C, int accumulate,
                    void* stream);
-/* nn.MaxPool2d backward: dx += route(dy) (first maximum of each window); dx must hold valid numbers          */
+/* nn.MaxPool2d backward: dx (+)= route(dy) (first maximum of each window); scratch = fp32[N*H*W*C]           */
 int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp, int N, int H, int W, int C, int k,
-                      int stride, int pad, void* dx, long long dxp, void* stream);
+                      int stride, int pad, void* dx, long long dxp, int accumulate, float* scratch, void* stream);
 /* nearest x2 upsample backward: dx[N,H,W,C] (+)= 2x2 block sums of dy[N,2H,2W,C]                             */
 int ryolo_upsample2x_bwd(const void* dy, long long dyp, int N, int H, int W, int C, void* dx, long long dxp,
                          int accumulate, void* stream);

@@ -15,8 +15,12 @@ class Net:
     """Evaluates the reference graph from a flat state_dict. train=True uses batch statistics
     (model/utils.py:16-17 BatchNorm2d in train mode) and records updated running stats."""
 
-    def __init__(self, sd, train, eps=1e-5, momentum=0.1):
+    def __init__(self, sd, train, eps=1e-5, momentum=0.1, emulate_bf16=False):
+        """emulate_bf16: round conv weights, raw conv outputs and block outputs to bf16 (straight-through
+        gradient), i.e. the storage points of the B200 stack, so that discontinuous derivatives (LeakyReLU's
+        kink, max-pool arg-max) are decided on the same numbers.  Arithmetic stays fp32 like the product's."""
         self.sd, self.train, self.eps, self.mom = sd, train, eps, momentum
+        self.q = (lambda t: t + (t.bfloat16().float() - t).detach()) if emulate_bf16 else (lambda t: t)
         self.new_stats = {}
         self.trace = None      # optional list of (module path, input, output) per Conv / RepConv
 
@@ -34,10 +38,12 @@ class Net:
         """model/utils.py:6-32 Conv = conv(+BN)(+act). `pre` is the module path of the Conv."""
         w = self.sd[pre + ".conv.0.weight"]
         bias = self.sd.get(pre + ".conv.0.bias")
-        y = F.conv2d(x, w, bias, stride=s, padding=(w.shape[2] - 1) // 2)
+        y = self.q(F.conv2d(x, self.q(w), bias, stride=s, padding=(w.shape[2] - 1) // 2))
         if (pre + ".conv.1.weight") in self.sd:
             y = self.bn(y, pre + ".conv.1")
         y = self.act(y, act)
+        if getattr(self, "_defer_round", False) is False:
+            y = self.q(y)
         if self.trace is not None:
             self.trace.append((pre, x, y))
         return y
@@ -54,8 +60,13 @@ class Net:
 
     # -- composites (model/utils.py) -----------------------------------------------------------
     def bottleneck(self, x, pre, act, add):
-        y = self.conv(self.conv(x, pre + ".cv1", act), pre + ".cv2", act)
-        return x + y if add else y
+        y = self.conv(x, pre + ".cv1", act)
+        if not add:
+            return self.conv(y, pre + ".cv2", act)
+        self._defer_round = True               # the product rounds once, after the residual add
+        y = self.conv(y, pre + ".cv2", act)
+        self._defer_round = False
+        return self.q(x + y)
 
     def csp(self, x, pre, n):  # utils.py:49-64
         y = self.conv(x, pre + ".cv1", "mish")
@@ -116,12 +127,12 @@ class Net:
         return torch.cat((x1, x2), 1)
 
     def repconv(self, x, pre):  # utils.py:189-215
-        d = self.bn(F.conv2d(x, self.sd[pre + ".rbr_dense.0.weight"], None, 1, 1), pre + ".rbr_dense.1")
-        o = self.bn(F.conv2d(x, self.sd[pre + ".rbr_1x1.0.weight"], None, 1, 0), pre + ".rbr_1x1.1")
+        d = self.bn(self.q(F.conv2d(x, self.q(self.sd[pre + ".rbr_dense.0.weight"]), None, 1, 1)), pre + ".rbr_dense.1")
+        o = self.bn(self.q(F.conv2d(x, self.q(self.sd[pre + ".rbr_1x1.0.weight"]), None, 1, 0)), pre + ".rbr_1x1.1")
         y = d + o
         if (pre + ".rbr_identity.weight") in self.sd:
             y = y + self.bn(x, pre + ".rbr_identity")
-        y = F.silu(y)
+        y = self.q(F.silu(y))
         if self.trace is not None:
             self.trace.append((pre, x, y))
         return y

@@ -70,7 +70,8 @@ SIGNATURES.update({
     "ryolo_bn_act_bwd": (_i32, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _i32, _ll, _i32, _vp, _vp, _ll, _vp, _vp, _vp]),
     "ryolo_act_bwd2": (_i32, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i32, _vp, _ll, _ll, _i32, _vp]),
     "ryolo_add_into": (_i32, [_vp, _ll, _vp, _ll, _ll, _i32, _i32, _vp]),
-    "ryolo_maxpool_bwd": (_i32, [_vp, _ll, _vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
+    "ryolo_maxpool_bwd": (_i32, [_vp, _ll, _vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _i32, _vp,
+                                 _vp]),
     "ryolo_upsample2x_bwd": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _vp, _ll, _i32, _vp]),
     "ryolo_head_grad_pack": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ryolo_sgd_step": (_i32, [_vp, _vp, _vp, _ll, _f32, _f32, _f32, _i32, _i32, _vp]),

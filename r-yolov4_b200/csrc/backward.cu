@@ -212,11 +212,12 @@ add_into_kernel(__nv_bfloat16* __restrict__ dst, long long dpitch, const __nv_bf
 }
 
 // MaxPool2d backward: every output routes its gradient to the first maximum of its window (row-major scan,
-// strict >).  Overlapping windows (stride < k) use bf16 atomics on dx (which must already hold valid numbers).
+// strict >).  Windows overlap (stride < k), so contributions are summed with fp32 atomics in a dense scratch
+// [N,H,W,C] (a 13x13 window can send 169 gradients to one element: bf16 accumulation would lose them).
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv_bfloat16* __restrict__ dy,
                    long long dyp, int N, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
-                   __nv_bfloat16* __restrict__ dx, long long dxp) {
+                   float* __restrict__ acc) {
   const int groups = C >> 3;
   const long long total = (long long)N * Ho * Wo * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -245,7 +246,30 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv
     unpack8(*reinterpret_cast<const uint4*>(dy + pix * dyp + c), g);
 #pragma unroll
     for (int j = 0; j < 8; j++)
-      if (am[j] >= 0) atomicAdd(dx + ((long long)n * H * W + am[j]) * dxp + c + j, __float2bfloat16_rn(g[j]));
+      if (am[j] >= 0) atomicAdd(acc + ((long long)n * H * W + am[j]) * C + c + j, g[j]);
+  }
+}
+
+// dst (bf16 view) (+)= acc (dense fp32 [P, C])
+__global__ void __launch_bounds__(256)
+add_f32_into_kernel(__nv_bfloat16* __restrict__ dst, long long dpitch, const float* __restrict__ acc, long long P, int C,
+                    int accumulate) {
+  const int groups = C >> 3;
+  const long long total = P * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long pix = i / groups;
+    const int c = (int)(i - pix * groups) * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(acc + pix * C + c);
+    const float4 a1 = *reinterpret_cast<const float4*>(acc + pix * C + c + 4);
+    float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (accumulate) {
+      float b[8];
+      unpack8(*reinterpret_cast<const uint4*>(dst + pix * dpitch + c), b);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] += b[j];
+    }
+    *reinterpret_cast<uint4*>(dst + pix * dpitch + c) = pack8(a);
   }
 }
 
@@ -396,16 +420,20 @@ int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, l
   return RYOLO_OK;
 }
 
-// dx must hold valid numbers on entry (zeros or a running gradient): the routed gradients are ADDED to it.
+// scratch: fp32 [N*H*W*C] (16-byte aligned); it is zeroed, filled with the routed gradients, then dx (+)= scratch.
 int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp, int N, int H, int W, int C, int k,
-                      int stride, int pad, void* dx, long long dxp, void* stream) {
-  RY_CHECK_ARG(C % 8 == 0 && k >= 1 && stride >= 1, "maxpool_bwd: bad arguments");
+                      int stride, int pad, void* dx, long long dxp, int accumulate, float* scratch, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && k >= 1 && stride >= 1 && scratch, "maxpool_bwd: bad arguments");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
-  if (total == 0) return RYOLO_OK;
-  maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, N, H, W, C, k, stride, pad, Ho, Wo,
-      (__nv_bfloat16*)dx, dxp);
+  const long long P = (long long)N * H * W;
+  if (P == 0) return RYOLO_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaMemsetAsync(scratch, 0, (size_t)P * C * sizeof(float), st);
+  if (total > 0)
+    maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, N,
+                                                            H, W, C, k, stride, pad, Ho, Wo, scratch);
+  add_f32_into_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((__nv_bfloat16*)dx, dxp, scratch, P, C, accumulate);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -73,6 +73,36 @@ def _accumulate(G, act, src):
     G.mark(act)
 
 
+def _implicit_head_grads(model, conv, gl, y, mul, param_grads):
+    """yolov7 head y = im * (conv(x + ia) + b): gradients of ImplicitM / ImplicitA (model/utils.py:163-186)."""
+    neck = model.neck
+    i = {id(getattr(neck, f"conv{4 + j}")): j for j in (1, 2, 3)}[id(conv)]
+    ia, im = getattr(neck, f"ia{i}"), getattr(neck, f"im{i}")
+    B, na, H, W, ch = gl.shape
+    d_im = (gl * y).sum((0, 2, 3)).reshape(-1) / mul                     # d/d im_c = sum dY * pre_c
+    param_grads[id(im.implicit)].add_(d_im.view_as(im.implicit))
+    dpre_sum = (gl.sum((0, 2, 3)).reshape(-1) * mul)                      # sum over pixels of d pre
+    w = conv.conv[0].weight.data.float().flatten(1)                       # [Cout, Cin]
+    param_grads[id(ia.implicit)].add_((w.t() @ dpre_sum).view_as(ia.implicit))
+
+def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads):
+    """out = silu(bn_d(conv3x3(x)) + bn_1(conv1x1(x)))   (model/utils.py:209-215)."""
+    C = mod.c2
+    ds = ops.Act.empty(rd.N, rd.H, rd.W, C, rd.buf.device)
+    ops.act_bwd2(dout, rd, affs[0][0], affs[0][1], r1, affs[1][0], affs[1][1], "swish", ds)
+    first = True
+    for raw, aff, seq, k, packed_t in ((rd, affs[0], mod.rbr_dense, mod.k, mod._pdt), (r1, affs[1], mod.rbr_1x1, 1, mod._p1t)):
+        bn = seq[1]
+        ops.bn_act_bwd(ds, raw, aff[0], aff[1], aff[2], aff[3], "linear", sums[:2 * C] if first else sums[2 * C:],
+                     raw, param_grads[id(bn.weight)], param_grads[id(bn.bias)])
+        ops.conv2d_wgrad(x, raw, C, k, mod.s, param_grads[id(seq[0].weight)])
+        gx, acc = G.writable(x)
+        ops.conv2d_dgrad(raw, packed_t.get(seq[0].weight, transpose=True), x.C, k, mod.s, gx, acc)
+        G.mark(x)
+        first = False
+
+
+
 def run_backward(model, ctx, dlevels, param_grads, seed=()):
     """dlevels: 3 fp32 tensors [B, na, gs, gs, ch] (d loss / d level, strides 8, 16, 32).
     param_grads: dict id(parameter) -> fp32 tensor (same shape) that receives += d loss / d parameter.
@@ -103,7 +133,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             Cout = na * ch
             Cpad = (Cout + 7) // 8 * 8
             if mul is not None:        # yolov7: y = im * (conv(x + ia) + b)   (model/neck.py:201,208,215)
-                model._implicit_head_grads(mod, gl, y, mul, param_grads)
+                _implicit_head_grads(model, mod, gl, y, mul, param_grads)
             dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias))
             ops.conv2d_wgrad(x, dpre, Cout, 1, 1, pg(conv.weight))
             w = conv.weight.data
@@ -134,13 +164,15 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
         elif kind == "repconv":
             _, mod, x, rd, r1, out, affs = e
             dout = G.view(out)
-            model._repconv_backward(mod, x, rd, r1, dout, affs, G, sums[soff:soff + 4 * mod.c2], param_grads)
+            _repconv_backward(mod, x, rd, r1, dout, affs, G, sums[soff:soff + 4 * mod.c2], param_grads)
             soff += 4 * mod.c2
         elif kind == "maxpool":
             _, src, dst, k, s, p = e
             if not G.is_init(dst):
                 continue
-            ops.maxpool_bwd(src, G.view(dst), k, s, p, G.add_only(src))
+            gs, acc = G.writable(src)
+            ops.maxpool_bwd(src, G.view(dst), k, s, p, gs, acc)
+            G.mark(src)
         elif kind == "resize":
             _, src, dst, factor = e
             if not G.is_init(dst):

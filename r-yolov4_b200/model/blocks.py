@@ -167,6 +167,21 @@ class C5(nn.Module):
         return self.cv5(ctx, x, out=out)
 
 
+def _spp_pools(ctx, src, dsts):
+    """5/9/13 stride-1 max-pools of `src`.  Inference cascades 5x5 pools (pool9 = pool5 o pool5, pool13 =
+    pool5 o pool9: identical values, 3.7x fewer loads).  Training pools directly so that the backward pass routes
+    gradients to the same arg-max positions as the reference's three independent pools even when values tie."""
+    if ctx.tape is None:
+        cur = src
+        for dst, _ in dsts:
+            ops.maxpool(cur, 5, 1, 2, out=dst)
+            cur = dst
+        return
+    for dst, k in dsts:
+        ops.maxpool(src, k, 1, k // 2, out=dst)
+        ctx.tape.append(("maxpool", src, dst, k, 1, k // 2))
+
+
 class SPP(nn.Module):
     def __init__(self, c1, c2):
         super().__init__()
@@ -187,13 +202,7 @@ class SPP(nn.Module):
         cat = ctx.new(x.N, x.H, x.W, 4 * c_)                      # order m3, m2, m1, x  (model/utils.py:241)
         src = cat.slice(3 * c_, c_)
         self.cv3(ctx, self.cv2(ctx, self.cv1(ctx, x)), out=src)
-        # pool9 = pool5(pool5), pool13 = pool5(pool9): exact for max with -inf padding, 3.7x fewer loads
-        for i in (2, 1, 0):
-            dst = cat.slice(i * c_, c_)
-            ops.maxpool(src, 5, 1, 2, out=dst)
-            if ctx.tape is not None:
-                ctx.tape.append(("maxpool", src, dst, 5, 1, 2))
-            src = dst
+        _spp_pools(ctx, src, [(cat.slice(2 * c_, c_), 5), (cat.slice(c_, c_), 9), (cat.slice(0, c_), 13)])
         return self.cv6(ctx, self.cv5(ctx, self.cv4(ctx, cat)), out=out)
 
 
@@ -217,12 +226,7 @@ class SPPCSPC(nn.Module):
         src = cat4.slice(0, c_)
         self.cv4(ctx, self.cv3(ctx, self.cv1(ctx, x)), out=src)
         assert self.ks == (5, 9, 13)
-        for i in range(3):                                         # cascaded 5x5 pools (see SPP)
-            dst = cat4.slice((i + 1) * c_, c_)
-            ops.maxpool(src, 5, 1, 2, out=dst)
-            if ctx.tape is not None:
-                ctx.tape.append(("maxpool", src, dst, 5, 1, 2))
-            src = dst
+        _spp_pools(ctx, src, [(cat4.slice((i + 1) * c_, c_), k) for i, k in enumerate(self.ks)])
         cat2 = ctx.new(x.N, x.H, x.W, 2 * c_)
         self.cv6(ctx, self.cv5(ctx, cat4), out=cat2.slice(0, c_))
         self.cv2(ctx, x, out=cat2.slice(c_, c_))

@@ -109,35 +109,6 @@ class Yolo(nn.Module):
         self._flat, self._flat_grad, self._grad_views = flat, grad, views
         return flat, grad
 
-    def _implicit_head_grads(self, conv, gl, y, mul, param_grads):
-        """yolov7 head y = im * (conv(x + ia) + b): gradients of ImplicitM / ImplicitA (model/utils.py:163-186)."""
-        neck = self.neck
-        i = {id(getattr(neck, f"conv{4 + j}")): j for j in (1, 2, 3)}[id(conv)]
-        ia, im = getattr(neck, f"ia{i}"), getattr(neck, f"im{i}")
-        B, na, H, W, ch = gl.shape
-        d_im = (gl * y).sum((0, 2, 3)).reshape(-1) / mul                     # d/d im_c = sum dY * pre_c
-        param_grads[id(im.implicit)].add_(d_im.view_as(im.implicit))
-        dpre_sum = (gl.sum((0, 2, 3)).reshape(-1) * mul)                      # sum over pixels of d pre
-        w = conv.conv[0].weight.data.float().flatten(1)                       # [Cout, Cin]
-        param_grads[id(ia.implicit)].add_((w.t() @ dpre_sum).view_as(ia.implicit))
-
-    def _repconv_backward(self, mod, x, rd, r1, dout, affs, G, sums, param_grads):
-        """out = silu(bn_d(conv3x3(x)) + bn_1(conv1x1(x)))   (model/utils.py:209-215)."""
-        from .. import ops as O
-        C = mod.c2
-        ds = O.Act.empty(rd.N, rd.H, rd.W, C, rd.buf.device)
-        O.act_bwd2(dout, rd, affs[0][0], affs[0][1], r1, affs[1][0], affs[1][1], "swish", ds)
-        first = True
-        for raw, aff, seq, k, packed_t in ((rd, affs[0], mod.rbr_dense, mod.k, mod._pdt), (r1, affs[1], mod.rbr_1x1, 1, mod._p1t)):
-            bn = seq[1]
-            O.bn_act_bwd(ds, raw, aff[0], aff[1], aff[2], aff[3], "linear", sums[:2 * C] if first else sums[2 * C:],
-                         raw, param_grads[id(bn.weight)], param_grads[id(bn.bias)])
-            O.conv2d_wgrad(x, raw, C, k, mod.s, param_grads[id(seq[0].weight)])
-            gx, acc = G.writable(x)
-            O.conv2d_dgrad(raw, packed_t.get(seq[0].weight, transpose=True), x.C, k, mod.s, gx, acc)
-            G.mark(x)
-            first = False
-
     @staticmethod
     def _make_anchors(strides, anchors):
         return [[[a[i] / s, a[i + 1] / s] for i in range(0, len(a), 2)] for s, a in zip(strides, anchors)]

@@ -231,10 +231,11 @@ def add_into(dst, src, accumulate):
     L.count(1)
 
 
-def maxpool_bwd(x, dy, k, stride, pad, dx):
+def maxpool_bwd(x, dy, k, stride, pad, dx, accumulate):
+    scratch = torch.empty(x.P * x.C, dtype=torch.float32, device=x.buf.device)
     L.check(L.lib().ryolo_maxpool_bwd(_vp(x.ptr), x.pitch, _vp(dy.ptr), dy.pitch, x.N, x.H, x.W, x.C, k, stride, pad,
-                                      _vp(dx.ptr), dx.pitch, L.stream()))
-    L.count(1)
+                                      _vp(dx.ptr), dx.pitch, 1 if accumulate else 0, _tp(scratch), L.stream()))
+    L.count(2)
 
 
 def upsample2x_bwd(dy, dx, accumulate):
