@@ -90,9 +90,12 @@ enum { RYOLO_OUT_NHWC_BF16 = 0, RYOLO_OUT_HEAD_F32 = 1 };
 /* Fused train-mode BatchNorm2d statistics (model/utils.py:16-17): the raw-output conv epilogue accumulates the
  * per-channel sum / sum of squares of what it stores, and the last CTA to finish turns them into
  * scale = gamma*rsqrt(var+eps), shift = beta-mean*scale, updates the running statistics (momentum, unbiased
- * variance) and num_batches_tracked.  sum, sumsq (fp32[Cout]) and counter (u32) must be zero on entry.      */
+ * variance) and num_batches_tracked.  The reduction order is fixed (bit-reproducible run to run, like the
+ * reference's cudnn.deterministic).  partial = fp32 scratch of RYOLO_BN_PARTIAL_ROWS*2*Cout floats (no init
+ * needed); counter (u32) must be zero on entry; sum / sumsq (fp32[Cout]) are optional outputs.               */
+#define RYOLO_BN_PARTIAL_ROWS 160   /* >= number of SMs (one partial row per persistent CTA) */
 typedef struct ryolo_bn_fuse {
-  float* sum; float* sumsq; unsigned int* counter;
+  float* partial; float* sum; float* sumsq; unsigned int* counter;
   const float* gamma; const float* beta;
   float* running_mean; float* running_var; long long* num_batches;     /* nullable */
   float eps, momentum;

@@ -42,7 +42,7 @@ _f32p, _dbl, _ll = ctypes.POINTER(_f32), ctypes.c_double, ctypes.c_longlong
 
 class BnFuse(ctypes.Structure):
     """struct ryolo_bn_fuse (include/ryolo_b200.h)."""
-    _fields_ = [("sum", _vp), ("sumsq", _vp), ("counter", _vp), ("gamma", _vp), ("beta", _vp), ("running_mean", _vp),
+    _fields_ = [("partial", _vp), ("sum", _vp), ("sumsq", _vp), ("counter", _vp), ("gamma", _vp), ("beta", _vp), ("running_mean", _vp),
                 ("running_var", _vp), ("num_batches", _vp), ("eps", _f32), ("momentum", _f32), ("scale", _vp),
                 ("shift", _vp), ("save_mean", _vp), ("save_invstd", _vp)]
 

@@ -149,7 +149,7 @@ struct ConvKernelParams {
   const __nv_bfloat16* residual;
   long long res_cpitch;
   int head_na, head_ch;
-  ryolo_bn_fuse bn;        // bn.sum != nullptr: fused train-mode BatchNorm statistics + finalize (EPI_RAW only)
+  ryolo_bn_fuse bn;        // bn.partial != nullptr: fused train-mode BatchNorm statistics + finalize (EPI_RAW only)
   double bn_count;         // N*Ho*Wo
 };
 
@@ -276,7 +276,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    const bool do_stats = (EPI == EPI_RAW) && (p.bn.sum != nullptr);
+    const bool do_stats = (EPI == EPI_RAW) && (p.bn.partial != nullptr);
     float st_s[8], st_q[8];                  // per-lane channel partial sums, one slot per 32-channel chunk
 #pragma unroll
     for (int i = 0; i < 8; i++) { st_s[i] = 0.f; st_q[i] = 0.f; }
@@ -400,14 +400,28 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
     if (do_stats) {
-      // flush this CTA's partial sums; the last CTA to arrive turns them into scale/shift + running stats
+      // Deterministic reduction (the reference runs with cudnn.deterministic, train.py:24): the 8 epilogue warps
+      // combine through smem in a fixed order, every CTA stores ONE partial row, and the last CTA to arrive sums the
+      // rows of each channel in CTA order before turning them into scale/shift + running statistics.
       const int n0c = (blockIdx.x % p.n_tiles) * BN;
+      float* comb = s_tr;                                  // reused as [8 warps][2][256]
+      asm volatile("bar.sync 1, 256;" ::: "memory");       // every warp is done with its transpose tile
 #pragma unroll
       for (int ci = 0; ci < 8; ci++) {
-        const int c = n0c + ci * 32 + lane;
-        if (ci * 32 < BN && c < p.Cout) {
-          atomicAdd(p.bn.sum + c, st_s[ci]);
-          atomicAdd(p.bn.sumsq + c, st_q[ci]);
+        if (ci * 32 < BN) {
+          comb[((warp - 2) * 2 + 0) * 256 + ci * 32 + lane] = st_s[ci];
+          comb[((warp - 2) * 2 + 1) * 256 + ci * 32 + lane] = st_q[ci];
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      float* prow = p.bn.partial + (size_t)blockIdx.x * 2 * p.Cout;
+      for (int i = et; i < 2 * BN; i += 256) {
+        const int q = i / BN, cl = i - q * BN, c = n0c + cl;
+        if (c < p.Cout) {
+          float a = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; w++) a += comb[(w * 2 + q) * 256 + cl];
+          prow[(size_t)q * p.Cout + c] = a;
         }
       }
       __threadfence();
@@ -418,8 +432,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __threadfence();
         if (et == 0 && p.bn.num_batches) *p.bn.num_batches += 1;
         for (int c = et; c < p.Cout; c += 256) {
-          const double mean = (double)__ldcg(p.bn.sum + c) / p.bn_count;
-          double var = (double)__ldcg(p.bn.sumsq + c) / p.bn_count - mean * mean;
+          float fs = 0.f, fq = 0.f;
+          for (int b = c / BN; b < (int)gridDim.x; b += p.n_tiles) {   // CTAs whose n-tile holds channel c
+            fs += __ldcg(p.bn.partial + ((size_t)b * 2 + 0) * p.Cout + c);
+            fq += __ldcg(p.bn.partial + ((size_t)b * 2 + 1) * p.Cout + c);
+          }
+          if (p.bn.sum) p.bn.sum[c] = fs;
+          if (p.bn.sumsq) p.bn.sumsq[c] = fq;
+          const double mean = (double)fs / p.bn_count;
+          double var = (double)fq / p.bn_count - mean * mean;
           if (var < 0.0) var = 0.0;
           const float invstd = (float)(1.0 / sqrt(var + (double)p.bn.eps));
           const float sc = p.bn.gamma[c] * invstd;
@@ -537,8 +558,8 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   if (d->bn) {
     RY_CHECK_ARG(d->out_mode == RYOLO_OUT_NHWC_BF16 && !d->scale && !d->shift && d->act == RYOLO_ACT_LINEAR &&
                      !d->residual, "conv: fused BatchNorm statistics need the raw (no scale/shift/act/residual) epilogue");
-    RY_CHECK_ARG(d->bn->sum && d->bn->sumsq && d->bn->counter && d->bn->gamma && d->bn->beta && d->bn->scale &&
-                     d->bn->shift, "conv: incomplete ryolo_bn_fuse");
+    RY_CHECK_ARG(d->bn->partial && d->bn->counter && d->bn->gamma && d->bn->beta && d->bn->scale && d->bn->shift,
+                 "conv: incomplete ryolo_bn_fuse");
     p->bn = *d->bn;
   }
   if (d->out_mode == RYOLO_OUT_NHWC_BF16) {

@@ -25,21 +25,19 @@ class Ctx:
         self.device = device
         self.model = model
         self.tape = [] if training else None
-        n = model._bn_channels
-        self._stats = torch.zeros(2 * n, dtype=torch.float32, device=device) if training else None
+        # one scratch for the per-CTA BN partial rows (layers run back to back on one stream) + a zeroed counter each
+        self._partial = torch.empty(ops.BN_PARTIAL_ROWS * 2 * 2048, dtype=torch.float32, device=device) \
+            if training else None
         self._counters = torch.zeros(model._bn_layers, dtype=torch.int32, device=device) if training else None
-        self._stat_off, self._ctr_off = 0, 0
+        self._ctr_off = 0
 
     def new(self, N, H, W, C):
         return Act.empty(N, H, W, C, self.device)
 
     def stat_slot(self, C):
-        s = self._stats[self._stat_off:self._stat_off + C]
-        q = self._stats[self._stat_off + C:self._stat_off + 2 * C]
-        self._stat_off += 2 * C
         ctr = self._counters[self._ctr_off:self._ctr_off + 1]
         self._ctr_off += 1
-        return s, q, ctr
+        return self._partial, ctr
 
 
 WEIGHT_EPOCH = [0]     # bumped by whoever rewrites parameters through raw pointers (TrainStep's SGD kernel)
@@ -106,11 +104,11 @@ class Conv(nn.Module):
             scale, shift = _bn_eval_affine(bn, self._affine)
             return ops.conv2d(x, w, self.c2, k, self.s, out=out, scale=scale, shift=shift, act=self.act,
                               residual=residual)
-        s, q, ctr = ctx.stat_slot(self.c2)
+        part, ctr = ctx.stat_slot(self.c2)
         aff = torch.empty(4 * self.c2, dtype=torch.float32, device=ctx.device)
         scale, shift, mean, invstd = aff[:self.c2], aff[self.c2:2 * self.c2], aff[2 * self.c2:3 * self.c2], \
             aff[3 * self.c2:]
-        raw = ops.conv2d(x, w, self.c2, k, self.s, bn=ops.bn_fuse(s, q, ctr, bn, scale, shift, mean, invstd))
+        raw = ops.conv2d(x, w, self.c2, k, self.s, bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
         if out is None:
             out = ctx.new(raw.N, raw.H, raw.W, self.c2)
         ops.scale_shift_act(raw, scale, shift, self.act, out, residual=residual)
@@ -343,10 +341,10 @@ class RepConv(nn.Module):
             return ops.scale_shift_act(rd, sd, bd, "swish", out, x2=r1, scale2=s1, shift2=b1)
         affs, raws = [], []
         for wgt, kk, bn in ((wd, self.k, self.rbr_dense[1]), (w1, 1, self.rbr_1x1[1])):
-            s, q, ctr = ctx.stat_slot(self.c2)
+            part, ctr = ctx.stat_slot(self.c2)
             aff = torch.empty(4, self.c2, dtype=torch.float32, device=ctx.device)
             raws.append(ops.conv2d(x, wgt, self.c2, kk, self.s,
-                                   bn=ops.bn_fuse(s, q, ctr, bn, aff[0], aff[1], aff[2], aff[3])))
+                                   bn=ops.bn_fuse(part, ctr, bn, aff[0], aff[1], aff[2], aff[3])))
             affs.append(aff)
         rd, r1 = raws
         ops.scale_shift_act(rd, affs[0][0], affs[0][1], "swish", out, x2=r1, scale2=affs[1][0], shift2=affs[1][1])

@@ -76,10 +76,15 @@ def out_hw(H, W, k, s):
     return (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
 
 
-def bn_fuse(sum_, sumsq, counter, bn, scale, shift, save_mean=None, save_invstd=None):
-    """ryolo_bn_fuse for an nn.BatchNorm2d `bn` (fused statistics + finalize in the conv epilogue)."""
+BN_PARTIAL_ROWS = 160   # RYOLO_BN_PARTIAL_ROWS
+
+
+def bn_fuse(partial, counter, bn, scale, shift, save_mean=None, save_invstd=None):
+    """ryolo_bn_fuse for an nn.BatchNorm2d `bn` (fused statistics + finalize in the conv epilogue).
+    partial: fp32 scratch with >= BN_PARTIAL_ROWS*2*C elements; counter: zeroed int32[1]."""
     f = L.BnFuse()
-    f.sum, f.sumsq, f.counter = sum_.data_ptr(), sumsq.data_ptr(), counter.data_ptr()
+    assert partial.numel() >= BN_PARTIAL_ROWS * 2 * bn.num_features
+    f.partial, f.sum, f.sumsq, f.counter = partial.data_ptr(), None, None, counter.data_ptr()
     f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
     f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
     f.num_batches = bn.num_batches_tracked.data_ptr()

@@ -108,19 +108,19 @@ def test_autograd_dropin_equals_native_and_reaches_all_params(ver, mode, nc):
     levels = m(img, training=True)
     it, dl = crit.value_and_grad(levels, tg)
     m.backward(dl)
-    # Two separate train-mode forwards: fp32 atomic summation order differs between runs and the randomly
-    # initialised stack amplifies it (see test_gpu_model.py), so the two paths are compared statistically.
-    assert abs(float(it[4]) - items["total_loss"]) <= 2e-2 * abs(items["total_loss"])
-    # (gradients of early layers back-propagate through ~100 randomly initialised layers and decorrelate between
-    # runs; the layers next to the heads are compared tensor by tensor)
-    named = list(m.named_parameters())
-    tail = [k for k, _ in named if k.split(".")[1] in ("conv37", "conv38", "conv29", "conv30", "conv21", "conv22",
-                                                      "repVgg3", "conv7", "im3", "ia3", "repVgg1", "conv5")]
-    assert len(tail) >= 6
-    for k in tail:
-        a, b = auto[k].flatten().double(), dict(named)[k].grad.flatten().double()
-        cos = float(torch.dot(a, b) / (a.norm() * b.norm()).clamp_min(1e-30))
-        assert cos > 0.9, (k, cos)
+    # The forward pass is bit-reproducible (fixed-order BN reductions), so both paths see the same activations;
+    # the backward differs only by the summation order of fp32 atomics (wgrad split-K, BN-backward sums).
+    assert float(it[4]) == items["total_loss"]
+    for k, p in m.named_parameters():
+        assert _l2(p.grad, auto[k]) < 1e-2, (k, _l2(p.grad, auto[k]))
+
+
+def test_forward_is_bit_reproducible():
+    R, m, img, tg, crit = _model_and_batch("yolov4", "csl", 2)
+    a = [l.clone() for l in m(img, training=True)]
+    b = m(img, training=True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
 
 
 def test_train_steps_reduce_loss_and_keep_state_dict_contract():
