@@ -1,11 +1,13 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark of the B200-native R-YOLOv4 hot path (contract: task prompt ④).
 
-Workload at every N: BASELINE.json configs[1] — synthetic 800x800, bs=32 PER GPU, yolov4 / csl / nc=2,
-train-mode forward (batch-statistics BatchNorm) + ComputeCSLLoss value and head gradients, random
-weights (reference init, train.py:28-33).  One "step" = one batch of 32 images through
-Yolo.forward(training=True) and compute_loss.  N>1 runs one rank per GPU on its own shard of the global
-batch (weak scaling); forward+loss has no exchange step, so no collective sits on the data path.
+Workload at every N (default): the model/size of BASELINE.json configs[1] — synthetic 800x800, bs=32 PER GPU,
+yolov4 / csl / nc=2, random weights (reference init, train.py:28-33) — driven through ONE FULL TRAINING STEP
+(train.py:184-202): train-mode forward (batch-statistics BatchNorm), ComputeCSLLoss value + gradient, conv-stack
+backward (dgrad + wgrad), one NCCL all-reduce of the flat fp32 gradients when N>1, SGD(momentum .937, nesterov).
+It is a superset of configs[1]'s "forward+loss", whose img/s is reported next to it (config.fwd_loss_img_s).
+N>1: one rank per GPU, its own 32-image shard of the global batch (weak scaling).
+--workload train_v7 runs BASELINE configs[2] (yolov7 / csl / nc=16) the same way.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
@@ -31,8 +33,14 @@ CFG = dict(anchors=[[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 1
            angles=[-90, -60, -30, 0, 30, 60])                                   # data/hyp.yaml:2-7
 HYP = dict(fl_gamma=0.0, box=0.05, obj=1.0, obj_pw=1.0, cls=0.5, cls_pw=1.0)   # data/hyp.yaml:11-17
 S, BS, NC, PER_IMG = 800, 32, 2, 100
-GFLOP_PER_IMG = 218.14        # 2*MAC over the 110 convs, yolov4/csl/nc2 @800^2
-METRIC, UNIT = "fwd+loss img/s, yolov4 csl nc=2, 800x800, bs=32 per GPU (train-mode BN, synthetic)", "img/s"
+# 2*MAC over the convs @800^2: forward; dgrad = forward minus the stem; wgrad = forward
+WORKLOADS = {
+    "train_v4": dict(ver="yolov4", nc=2, fwd_gflop=218.14, stem_gflop=1.106,
+                     name="yolov4/csl/nc2 800x800 full train step (fwd + CSL loss + bwd + SGD)"),
+    "train_v7": dict(ver="yolov7", nc=16, fwd_gflop=168.38, stem_gflop=1.106,
+                     name="yolov7/csl/nc16 800x800 full train step (fwd + CSL loss + bwd + SGD)"),
+}
+METRIC, UNIT = "training-step img/s, 800x800, bs=32 per GPU (synthetic, random weights)", "img/s"
 
 
 def weights_init_normal(m):                                                   # train.py:28-33
@@ -51,7 +59,7 @@ def gaussian_label(label, num_class=180, u=0, sig=6.0):
     return np.concatenate([y[i:], y[:i]], axis=0)
 
 
-def make_targets(seed, bs):
+def make_targets(seed, bs, nc=NC):
     g = np.random.default_rng(seed)
     rows = []
     for b in range(bs):
@@ -59,7 +67,7 @@ def make_targets(seed, bs):
             w = g.uniform(0.02, 0.15)
             h = min(w * g.uniform(1, 3), 0.9)
             th = g.uniform(-np.pi / 2, np.pi / 2 - 1e-3)
-            rows.append([b, float(g.integers(0, NC)), g.uniform(0.05, 0.95), g.uniform(0.05, 0.95), w, h, th]
+            rows.append([b, float(g.integers(0, nc)), g.uniform(0.05, 0.95), g.uniform(0.05, 0.95), w, h, th]
                         + list(gaussian_label(th * 180 / np.pi + 90)))
     return torch.tensor(np.array(rows), dtype=torch.float32)
 
@@ -116,44 +124,53 @@ class _M:
 
 
 # ------------------------------------------------------------------------------------ CPU arm
-def cpu_arm(steps, warmup, sample_imgs=2):
-    """Oracle port of the reference forward+loss on the host cores.  Returns img/s and a description."""
+def cpu_arm(wl, steps, warmup, sample_imgs=2):
+    """Oracle port of the reference training step (forward, CSL loss, autograd backward, SGD) on the host cores.
+    Returns img/s and a description of the bounded sample."""
     from oracle import hotpath as hp
     from oracle import model_cpu
     import ryolo_b200 as R
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     torch.manual_seed(42)
-    m = R.Yolo(NC, CFG, "csl", "yolov4")
+    m = R.Yolo(wl["nc"], CFG, "csl", wl["ver"])
     m.apply(weights_init_normal)
-    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    pnames = {k for k, _ in m.named_parameters()}
+    sd = {k: v.clone().requires_grad_(k in pnames) for k, v in m.state_dict().items()}
+    params = [sd[k] for k in sd if k in pnames]
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.937, nesterov=True)
     img = torch.rand(sample_imgs, 3, S, S)
-    tg = make_targets(0, sample_imgs)
+    tg = make_targets(0, sample_imgs, wl["nc"])
     an = hp.make_anchors(CFG["anchors"])
     ts = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
-        levels, _, _ = model_cpu.forward(sd, img, "yolov4", "csl", NC, train=True, decode=False)
-        lv = [l.requires_grad_(True) for l in levels]
-        loss, _ = hp.csl_loss(lv, tg, an, NC, HYP)
+        opt.zero_grad()
+        levels, _, stats = model_cpu.forward(sd, img, wl["ver"], "csl", wl["nc"], train=True, decode=False)
+        loss, _ = hp.csl_loss(levels, tg, an, wl["nc"], HYP)
         loss.backward()
+        opt.step()
+        with torch.no_grad():
+            for k, v in stats.items():
+                sd[k].copy_(v)
         dt = time.perf_counter() - t0
         if i >= warmup:
             ts.append(dt)
-    return sample_imgs / float(np.mean(ts)), cores, f"{sample_imgs} of the {BS} images per step, {steps} step(s), torch CPU fp32"
+    return sample_imgs / float(np.mean(ts)), cores, \
+        f"{sample_imgs} of the {BS} images per step, {steps} timed step(s), torch CPU fp32 ({cores} threads)"
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    wl = WORKLOADS[args.workload if args.workload != "fwd_loss" else "train_v4"]
     steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
-    v, cores, sample = cpu_arm(steps, warm)
+    v, cores, sample = cpu_arm(wl, steps, warm)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 * 2 / v, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "yolov4/csl/nc2 800x800 train-mode forward + CSL loss (value+head grads)",
-                       "per_gpu_batch": BS, "sample": sample},
+            "config": {"workload": wl["name"], "per_gpu_batch": BS, "sample": sample},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -173,22 +190,19 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L.check(L.lib().ryolo_check_device(local))
+    wl = WORKLOADS[args.workload if args.workload != "fwd_loss" else "train_v4"]
+    nc = wl["nc"]
     torch.manual_seed(42)
-    model = R.Yolo(NC, CFG, "csl", "yolov4")
+    model = R.Yolo(nc, CFG, "csl", wl["ver"])
     model.apply(weights_init_normal)
     model = model.to(dev).train()
     crit = R.ComputeCSLLoss(model, HYP)
     crit.sync_items = False
+    trainer = R.TrainStep(model, crit, lr=0.01, momentum=0.937, nesterov=True)      # train.py:156
     host_imgs = [torch.rand(BS, 3, S, S).pin_memory() for _ in range(2)]
-    host_tg = [make_targets(rank * 2 + i, BS).pin_memory() for i in range(2)]
+    host_tg = [make_targets(rank * 2 + i, BS, nc).pin_memory() for i in range(2)]
     dev_imgs = [h.to(dev) for h in host_imgs]
     dev_tg = [h.to(dev) for h in host_tg]
-
-    def step(imgs, tg):
-        levels = model(imgs, training=True)
-        lv = [l.requires_grad_(True) for l in levels]
-        loss, _ = crit(lv, tg)
-        return loss
 
     def barrier():
         if world > 1:
@@ -207,12 +221,13 @@ def run_gpu(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    # ---- device-resident arm ("value")
+    # ---- device-resident arm ("value"): full training steps
     def resident(n):
         for i in range(n):
-            step(dev_imgs[i & 1], dev_tg[i & 1])
+            trainer(dev_imgs[i & 1], dev_tg[i & 1])
 
-    resident(max(args.warmup, 3))
+    warm = max(args.warmup, 3)
+    resident(warm)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = L.LAUNCHES[0]
     ops.PROFILE = []
@@ -220,8 +235,19 @@ def run_gpu(args):
     prof, ops.PROFILE = ops.PROFILE, None
     launches = L.LAUNCHES[0] - l0
     clocks = sampler.stop() if sampler else None
-    conv_ms = sum(a.elapsed_time(b) for _, a, b in prof) / args.steps
-    n_conv = len(prof) // args.steps
+    tc_ms = {}
+    for tag, a, b in prof:
+        tc_ms[tag[0]] = tc_ms.get(tag[0], 0.0) + a.elapsed_time(b) / args.steps
+
+    # ---- forward + loss only (BASELINE configs[1] wording), same model and inputs
+    def fwd_loss(n):
+        for i in range(n):
+            lv = model(dev_imgs[i & 1], training=True)
+            crit.value_and_grad(lv, dev_tg[i & 1])
+
+    fwd_loss(2)
+    ms_fl = timed(fwd_loss, min(args.steps, 5))
+    fl_steps = min(args.steps, 5)
 
     # ---- end-to-end arm: pinned host -> device copies (prefetched on a side stream) + loss read-back
     copy_stream = torch.cuda.Stream(dev)
@@ -249,9 +275,9 @@ def run_gpu(args):
             if i + 1 < n:
                 upload(i + 1)
             cur.wait_event(ready[s])
-            step(stage_i[s], stage_t[s])
+            items = trainer(stage_i[s], stage_t[s])
             freed[s].record(cur)
-            out_host.copy_(crit.last_items_device, non_blocking=True)
+            out_host.copy_(items, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         return float(out_host[4])
 
@@ -261,28 +287,36 @@ def run_gpu(args):
     if rank == 0:
         pk, pk_src = peaks()
         value = world * BS * args.steps / ms_total * 1e3
-        tflops = GFLOP_PER_IMG * BS / conv_ms                      # GFLOP / ms == TFLOP/s
+        gflop = (3 * wl["fwd_gflop"] - wl["stem_gflop"]) * BS          # fwd + dgrad (no stem) + wgrad, per step
+        tc_total = sum(tc_ms.values())
+        tflops = gflop / tc_total                                         # GFLOP / ms == TFLOP/s
         peak = pk["bf16_tflops_sustained"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "yolov4/csl/nc2 800x800 train-mode forward + CSL loss (value+head grads)",
-                       "per_gpu_batch": BS, "global_batch": BS * world, "targets_per_img": PER_IMG,
-                       "parallelism": f"dp{world} (independent shards, no data-path collective)",
+            "config": {"workload": wl["name"], "per_gpu_batch": BS, "global_batch": BS * world,
+                       "targets_per_img": PER_IMG,
+                       "parallelism": f"dp{world}" + (" (one NCCL all-reduce of the flat fp32 gradients per step)"
+                                                      if world > 1 else ""),
+                       "optimizer": "SGD lr .01 momentum .937 nesterov (train.py:156)",
+                       "fwd_loss_img_s": world * BS * fl_steps / ms_fl * 1e3,
+                       "fwd_loss_ms_per_step": ms_fl / fl_steps,
                        "l2": "inputs (246 MB images + multi-GB activations per step) exceed the 126 MB L2"},
             "e2e": {"value": world * BS * args.steps / ms_e2e * 1e3, "unit": UNIT,
                     "h2d_bytes_per_step": int(host_imgs[0].numel() * 4 + host_tg[0].numel() * 4),
                     "d2h_bytes_per_step": 32, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"kernel": "conv_fwd_kernel (tcgen05 implicit GEMM)", "bound": "tensor", "achieved": tflops,
-                         "peak": peak, "unit": "TFLOP/s", "frac": tflops / peak, "traffic": None,
-                         "peak_source": f"{pk_src} bf16_tflops_sustained", "conv_ms_per_step": conv_ms,
-                         "conv_launches_per_step": n_conv, "algorithmic_gflop_per_step": GFLOP_PER_IMG * BS},
+            "roofline": {"kernel": "tcgen05 conv family: conv_fwd_kernel (forward + dgrad) and conv_wgrad_kernel",
+                         "bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
+                         "frac": tflops / peak, "traffic": None,
+                         "peak_source": f"{pk_src} bf16_tflops_sustained",
+                         "ms_per_step": {k: round(v, 3) for k, v in tc_ms.items()},
+                         "algorithmic_gflop_per_step": gflop},
         }
         if world == 1 and not args.no_cpu:
-            v, cores, sample = cpu_arm(1, 0)
+            v, cores, sample = cpu_arm(wl, 1, 0)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         print(json.dumps(line))
     if world > 1:
@@ -296,6 +330,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--workload", default="fwd_loss", choices=["fwd_loss", "train_v4", "train_v7"],
+                    help="fwd_loss = BASELINE configs[1] (default, the N=1 headline); train_v7 = configs[2] "
+                         "(yolov7/csl/nc16 full train step with the gradient all-reduce)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -203,17 +203,25 @@ def resize_copy(x, factor, out=None):
 def conv2d_dgrad(dy, wt, Cin, k, stride, dx, accumulate):
     """dx (Act [N,H,W,Cin]) (+)= conv^T(dy, w);  wt = pack_weights(w, transpose=True) with Cout == dy.C."""
     assert wt.dtype == torch.bfloat16 and wt.numel() == Cin * k * k * dy.C
+    if PROFILE is not None:
+        _prof_begin()
     L.check(L.lib().ryolo_conv2d_dgrad(_vp(dy.ptr), dy.pitch, dx.N, dx.H, dx.W, Cin, dy.C, k, stride, _tp(wt),
                                        _vp(dx.ptr), dx.pitch, 1 if accumulate else 0, L.stream()))
     L.count(stride * stride)
+    if PROFILE is not None:
+        _prof_end(('dgrad', dx.P, Cin, k * k * dy.C))
 
 
 def conv2d_wgrad(x, dy, Cout, k, stride, dw, stem=False):
     """dw (fp32, OIHW) += conv_backward_weight(x, dy)."""
     assert dw.dtype == torch.float32 and dw.is_contiguous()
+    if PROFILE is not None:
+        _prof_begin()
     L.check(L.lib().ryolo_conv2d_wgrad(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, _vp(dy.ptr), dy.pitch, dy.C, Cout, k,
                                        stride, 1 if stem else 0, _tp(dw), L.stream()))
     L.count(1)
+    if PROFILE is not None:
+        _prof_end(('wgrad', dy.P, Cout, k * k * x.C))
 
 
 def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, dbeta):
