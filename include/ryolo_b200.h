@@ -165,8 +165,9 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
                        long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, int stem, float* dw,
                        void* stream);
 /* d raw = backward of act(BatchNorm2d_train(raw)) given d out; also d gamma, d beta (fp32[C], nullable).
- * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.                   */
-int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long rp, const float* scale,
+ * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.  dout is overwritten
+ * with dout*act'(.) (dead afterwards).                                                                        */
+int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
                      float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream);
 /* ds = dout * act'(x1*s1+b1 + x2*s2+b2): backward through RepConv's SiLU of two summed BN branches          */

@@ -36,8 +36,10 @@ __device__ __forceinline__ float act_grad(float y) {
     if (y > 20.f) return 1.f;
     const float e = __expf(y);
     const float n = e * (e + 2.f);
-    const float t = __fdividef(n, n + 2.f);
-    const float sg = __fdividef(e, 1.f + e);
+    const float d1 = n + 2.f, d2 = 1.f + e;
+    const float r = __fdividef(1.f, d1 * d2);          // one reciprocal serves tanh(softplus) and sigmoid
+    const float t = n * d2 * r;
+    const float sg = e * d1 * r;
     return t + y * (1.f - t * t) * sg;
   }
   if (ACT == RYOLO_ACT_SWISH) {
@@ -48,10 +50,11 @@ __device__ __forceinline__ float act_grad(float y) {
 }
 
 // Pass 1: per-channel  s1 = sum dY,  s2 = sum dY * xhat   with dY = dOut * act'(raw*scale+shift),
-// xhat = (raw - mean) * invstd.  sums = [s1 | s2] (fp32[2C], zeroed by the caller).
+// xhat = (raw - mean) * invstd.  sums = [s1 | s2] (fp32[2C], zeroed by the caller).  dY overwrites dOut (the
+// gradient of this layer's output is dead after this pass), so pass 2 needs no transcendental.
 template <int ACT>
 __global__ void __launch_bounds__(256)
-bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+bn_act_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
                          float* __restrict__ sums) {
@@ -84,10 +87,14 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, c
           unpack8(vd[u], d);
           unpack8(vr[u], x);
 #pragma unroll
+          for (int j = 0; j < 8; j++) d[j] *= act_grad<ACT>(x[j] * sc[j] + sh[j]);
+          const uint4 pk = pack8(d);
+          if (ACT != RYOLO_ACT_LINEAR) *reinterpret_cast<uint4*>(dout + pix * dp + c) = pk;
+          unpack8(pk, d);                         // statistics of dY as stored
+#pragma unroll
           for (int j = 0; j < 8; j++) {
-            const float dy = d[j] * act_grad<ACT>(x[j] * sc[j] + sh[j]);
-            s1[j] += dy;
-            s2[j] += dy * (x[j] - mu[j]) * is[j];
+            s1[j] += d[j];
+            s2[j] += d[j] * (x[j] - mu[j]) * is[j];
           }
         }
       }
@@ -108,14 +115,14 @@ bn_act_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, c
   }
 }
 
-// Pass 2: d raw = scale * (dY - s1/P - xhat * s2/P);  block 0 also emits d gamma = s2, d beta = s1.
-template <int ACT>
+// Pass 2: d raw = scale * (dY - s1/P - xhat * s2/P) with dY read back from pass 1;  block 0 also emits
+// d gamma = s2, d beta = s1.
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
-                        long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
-                        const float* __restrict__ mean, const float* __restrict__ invstd,
-                        const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
-                        long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                        long long rp, const float* __restrict__ scale, const float* __restrict__ mean,
+                        const float* __restrict__ invstd, const float* __restrict__ sums, long long P, int C,
+                        __nv_bfloat16* __restrict__ draw, long long op, float* __restrict__ dgamma,
+                        float* __restrict__ dbeta) {
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -128,10 +135,10 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, co
   if (r >= rows) return;
   const int c = 8 * g;
   const float invP = 1.f / (float)P;
-  float sc[8], sh[8], mu[8], is[8], m1[8], m2[8];
+  float sc[8], mu[8], is[8], m1[8], m2[8];
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    sc[j] = scale[c + j]; sh[j] = shift[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j];
+    sc[j] = scale[c + j]; mu[j] = mean[c + j]; is[j] = invstd[c + j];
     m1[j] = sums[c + j] * invP; m2[j] = sums[C + c + j] * invP;
   }
   const long long stride = (long long)gridDim.x * rows;
@@ -154,9 +161,8 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, co
         unpack8(vr[u], x);
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-          const float dy = d[j] * act_grad<ACT>(x[j] * sc[j] + sh[j]);
           const float xh = (x[j] - mu[j]) * is[j];
-          o[j] = sc[j] * (dy - m1[j] - xh * m2[j]);
+          o[j] = sc[j] * (d[j] - m1[j] - xh * m2[j]);
         }
         *reinterpret_cast<uint4*>(draw + pix * op + c) = pack8(o);
       }
@@ -355,9 +361,10 @@ inline int grid_for(long long total, int block) {
 extern "C" {
 
 // Backward of act(BatchNorm2d_train(raw)) (+ gradient already flowing to a residual is the caller's business).
+// NOTE: dout is overwritten with dY = dout * act'(.) (it is dead afterwards).
 //   dout, raw: bf16 NHWC views over P pixels x C channels; scale/shift/mean/invstd: fp32[C] saved by the forward pass
 //   sums: fp32[2C] scratch, zeroed;  draw: bf16 view;  dgamma / dbeta: fp32[C] outputs (nullable)
-int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long rp, const float* scale,
+int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
                      float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream) {
   RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && dp % 8 == 0 && rp % 8 == 0 && op % 8 == 0,
@@ -370,13 +377,11 @@ int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long 
   const size_t smem = (size_t)2 * rows * C * sizeof(float);
   long long want = (P + 2ll * rows - 1) / (2ll * rows);
   const int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
-  const __nv_bfloat16* d = (const __nv_bfloat16*)dout;
+  __nv_bfloat16* d = (__nv_bfloat16*)dout;
   const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
   __nv_bfloat16* o = (__nv_bfloat16*)draw;
-#define RY_BWD(ACT)                                                                                                  \
-  bn_act_bwd_reduce_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C, sums); \
-  bn_act_bwd_apply_kernel<ACT><<<blocks * 2, threads, 0, st>>>(d, dp, r, rp, scale, shift, mean, invstd, sums, P, C, o, \
-                                                              op, dgamma, dbeta);
+#define RY_BWD(ACT) \
+  bn_act_bwd_reduce_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C, sums);
   switch (act) {
     case RYOLO_ACT_LEAKY: RY_BWD(RYOLO_ACT_LEAKY) break;
     case RYOLO_ACT_MISH: RY_BWD(RYOLO_ACT_MISH) break;
@@ -384,6 +389,8 @@ int ryolo_bn_act_bwd(const void* dout, long long dp, const void* raw, long long 
     default: RY_BWD(RYOLO_ACT_LINEAR) break;
   }
 #undef RY_BWD
+  bn_act_bwd_apply_kernel<<<blocks * 2, threads, 0, st>>>(d, dp, r, rp, scale, mean, invstd, sums, P, C, o, op, dgamma,
+                                                          dbeta);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }
