@@ -156,6 +156,15 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stre
 /* state-dict OIHW fp32 -> bf16: layout 0 [Cout][kh][kw][Cin]; 1 (stem) [Cout][64] in the im2col channel
  * order; 2 (dgrad) [Cin][kh][kw][Cout]                                                                     */
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream);
+/* all conv weights of a model in one launch.  table (DEVICE array, sorted by `first`): tensor i holds flat
+ * elements [first, first + Cout*Cin*k*k) of the launch; dst = layout 0 (or the stem's [Cout][64], padding
+ * pre-zeroed by the caller), dst_t = layout 2 or NULL.                                                         */
+typedef struct ryolo_pack_entry {
+  const float* src; void* dst; void* dst_t;
+  long long first;
+  int Cout, Cin, k, stem;
+} ryolo_pack_entry;
+int ryolo_pack_weights_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream);
 
 /* ---- conv stack backward (autograd's backward of the reference, train.py:198) ------------------------------
  * dw (fp32 OIHW [Cout][Cin][k][k]; stem != 0: [Cout][3][3][3] with x = the 64-channel im2col tensor) +=

@@ -65,6 +65,7 @@ SIGNATURES.update({
     "ryolo_resize_copy": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
     "ryolo_stem_im2col": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
     "ryolo_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "ryolo_pack_weights_multi": (_i32, [_vp, _i32, _ll, _vp]),
     "ryolo_conv2d_dgrad": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _ll, _i32, _vp]),
     "ryolo_conv2d_wgrad": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _vp, _ll, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ryolo_bn_act_bwd": (_i32, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _i32, _ll, _i32, _vp, _vp, _ll, _vp, _vp, _vp]),

@@ -292,6 +292,34 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
   }
 }
 
+// All conv weights of a model in ONE launch: table[i] describes tensor i; thread t handles flat element t.
+__global__ void __launch_bounds__(256)
+pack_weights_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;                       // last entry whose first element <= i
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const ryolo_pack_entry e = table[lo];
+    const long long r = i - e.first;              // OIHW index: ((co*Cin + ci)*k*k + tap)
+    const int kk = e.k * e.k;
+    const int tap = (int)(r % kk);
+    const int ci = (int)((r / kk) % e.Cin);
+    const int co = (int)(r / ((long long)kk * e.Cin));
+    const __nv_bfloat16 v = __float2bfloat16_rn(e.src[r]);
+    __nv_bfloat16* dst = (__nv_bfloat16*)e.dst;
+    __nv_bfloat16* dst_t = (__nv_bfloat16*)e.dst_t;
+    if (e.stem) {
+      dst[(long long)co * 64 + tap * 3 + ci] = v;                       // [Cout][64] im2col order (pad pre-zeroed)
+    } else {
+      dst[((long long)co * kk + tap) * e.Cin + ci] = v;                 // [Cout][kh][kw][Cin]
+      if (dst_t) dst_t[((long long)ci * kk + tap) * e.Cout + co] = v;   // [Cin][kh][kw][Cout]
+    }
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148ll * 32;
@@ -380,6 +408,13 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stre
   const long long total = (long long)N * H * W;
   if (total == 0) return RYOLO_OK;
   stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W, (__nv_bfloat16*)y);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_pack_weights_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream) {
+  RY_CHECK_ARG(n > 0 && total > 0, "pack_weights_multi: empty table");
+  pack_weights_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(table_dev, n, total);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

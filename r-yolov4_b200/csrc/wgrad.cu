@@ -22,7 +22,6 @@
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kBoxBytes = 128 * 128;     // one [128 pixels x 64 channels] bf16 box
 constexpr int kMaxBStages = 8;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,6 +113,7 @@ struct WgradParams {
   int nb, tg;                               // X boxes per item (N = 64*nb), taps per item
   int n_co_tiles, n_ci_tiles, n_tap_groups, ksplit;
   int b_stages;
+  int slot_rows;                            // rows per smem box slot: 128, or 64 for wide Cin tiles (deeper ring)
   uint32_t tmem_cols;
   float* dw;                                // fp32 OIHW [Cout][Cin][k][k] (stem: [Cout][3][3][3] from the 64-ch im2col)
   int stem;
@@ -124,6 +124,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                   const WgradParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t kBoxBytes = (uint32_t)p.slot_rows * 128u;         // one [slot_rows pixels x 64 channels] bf16 box
   const uint32_t sA = smem_base;                                   // 2 slots x 2 boxes (dY, 128 channels)
   const uint32_t sB = smem_base + 4 * kBoxBytes;                   // b_stages slots x nb boxes (X)
   __shared__ __align__(8) uint64_t bars[2 * kMaxBStages + 5];
@@ -163,9 +164,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     tmem_alloc(smem_u32(&tmem_slot), p.tmem_cols);
     tmem_relinquish();
   }
-  if (rows < 128) {   // rows the TMA boxes never write must read as zeros (K padding of the GEMM)
+  if (rows < ((rows + 15) & ~15)) {   // rows the TMA boxes never write but the last K step reads must be zeros
     const int nbox = 4 + p.b_stages * p.nb;
-    const int tail16 = (128 - rows) * 8;                           // 16-byte words per box tail
+    const int tail16 = (p.slot_rows - rows) * 8;                   // 16-byte words per box tail
     uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
     for (int i = threadIdx.x; i < nbox * tail16; i += kThreads) {
       const int b = i / tail16, w = i - b * tail16;
@@ -280,13 +281,13 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-void pick_patch(int Ho, int Wo, int* TH, int* TW) {
+void pick_patch(int Ho, int Wo, int cap, int* TH, int* TW) {
   double best = -1.0;
-  for (int tw = 1; tw <= 128 && tw <= Wo; tw++) {
-    int th = 128 / tw;
+  for (int tw = 1; tw <= cap && tw <= Wo; tw++) {
+    int th = cap / tw;
     if (th > Ho) th = Ho;
     const double tiles = (double)((Ho + th - 1) / th) * ((Wo + tw - 1) / tw);
-    const double eff = (double)Ho * Wo / (tiles * 128.0);
+    const double eff = (double)Ho * Wo / (tiles * (double)cap);
     if (eff > best + 1e-9 || (eff > best - 1e-9 && tw > *TW)) { best = eff; *TH = th; *TW = tw; }
   }
 }
@@ -338,13 +339,14 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   p.Ho = (H + 2 * p.pad - ksize) / stride + 1;
   p.Wo = (W + 2 * p.pad - ksize) / stride + 1;
   p.ntaps = ksize * ksize;
-  p.TH = 1; p.TW = 1;
-  pick_patch(p.Ho, p.Wo, &p.TH, &p.TW);
-  if (p.TW * stride > 256) { p.TW = 256 / stride; p.TH = 128 / p.TW; if (p.TH > p.Ho) p.TH = p.Ho; }
-  p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
-  p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
   p.nb = (Cin + 63) / 64;
   if (p.nb > 4) p.nb = 4;
+  p.slot_rows = p.nb >= 2 ? 64 : 128;        // wide Cin tiles: half-size K blocks buy a deeper X ring
+  p.TH = 1; p.TW = 1;
+  pick_patch(p.Ho, p.Wo, p.slot_rows, &p.TH, &p.TW);
+  if (p.TW * stride > 256) { p.TW = 256 / stride; p.TH = p.slot_rows / p.TW; if (p.TH > p.Ho) p.TH = p.Ho; }
+  p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
+  p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
   const int CIT = 64 * p.nb;
   p.n_ci_tiles = (Cin + CIT - 1) / CIT;
   p.n_co_tiles = (Cout + 127) / 128;
@@ -362,11 +364,12 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   if (ksplit > n_patches) ksplit = (int)n_patches;
   p.ksplit = ksplit;
   const size_t budget = 200 * 1024;
-  int bst = (int)((budget - 1024 - 4 * (size_t)kBoxBytes) / ((size_t)p.nb * kBoxBytes));
+  const size_t kBoxBytes = (size_t)p.slot_rows * 128;
+  int bst = (int)((budget - 1024 - 4 * kBoxBytes) / ((size_t)p.nb * kBoxBytes));
   if (bst > kMaxBStages) bst = kMaxBStages;
   RY_CHECK_ARG(bst >= 2, "wgrad: shared memory budget too small");
   p.b_stages = bst;
-  const size_t smem = 1024 + 4 * (size_t)kBoxBytes + (size_t)bst * p.nb * kBoxBytes;
+  const size_t smem = 1024 + 4 * kBoxBytes + (size_t)bst * p.nb * kBoxBytes;
   p.dw = dw; p.stem = stem;
   CUtensorMap tmG, tmX;
   if (encode_nhwc(enc, &tmG, dy, N, p.Ho, p.Wo, Cdy, dy_cpitch, p.TH, p.TW, 1) ||

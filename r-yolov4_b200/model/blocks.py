@@ -47,9 +47,11 @@ class _Packed:
     """bf16 [Cout][kh][kw][Cin] copy of an fp32 OIHW parameter, refreshed when the parameter changes."""
 
     def __init__(self):
-        self.key, self.w = None, None
+        self.key, self.w, self.pinned = None, None, False
 
     def get(self, p, stem=False, transpose=False):
+        if self.pinned:                       # refreshed in bulk by Yolo.repack_weights()
+            return self.w
         key = (p.data_ptr(), p._version, p.device, WEIGHT_EPOCH[0])
         if key != self.key:
             self.w = ops.pack_weights(p.data, stem=stem, transpose=transpose)

@@ -56,6 +56,7 @@ class Yolo(nn.Module):
         self.yolo = layer
         self.autograd = True          # False: the caller drives Yolo.backward() itself (TrainStep)
         self._flat = self._flat_grad = self._grad_views = None
+        self._pack_table = None
         self._bn_channels = sum(m.num_features for m in self.modules() if isinstance(m, nn.BatchNorm2d))
         self._bn_layers = sum(1 for m in self.modules() if isinstance(m, nn.BatchNorm2d))
         self.last_ctx = None
@@ -108,6 +109,52 @@ class Yolo(nn.Module):
             off += n
         self._flat, self._flat_grad, self._grad_views = flat, grad, views
         return flat, grad
+
+    def enable_fused_pack(self):
+        """Pre-allocates the bf16 operand copies of every conv weight and refreshes ALL of them with one kernel
+        launch (repack_weights) instead of one launch per layer and layout."""
+        import numpy as np_
+        from .blocks import Conv, RepConv
+        dev = next(self.parameters()).device
+        ents, first = [], 0
+        for m in self.modules():
+            todo = []
+            if isinstance(m, Conv):
+                todo.append((m.conv[0].weight, m._packed, None if (m.stem or not m.has_bn) else m._packed_t, m.stem))
+            elif isinstance(m, RepConv):
+                todo.append((m.rbr_dense[0].weight, m._pd, m._pdt, False))
+                todo.append((m.rbr_1x1[0].weight, m._p1, m._p1t, False))
+            for w, pk, pkt, stem in todo:
+                Cout, Cin, k, _ = w.shape
+                pk.w = torch.zeros((Cout, 64 if stem else k * k * Cin), dtype=torch.bfloat16, device=dev)
+                pk.pinned = True
+                dt = 0
+                if pkt is not None:
+                    pkt.w = torch.empty((Cin, k * k * Cout), dtype=torch.bfloat16, device=dev)
+                    pkt.pinned = True
+                    dt = pkt.w.data_ptr()
+                ents.append((w, pk.w.data_ptr(), dt, first, Cout, Cin, k, 1 if stem else 0))
+                first += w.numel()
+        self._pack_params = [e[0] for e in ents]
+        self._pack_meta = [e[1:] for e in ents]
+        self._pack_total = first
+        self._pack_table = None
+        self.repack_weights()
+
+    def repack_weights(self):
+        import numpy as np_
+        from .. import _lib as L_
+        if self._pack_table is None or any(p.data_ptr() != a for p, a in zip(self._pack_params, self._pack_addrs)):
+            rows = np_.zeros((len(self._pack_meta), 6), dtype=np_.int64)          # 48-byte ryolo_pack_entry
+            for i, (p, (dst, dst_t, first, Cout, Cin, k, stem)) in enumerate(zip(self._pack_params, self._pack_meta)):
+                rows[i, 0], rows[i, 1], rows[i, 2], rows[i, 3] = p.data_ptr(), dst, dst_t, first
+                rows[i, 4] = Cout | (Cin << 32)
+                rows[i, 5] = k | (stem << 32)
+            self._pack_table = torch.from_numpy(rows).to(next(self.parameters()).device)
+            self._pack_addrs = [p.data_ptr() for p in self._pack_params]
+        L_.check(L_.lib().ryolo_pack_weights_multi(L_.ptr(self._pack_table), len(self._pack_meta), self._pack_total,
+                                                   L_.stream()))
+        L_.count(1)
 
     @staticmethod
     def _make_anchors(strides, anchors):

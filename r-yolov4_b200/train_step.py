@@ -23,6 +23,7 @@ class TrainStep:
         model.autograd = False
         self.flat, self.grad = model.flatten_parameters()
         self.buf = torch.zeros_like(self.flat)
+        model.enable_fused_pack()
         self.first = True
         self.pg = process_group
         self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -44,7 +45,8 @@ class TrainStep:
             allreduce_mean(self.grad, self.pg)
         ops.sgd_step(self.flat, self.grad, self.buf, self.lr, self.momentum, self.wd, self.nesterov, self.first)
         self.first = False
-        blocks.WEIGHT_EPOCH[0] += 1          # packed bf16 weight copies are stale now
+        blocks.WEIGHT_EPOCH[0] += 1          # BN-eval affine caches are stale now
+        self.model.repack_weights()          # refresh every bf16 operand copy in one launch
 
     def __call__(self, imgs, targets):
         self.zero_grad()
