@@ -165,14 +165,16 @@ typedef struct ryolo_pack_entry {
   int Cout, Cin, k, stem;
 } ryolo_pack_entry;
 int ryolo_pack_weights_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream);
+int ryolo_unpack_wgrad_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream);
 
 /* ---- conv stack backward (autograd's backward of the reference, train.py:198) ------------------------------
- * dw (fp32 OIHW [Cout][Cin][k][k]; stem != 0: [Cout][3][3][3] with x = the 64-channel im2col tensor) +=
- * conv_backward_weight(x, dy).  x bf16 NHWC view [N,H,W,Cin]; dy bf16 NHWC view [N,Ho,Wo,Cdy], Cdy >= Cout.
- * tcgen05 GEMM over pixels with MN-major operands, split-K across CTAs, fp32 atomics into dw (csrc/wgrad.cu). */
+ * dwk (fp32, K-major [Cout][kh*kw][Cin] like the packed forward weights; stem: x = the 64-channel im2col tensor,
+ * dwk = [Cout][64]) += conv_backward_weight(x, dy).  x bf16 NHWC view [N,H,W,Cin]; dy bf16 NHWC view
+ * [N,Ho,Wo,Cdy], Cdy >= Cout.  tcgen05 GEMM over pixels with MN-major operands, split-K across CTAs, vector fp32
+ * atomics into dwk (csrc/wgrad.cu).  ryolo_unpack_wgrad_multi then adds every dwk into its OIHW gradient
+ * (table as for ryolo_pack_weights_multi with src = dwk (fp32), dst = OIHW fp32 gradient, dst_t unused).       */
 int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
-                       long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, int stem, float* dw,
-                       void* stream);
+                       long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, float* dwk, void* stream);
 /* d raw = backward of act(BatchNorm2d_train(raw)) given d out; also d gamma, d beta (fp32[C], nullable).
  * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.  dout is overwritten
  * with dout*act'(.) (dead afterwards).                                                                        */

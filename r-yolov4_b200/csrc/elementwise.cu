@@ -320,6 +320,29 @@ pack_weights_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, lon
   }
 }
 
+// Reverse of pack_weights_multi for gradients: grad_oihw[first + r] += dwk[K-major index of r]  (dst = OIHW fp32
+// gradient, src = K-major fp32 scratch written by ryolo_conv2d_wgrad; stem: src is [Cout][64] im2col order).
+__global__ void __launch_bounds__(256)
+unpack_wgrad_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, long long total) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (table[mid].first <= i) lo = mid; else hi = mid - 1;
+    }
+    const ryolo_pack_entry e = table[lo];
+    const long long r = i - e.first;
+    const int kk = e.k * e.k;
+    const int tap = (int)(r % kk);
+    const int ci = (int)((r / kk) % e.Cin);
+    const int co = (int)(r / ((long long)kk * e.Cin));
+    const float* src = e.src;
+    const float v = e.stem ? src[(long long)co * 64 + tap * 3 + ci] : src[((long long)co * kk + tap) * e.Cin + ci];
+    ((float*)e.dst)[r] += v;
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148ll * 32;
@@ -415,6 +438,13 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stre
 int ryolo_pack_weights_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream) {
   RY_CHECK_ARG(n > 0 && total > 0, "pack_weights_multi: empty table");
   pack_weights_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(table_dev, n, total);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_unpack_wgrad_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream) {
+  RY_CHECK_ARG(n > 0 && total > 0, "unpack_wgrad_multi: empty table");
+  unpack_wgrad_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(table_dev, n, total);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

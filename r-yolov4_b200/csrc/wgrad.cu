@@ -115,8 +115,7 @@ struct WgradParams {
   int b_stages;
   int slot_rows;                            // rows per smem box slot: 128, or 64 for wide Cin tiles (deeper ring)
   uint32_t tmem_cols;
-  float* dw;                                // fp32 OIHW [Cout][Cin][k][k] (stem: [Cout][3][3][3] from the 64-ch im2col)
-  int stem;
+  float* dw;                                // fp32 K-major [Cout][k*k][Cin] (16-byte aligned)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -234,11 +233,13 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       umma_commit(bar_acc);
     }
   } else if (has_work) {
+    // dw is K-major like the packed forward weights: [Cout][tap][Cin] (stem: [Cout][64]).  A lane owns one Cout row
+    // and adds 4 consecutive Cin values per vector atomic (red.global.add.v4.f32).
     const int sub = warp & 3;
     const int co = co0 + sub * 32 + lane;
     mbar_wait(bar_acc, 0);
     tc_fence_after();
-    const int kk2 = p.ksize * p.ksize;
+    const int rowlen = p.ntaps * p.Cin;
     for (int ti = 0; ti < ntap; ti++) {
       const int tap = tap0 + ti;
 #pragma unroll 1
@@ -247,14 +248,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(ti * CIT + c0), v);
         tmem_ld_wait();
         if (co < p.Cout) {
+          float* row = p.dw + (long long)co * rowlen + (long long)tap * p.Cin + ci0 + c0;
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            const int ci = ci0 + c0 + j;
-            if (p.stem) {   // im2col channel ci = (kh*3+kw)*3 + c  ->  OIHW [co][c][kh][kw]
-              if (ci < 27) atomicAdd(p.dw + ((long long)co * 3 + ci % 3) * 9 + ci / 3, __uint_as_float(v[j]));
-            } else if (ci < p.Cin) {
-              atomicAdd(p.dw + ((long long)co * p.Cin + ci) * kk2 + tap, __uint_as_float(v[j]));
-            }
+          for (int j = 0; j < 32; j += 4) {
+            if (ci0 + c0 + j < p.Cin)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                           "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
           }
         }
       }
@@ -319,18 +320,18 @@ int encode_nhwc(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int N, int 
 
 extern "C" {
 
-// dw (fp32 OIHW [Cout][Cin][k][k], or [Cout][3][3][3] when stem != 0 and x is the 64-channel im2col tensor) +=
-// conv_backward_weight(x, dy).   x: bf16 NHWC view [N,H,W,Cin]; dy: bf16 NHWC view [N,Ho,Wo,Cdy] with Cdy >= Cout
-// channels readable (extra channels are ignored).  dw must be zeroed (or hold a running sum) on entry.
+// dwk (fp32, K-major [Cout][kh*kw][Cin] = the layout of the packed forward weights; for the stem x is the 64-channel
+// im2col tensor and dwk is [Cout][64]) += conv_backward_weight(x, dy).   x: bf16 NHWC view [N,H,W,Cin]; dy: bf16 NHWC
+// view [N,Ho,Wo,Cdy] with Cdy >= Cout channels readable (extra channels are ignored).  dwk must be zeroed (or hold a
+// running sum) on entry and be 16-byte aligned; ryolo_unpack_wgrad_multi adds it into the OIHW gradients.
 int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
-                       long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, int stem, float* dw,
-                       void* stream) {
+                       long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, float* dwk, void* stream) {
   RY_CHECK_ARG(ksize == 1 || ksize == 3, "wgrad: ksize must be 1 or 3");
   RY_CHECK_ARG(stride == 1 || stride == 2, "wgrad: stride must be 1 or 2");
   RY_CHECK_ARG(Cin % 8 == 0 && Cdy % 8 == 0 && x_cpitch % 8 == 0 && dy_cpitch % 8 == 0 && Cdy >= Cout,
                "wgrad: channel counts and pitches must be multiples of 8");
-  RY_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)dy) & 15) == 0, "wgrad: operands must be 16-byte aligned");
-  RY_CHECK_ARG(!stem || (Cin == 64 && ksize == 1), "wgrad: the stem path expects the 64-channel im2col input");
+  RY_CHECK_ARG((((uintptr_t)x) & 15) == 0 && (((uintptr_t)dy) & 15) == 0 && (((uintptr_t)dwk) & 15) == 0,
+               "wgrad: operands must be 16-byte aligned");
   if (N == 0) return RYOLO_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
@@ -341,7 +342,7 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   p.ntaps = ksize * ksize;
   p.nb = (Cin + 63) / 64;
   if (p.nb > 4) p.nb = 4;
-  p.slot_rows = p.nb >= 2 ? 64 : 128;        // wide Cin tiles: half-size K blocks buy a deeper X ring
+  p.slot_rows = 128;   // (64-row K blocks were measured slower: more barrier round trips per byte)
   p.TH = 1; p.TW = 1;
   pick_patch(p.Ho, p.Wo, p.slot_rows, &p.TH, &p.TW);
   if (p.TW * stride > 256) { p.TW = 256 / stride; p.TH = p.slot_rows / p.TW; if (p.TH > p.Ho) p.TH = p.Ho; }
@@ -370,7 +371,7 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   RY_CHECK_ARG(bst >= 2, "wgrad: shared memory budget too small");
   p.b_stages = bst;
   const size_t smem = 1024 + 4 * kBoxBytes + (size_t)bst * p.nb * kBoxBytes;
-  p.dw = dw; p.stem = stem;
+  p.dw = dwk;
   CUtensorMap tmG, tmX;
   if (encode_nhwc(enc, &tmG, dy, N, p.Ho, p.Wo, Cdy, dy_cpitch, p.TH, p.TW, 1) ||
       encode_nhwc(enc, &tmX, x, N, H, W, Cin, x_cpitch, p.TH, p.TW, stride)) {

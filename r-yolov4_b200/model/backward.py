@@ -85,7 +85,7 @@ def _implicit_head_grads(model, conv, gl, y, mul, param_grads):
     w = conv.conv[0].weight.data.float().flatten(1)                       # [Cout, Cin]
     param_grads[id(ia.implicit)].add_((w.t() @ dpre_sum).view_as(ia.implicit))
 
-def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads):
+def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
     """out = silu(bn_d(conv3x3(x)) + bn_1(conv1x1(x)))   (model/utils.py:209-215)."""
     C = mod.c2
     ds = ops.Act.empty(rd.N, rd.H, rd.W, C, rd.buf.device)
@@ -95,12 +95,43 @@ def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads):
         bn = seq[1]
         ops.bn_act_bwd(ds, raw, aff[0], aff[1], aff[2], aff[3], "linear", sums[:2 * C] if first else sums[2 * C:],
                      raw, param_grads[id(bn.weight)], param_grads[id(bn.bias)])
-        ops.conv2d_wgrad(x, raw, C, k, mod.s, param_grads[id(seq[0].weight)])
+        ops.conv2d_wgrad(x, raw, C, k, mod.s, sink.buffer(seq[0].weight))
         gx, acc = G.writable(x)
         ops.conv2d_dgrad(raw, packed_t.get(seq[0].weight, transpose=True), x.C, k, mod.s, gx, acc)
         G.mark(x)
         first = False
 
+
+
+class _WgradSink:
+    """Where conv_wgrad writes.  Fused path (TrainStep): the model's flat K-major scratch, folded into the flat OIHW
+    gradients by one launch at the end.  Generic path (autograd node, block tests): per-layer scratch + torch glue."""
+
+    def __init__(self, model, param_grads):
+        self.param_grads = param_grads
+        self.fused = getattr(model, "_pack_table", None) is not None and \
+            param_grads is getattr(model, "_grad_views", None)
+        self.model = model
+        self.pending = []
+        if self.fused:
+            self.views = model.wgrad_scratch()
+            model._wg_flat.zero_()
+
+    def buffer(self, weight, stem=False):
+        if self.fused:
+            return self.views[id(weight)]
+        Cout, Cin, k, _ = weight.shape
+        buf = torch.zeros(Cout * (64 if stem else k * k * Cin), dtype=torch.float32, device=weight.device)
+        self.pending.append((weight, buf, stem))
+        return buf
+
+    def finish(self):
+        if self.fused:
+            self.model.unpack_wgrads()
+            return
+        for weight, buf, stem in self.pending:
+            Cout, Cin, k, _ = weight.shape
+            self.param_grads[id(weight)].add_(ops.wgrad_to_oihw(buf, Cout, Cin, k, stem))
 
 
 def run_backward(model, ctx, dlevels, param_grads, seed=()):
@@ -112,6 +143,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
     assert tape is not None, "backward needs a training-mode forward"
     dev = ctx.device
     G = GradStore()
+    sink = _WgradSink(model, param_grads)
     for act, g in seed:
         ops.add_into(G.view(act), g, False)
         G.mark(act)
@@ -135,7 +167,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             if mul is not None:        # yolov7: y = im * (conv(x + ia) + b)   (model/neck.py:201,208,215)
                 _implicit_head_grads(model, mod, gl, y, mul, param_grads)
             dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias))
-            ops.conv2d_wgrad(x, dpre, Cout, 1, 1, pg(conv.weight))
+            ops.conv2d_wgrad(x, dpre, Cout, 1, 1, sink.buffer(conv.weight))
             w = conv.weight.data
             if Cpad != Cout:
                 w = torch.cat((w, w.new_zeros(Cpad - Cout, *w.shape[1:])), 0)
@@ -156,7 +188,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
                            pg(bn.weight), pg(bn.bias))     # d raw overwrites raw in place
             soff += 2 * C
             k = 1 if mod.stem else mod.k
-            ops.conv2d_wgrad(x, raw, C, k, mod.s, pg(mod.conv[0].weight), stem=mod.stem)
+            ops.conv2d_wgrad(x, raw, C, k, mod.s, sink.buffer(mod.conv[0].weight, mod.stem))
             if not mod.stem:
                 gx, acc = G.writable(x)
                 ops.conv2d_dgrad(raw, mod.weight_t(), x.C, mod.k, mod.s, gx, acc)
@@ -164,7 +196,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
         elif kind == "repconv":
             _, mod, x, rd, r1, out, affs = e
             dout = G.view(out)
-            _repconv_backward(mod, x, rd, r1, dout, affs, G, sums[soff:soff + 4 * mod.c2], param_grads)
+            _repconv_backward(mod, x, rd, r1, dout, affs, G, sums[soff:soff + 4 * mod.c2], param_grads, sink)
             soff += 4 * mod.c2
         elif kind == "maxpool":
             _, src, dst, k, s, p = e
@@ -185,5 +217,6 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             G.mark(src)
         else:
             raise RuntimeError(f"unknown tape entry {kind}")
+    sink.finish()
     ctx.tape = None            # the tape's raw buffers now hold gradients: a second backward would be wrong
     return G

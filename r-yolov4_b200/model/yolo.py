@@ -141,6 +141,34 @@ class Yolo(nn.Module):
         self._pack_table = None
         self.repack_weights()
 
+    def wgrad_scratch(self):
+        """fp32 K-major scratch for every conv weight gradient (one flat buffer) + the table that lets ONE launch
+        add all of them into the flat OIHW gradient buffer.  Needs flatten_parameters() + enable_fused_pack()."""
+        import numpy as np_
+        if getattr(self, "_wg_flat", None) is None or self._wg_grad_ptr != self._flat_grad.data_ptr():
+            dev = self._flat_grad.device
+            sizes = []
+            for p, (_, _, _, Cout, Cin, k, stem) in zip(self._pack_params, self._pack_meta):
+                sizes.append((Cout * (64 if stem else k * k * Cin) + 3) // 4 * 4)
+            self._wg_flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
+            rows = np_.zeros((len(sizes), 6), dtype=np_.int64)
+            self._wg_views, off = {}, 0
+            for i, (p, (_, _, first, Cout, Cin, k, stem), n) in enumerate(zip(self._pack_params, self._pack_meta, sizes)):
+                v = self._wg_flat[off:off + Cout * (64 if stem else k * k * Cin)]
+                self._wg_views[id(p)] = v
+                rows[i, 0], rows[i, 1], rows[i, 3] = v.data_ptr(), self._grad_views[id(p)].data_ptr(), first
+                rows[i, 4], rows[i, 5] = Cout | (Cin << 32), k | (stem << 32)
+                off += n
+            self._wg_table = torch.from_numpy(rows).to(dev)
+            self._wg_grad_ptr = self._flat_grad.data_ptr()
+        return self._wg_views
+
+    def unpack_wgrads(self):
+        from .. import _lib as L_
+        L_.check(L_.lib().ryolo_unpack_wgrad_multi(L_.ptr(self._wg_table), len(self._pack_meta), self._pack_total,
+                                                   L_.stream()))
+        L_.count(1)
+
     def repack_weights(self):
         import numpy as np_
         from .. import _lib as L_

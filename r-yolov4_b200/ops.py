@@ -212,16 +212,24 @@ def conv2d_dgrad(dy, wt, Cin, k, stride, dx, accumulate):
         _prof_end(('dgrad', dx.P, Cin, k * k * dy.C))
 
 
-def conv2d_wgrad(x, dy, Cout, k, stride, dw, stem=False):
-    """dw (fp32, OIHW) += conv_backward_weight(x, dy)."""
-    assert dw.dtype == torch.float32 and dw.is_contiguous()
+def conv2d_wgrad(x, dy, Cout, k, stride, dwk):
+    """dwk (fp32, K-major [Cout, k*k*Cin]; the stem passes its im2col input and [Cout, 64]) +=
+    conv_backward_weight(x, dy)."""
+    assert dwk.dtype == torch.float32 and dwk.is_contiguous() and dwk.numel() == Cout * k * k * x.C
     if PROFILE is not None:
         _prof_begin()
     L.check(L.lib().ryolo_conv2d_wgrad(_vp(x.ptr), x.pitch, x.N, x.H, x.W, x.C, _vp(dy.ptr), dy.pitch, dy.C, Cout, k,
-                                       stride, 1 if stem else 0, _tp(dw), L.stream()))
+                                       stride, _tp(dwk), L.stream()))
     L.count(1)
     if PROFILE is not None:
         _prof_end(('wgrad', dy.P, Cout, k * k * x.C))
+
+
+def wgrad_to_oihw(dwk, Cout, Cin, k, stem=False):
+    """K-major wgrad scratch -> OIHW tensor (torch glue for the non-fused paths / tests)."""
+    if stem:
+        return dwk.view(Cout, 64)[:, :27].reshape(Cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+    return dwk.view(Cout, k * k, Cin).permute(0, 2, 1).reshape(Cout, Cin, k, k).contiguous()
 
 
 def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, dbeta):

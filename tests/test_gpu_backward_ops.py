@@ -54,12 +54,12 @@ def test_wgrad(shape):
     from ryolo_b200 import ops
     N, H, W, Cin, Cout, k, s = shape
     x, w, dy, _, dw_ref = _case(shape, seed=1)
-    dw = torch.zeros(Cout, Cin, k, k, device="cuda")
-    ops.conv2d_wgrad(ops.Act(x.cuda()), ops.Act(dy.cuda()), Cout, k, s, dw)
-    got = dw.cpu()
+    dwk = torch.zeros(Cout * k * k * Cin, device="cuda")                          # K-major [Cout][tap][Cin]
+    ops.conv2d_wgrad(ops.Act(x.cuda()), ops.Act(dy.cuda()), Cout, k, s, dwk)
+    got = ops.wgrad_to_oihw(dwk, Cout, Cin, k).cpu()
     assert (got - dw_ref).abs().max() < 1e-2 * dw_ref.abs().max(), (got - dw_ref).abs().max() / dw_ref.abs().max()
-    ops.conv2d_wgrad(ops.Act(x.cuda()), ops.Act(dy.cuda()), Cout, k, s, dw)      # accumulates
-    assert (dw.cpu() - 2 * dw_ref).abs().max() < 2e-2 * dw_ref.abs().max()
+    ops.conv2d_wgrad(ops.Act(x.cuda()), ops.Act(dy.cuda()), Cout, k, s, dwk)     # accumulates
+    assert (ops.wgrad_to_oihw(dwk, Cout, Cin, k).cpu() - 2 * dw_ref).abs().max() < 2e-2 * dw_ref.abs().max()
 
 
 def test_wgrad_channel_slices_and_padded_dy():
@@ -72,9 +72,9 @@ def test_wgrad_channel_slices_and_padded_dy():
     dyb = torch.zeros(2, 20, 20, 48).bfloat16()
     dyb[..., :40] = dy
     dyb[..., 40:] = 5.0          # garbage in the padding must not leak into rows < Cout
-    dw = torch.zeros(40, 64, 1, 1, device="cuda")
-    ops.conv2d_wgrad(ops.Act(xb.cuda(), 64, 32), ops.Act(dyb.cuda()), 40, 1, 1, dw)
-    assert (dw.cpu() - dw_ref).abs().max() < 1e-2 * dw_ref.abs().max()
+    dwk = torch.zeros(40 * 64, device="cuda")
+    ops.conv2d_wgrad(ops.Act(xb.cuda(), 64, 32), ops.Act(dyb.cuda()), 40, 1, 1, dwk)
+    assert (ops.wgrad_to_oihw(dwk, 40, 64, 1).cpu() - dw_ref).abs().max() < 1e-2 * dw_ref.abs().max()
 
 
 def test_wgrad_stem():
@@ -85,9 +85,9 @@ def test_wgrad_stem():
     w = torch.zeros(32, 3, 3, 3, requires_grad=True)
     y = F.conv2d(img.bfloat16().float(), w, None, 1, 1)
     y.backward(dy.float().permute(0, 3, 1, 2))
-    dw = torch.zeros(32, 3, 3, 3, device="cuda")
-    ops.conv2d_wgrad(ops.stem_im2col(img.cuda()), ops.Act(dy.cuda()), 32, 1, 1, dw, stem=True)
-    assert (dw.cpu() - w.grad).abs().max() < 1e-2 * w.grad.abs().max()
+    dwk = torch.zeros(32 * 64, device="cuda")
+    ops.conv2d_wgrad(ops.stem_im2col(img.cuda()), ops.Act(dy.cuda()), 32, 1, 1, dwk)
+    assert (ops.wgrad_to_oihw(dwk, 32, 3, 3, stem=True).cpu() - w.grad).abs().max() < 1e-2 * w.grad.abs().max()
 
 
 @pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
