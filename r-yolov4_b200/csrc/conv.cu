@@ -20,6 +20,7 @@
 #include "ryolo_b200.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -114,6 +115,14 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
          ((uint64_t)(1024 >> 4) << 32) /* SBO */ | ((uint64_t)1 << 46) /* descriptor version (sm_100) */ |
          ((uint64_t)2 << 61) /* SWIZZLE_128B */;
 }
+// Same layout, but the 8-row groups are `sbo_bytes` apart and the start may sit on any 128-byte row of a swizzle atom
+// (shifted view into a halo tile): base_offset carries the row phase of the start address.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128_view(uint32_t saddr, uint32_t sbo_bytes, int use_base_offset) {
+  uint64_t d = (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) |
+               ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+  if (use_base_offset) d |= (uint64_t)((saddr >> 7) & 7u) << 49;
+  return d;
+}
 // instruction descriptor: D fp32, A/B bf16, both K-major, M = 128, N = n
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
@@ -140,6 +149,8 @@ struct ConvKernelParams {
   int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
+  int halo;                        // 0 | 1 | 2: 3x3 stride-1 taps read shifted views of ONE (TH+2)x(TW+2) halo box (2: base_offset set)
+  int a_slots; uint32_t a_slot_bytes;
   int out_s, out_oh, out_ow, OutH, OutW;   // output lattice: pixel (ho*out_s + out_oh, wo*out_s + out_ow) of an OutH x OutW map
   int mode, act;
   void* out;
@@ -176,11 +187,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t kABytes = kBM * kBK * 2, kBBytes = (uint32_t)BN * kBK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
-  const uint32_t sA = smem_base, sB = smem_base + STAGES * kABytes;
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + (p.halo ? (uint32_t)p.a_slots * p.a_slot_bytes : (uint32_t)STAGES * kABytes);
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4 + 8];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
-                 bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + 2]);
+                 bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + 2]),
+                 bar_afull = smem_u32(&bars[2 * kMaxStages + 4]), bar_aempty = smem_u32(&bars[2 * kMaxStages + 8]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.ntaps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
@@ -199,6 +212,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(bar_acc_full + 8 * b, 1);
       mbar_init(bar_acc_empty + 8 * b, 4);     // one arrival per epilogue warp
     }
+    for (int b = 0; b < 4; b++) {
+      mbar_init(bar_afull + 8 * b, 1);
+      mbar_init(bar_aempty + 8 * b, 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -214,8 +231,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ TMA producer (one lane) ================================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * kBK * 2;
-      int s = 0;
-      uint32_t phase = 0;
+      int s = 0, as = 0;
+      uint32_t phase = 0, aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int nt = t % p.n_tiles;
         int mt = t / p.n_tiles;
@@ -223,6 +240,23 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int ph = mt % p.tiles_h;
         const int img = mt / p.tiles_h;
         const int hs = ph * p.TH * p.stride, ws = pw * p.TW * p.stride, n0 = nt * BN;
+        if (p.halo) {
+          // one (TH+2)x(TW+2) halo box per 64-channel chunk serves all 9 taps; weights stream through the B ring
+          const uint32_t halo_bytes = (uint32_t)((p.TH + 2) * (p.TW + 2)) * kBK * 2;
+          for (int cb = 0; cb < p.kb_per_tap; cb++) {
+            mbar_wait(bar_aempty + 8 * as, aphase ^ 1u);
+            mbar_expect_tx(bar_afull + 8 * as, halo_bytes);
+            tma_load_4d(sA + as * p.a_slot_bytes, &tmA, bar_afull + 8 * as, cb * kBK, ws - 1, hs - 1, img);
+            if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+            for (int tap = 0; tap < p.ntaps; tap++) {
+              mbar_wait(bar_empty + 8 * s, phase ^ 1u);
+              mbar_expect_tx(bar_full + 8 * s, kBBytes);
+              tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * kBK, n0);
+              if (++s == STAGES) { s = 0; phase ^= 1u; }
+            }
+          }
+          continue;
+        }
         for (int kb = 0; kb < KB; kb++) {
           const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
           mbar_wait(bar_empty + 8 * s, phase ^ 1u);
@@ -237,13 +271,38 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ MMA issuer (one lane) ==================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
-      int s = 0;
-      uint32_t phase = 0, it = 0;
+      int s = 0, hslot = 0;
+      uint32_t phase = 0, hphase = 0, it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
         const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
         mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+        if (p.halo) {
+          const uint32_t sbo = (uint32_t)(p.TW + 2) * 128u;      // 8-pixel patch rows sit one halo row apart
+          for (int cb = 0; cb < p.kb_per_tap; cb++) {
+            mbar_wait(bar_afull + 8 * hslot, hphase);
+            tc_fence_after();
+            const uint32_t ah = sA + hslot * p.a_slot_bytes;
+            for (int tap = 0; tap < p.ntaps; tap++) {
+              mbar_wait(bar_full + 8 * s, phase);
+              tc_fence_after();
+              const uint32_t a0 = ah + (uint32_t)((p.tap_dh[tap] + 1) * (p.TW + 2) + (p.tap_dw[tap] + 1)) * 128u;
+              const uint32_t b0 = sB + s * kBBytes;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; k++) {
+                umma_bf16(d_tmem, umma_desc_k_sw128_view(a0 + k * 32, sbo, p.halo == 2),
+                          umma_desc_k_sw128(b0 + k * 32), idesc, (cb | tap | k) ? 1u : 0u);
+              }
+              umma_commit(bar_empty + 8 * s);
+              if (++s == STAGES) { s = 0; phase ^= 1u; }
+            }
+            umma_commit(bar_aempty + 8 * hslot);   // halo slot free once all nine taps have read it
+            if (++hslot == p.a_slots) { hslot = 0; hphase ^= 1u; }
+          }
+          umma_commit(bar_acc_full + 8 * buf);
+          continue;
+        }
         for (int kb = 0; kb < KB; kb++) {
           mbar_wait(bar_full + 8 * s, phase);
           tc_fence_after();
@@ -533,6 +592,27 @@ void pick_patch(int Ho, int Wo, int stride, int* TH, int* TW) {
   }
 }
 
+// 3x3 / stride-1 tap sets can read nine shifted views of one halo box (TW = 8 so that every 8-row UMMA group is one
+// patch row and the groups sit a constant (TW+2)*128 bytes apart).  Used when the 16x8 patch grid wastes little.
+// RYOLO_HALO=0 disables it, 2 sets the descriptor's base_offset field (bring-up switch).
+void maybe_enable_halo(ConvKernelParams* p) {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("RYOLO_HALO");
+    mode = e ? atoi(e) : 0;
+  }
+  p->halo = 0;
+  if (!mode || p->ntaps != 9 || p->stride != 1 || p->ksize != 3) return;
+  const double tiles = (double)((p->Ho + 15) / 16) * ((p->Wo + 7) / 8);
+  const double eff = (double)p->Ho * p->Wo / (tiles * 128.0);
+  const double cur = (double)p->Ho * p->Wo / ((double)p->tiles_h * p->tiles_w * 128.0);
+  if (eff < 0.85 * cur) return;
+  p->halo = mode;
+  p->TH = 16; p->TW = 8;
+  p->tiles_h = (p->Ho + 15) / 16;
+  p->tiles_w = (p->Wo + 7) / 8;
+}
+
 int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   RY_CHECK_ARG(d->ksize == 1 || d->ksize == 3, "conv: ksize must be 1 or 3");
   RY_CHECK_ARG(d->stride == 1 || d->stride == 2, "conv: stride must be 1 or 2");
@@ -576,6 +656,7 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   p->tiles_h = (p->Ho + p->TH - 1) / p->TH;
   p->tiles_w = (p->Wo + p->TW - 1) / p->TW;
   p->bn_count = (double)p->N * p->Ho * p->Wo;
+  maybe_enable_halo(p);
   return RYOLO_OK;
 }
 
@@ -593,11 +674,17 @@ int sm_count() {
 constexpr size_t kSmemBudget = 204 * 1024;   // dynamic; + ~20 KB static (transpose tile, scale/shift, barriers)
 
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, cudaStream_t st) {
-  const size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2;
-  int stages = (int)((kSmemBudget - 1024) / stage_bytes);
+  size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2, fixed = 0;
+  if (p.halo) {
+    p.a_slots = 3;
+    p.a_slot_bytes = (uint32_t)ry_align_up((size_t)(p.TH + 2) * (p.TW + 2) * kBK * 2, 1024);
+    fixed = (size_t)p.a_slots * p.a_slot_bytes;
+    stage_bytes = (size_t)p.BN * kBK * 2;
+  }
+  int stages = (int)((kSmemBudget - 1024 - fixed) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024;
+  const size_t smem = fixed + (size_t)stages * stage_bytes + 1024;
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;
@@ -654,7 +741,8 @@ int encode_and_launch(const void* x, int N, int H, int W, int C, long long cpitc
   {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * W, (cuuint64_t)cpitch * 2 * W * H};
-    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(p.TW * estride), (cuuint32_t)(p.TH * estride), 1};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(p.halo ? p.TW + 2 : p.TW * estride),
+                         (cuuint32_t)(p.halo ? p.TH + 2 : p.TH * estride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -733,6 +821,7 @@ int ryolo_conv2d_dgrad(const void* dy, long long dy_cpitch, int N, int H, int W,
       pick_patch(Hl, Wl, 1, &p.TH, &p.TW);
       p.tiles_h = (Hl + p.TH - 1) / p.TH;
       p.tiles_w = (Wl + p.TW - 1) / p.TW;
+      if (stride == 1) maybe_enable_halo(&p);
       p.BN = pick_bn(Cin);
       if (p.ntaps == 0) {      // no contribution for this parity class (cannot happen for k=3/s=2, k=1/s=1)
         ryolo_set_error("dgrad: empty tap set");
