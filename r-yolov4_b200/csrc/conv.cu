@@ -231,6 +231,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ================================ TMA producer (one lane) ================================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * kBK * 2;
+      const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
       int s = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -248,7 +249,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_expect_tx(bar_afull + 8 * as, halo_bytes);
             tma_load_4d(sA + as * p.a_slot_bytes, &tmA, bar_afull + 8 * as, cb * kBK, ws - 1, hs - 1, img);
             if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
-            for (int tap = 0; tap < p.ntaps; tap++) {
+            for (int tap0 = 0; tap0 < p.ntaps; tap0++) {
+              int tap = tap0 + (int)(blockIdx.x % 9u);
+              if (tap >= p.ntaps) tap -= p.ntaps;
               mbar_wait(bar_empty + 8 * s, phase ^ 1u);
               mbar_expect_tx(bar_full + 8 * s, kBBytes);
               tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * kBK, n0);
@@ -257,7 +260,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           }
           continue;
         }
-        for (int kb = 0; kb < KB; kb++) {
+        for (int kb0 = 0; kb0 < KB; kb0++) {
+          // every CTA walks the K blocks in its own rotation: otherwise all 148 CTAs request the SAME weight tile
+          // from the same L2 lines at the same time (the sum is order-independent up to fp32 rounding, and the
+          // tile -> CTA map is static, so results stay reproducible)
+          int kb = kb0 + krot;
+          if (kb >= KB) kb -= KB;
           const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
           mbar_wait(bar_empty + 8 * s, phase ^ 1u);
           mbar_expect_tx(bar_full + 8 * s, a_bytes + kBBytes);
@@ -284,7 +292,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             mbar_wait(bar_afull + 8 * hslot, hphase);
             tc_fence_after();
             const uint32_t ah = sA + hslot * p.a_slot_bytes;
-            for (int tap = 0; tap < p.ntaps; tap++) {
+            for (int tap0 = 0; tap0 < p.ntaps; tap0++) {
+              int tap = tap0 + (int)(blockIdx.x % 9u);
+              if (tap >= p.ntaps) tap -= p.ntaps;
               mbar_wait(bar_full + 8 * s, phase);
               tc_fence_after();
               const uint32_t a0 = ah + (uint32_t)((p.tap_dh[tap] + 1) * (p.TW + 2) + (p.tap_dw[tap] + 1)) * 128u;
@@ -292,7 +302,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
               for (int k = 0; k < kBK / 16; k++) {
                 umma_bf16(d_tmem, umma_desc_k_sw128_view(a0 + k * 32, sbo, p.halo == 2),
-                          umma_desc_k_sw128(b0 + k * 32), idesc, (cb | tap | k) ? 1u : 0u);
+                          umma_desc_k_sw128(b0 + k * 32), idesc, (cb | tap0 | k) ? 1u : 0u);
               }
               umma_commit(bar_empty + 8 * s);
               if (++s == STAGES) { s = 0; phase ^= 1u; }
