@@ -61,6 +61,12 @@ int ryolo_decode_kfiou(const float* level, int64_t B, int na, int gs, int nc, fl
 size_t ryolo_pos_record_bytes(void);
 size_t ryolo_loss_workspace(int64_t B, int na, const int32_t* grid_hw /* host [3][2] */, int64_t T);
 
+/* KFLoss()(pred, target) -> (loss, KFIoU) (lib/loss.py:81-150) on N pairs, O(N) (the reference's accidental
+ * [N,1]+[N] -> [N,N] broadcast at :114,:148 is reproduced in value only).  pred/target device fp32 [N,5]
+ * (x,y,w,h,theta rad); kfiou [N]; grad = d loss/d pred [N,5] or NULL; loss [1]; workspace >= 16 bytes.           */
+int ryolo_kfloss(const float* pred, const float* target, int64_t N, float* kfiou, float* grad, float* loss,
+                 void* workspace, size_t ws_bytes, void* stream);
+
 /* ComputeCSLLoss.build_targets (lib/loss.py:270-331, rotated=0) /
  * ComputeKFIoULoss.build_targets (lib/loss.py:427-492, rotated=1).
  *   targets device [T,tcols] (img, cls, x, y, w, h, theta, ...); anchors device [3,na,3] (w,h,rad)

@@ -28,6 +28,7 @@ SIGNATURES = {
                                   _sz, _vp]),
     "ryolo_decode_csl": (_i32, [_vp, _i64, _i32, _i32, _f32, ctypes.POINTER(_f32), _vp, _i64, _i64, _vp]),
     "ryolo_decode_kfiou": (_i32, [_vp, _i64, _i32, _i32, _i32, _f32, _vp, _vp, _i64, _i64, _vp]),
+    "ryolo_kfloss": (_i32, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_pos_record_bytes": (_sz, []),
     "ryolo_loss_workspace": (_sz, [_i64, _i32, ctypes.POINTER(ctypes.c_int32), _i64]),
     "ryolo_build_targets": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i64, ctypes.POINTER(ctypes.c_int32), _vp, _vp,

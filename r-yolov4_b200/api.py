@@ -3,7 +3,7 @@ test.py / detect.py use, under their real names plus the aliases BASELINE.json's
 from ._lib import RyoloError, SO_PATH, lib
 from .lib.general import (nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
                           post_process_device)
-from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss
+from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
 from .train_step import TrainStep
 
@@ -19,6 +19,6 @@ def compute_loss(model, hyp, mode="csl"):
     return ComputeCSLLoss(model, hyp) if mode == "csl" else ComputeKFIoULoss(model, hyp)
 
 
-__all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "compute_loss", "post_process",
+__all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
            "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "RyoloError", "SO_PATH", "lib"]

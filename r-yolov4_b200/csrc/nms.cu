@@ -60,6 +60,7 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
 
   __shared__ RPrep srow[kTile], scol[kTile];
   __shared__ float qx[2][kTile], qy[2][kTile], qr[2][kTile];
+  __shared__ float qw[2][kTile], qh[2][kTile], qc[2][kTile], qs[2][kTile], qa[2][kTile];   // SoA for the early-outs
   __shared__ unsigned short queue[kTile * kTile];
   __shared__ unsigned long long tmask[kTile];
   __shared__ int qn;
@@ -69,16 +70,19 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
     int g = rb * kTile + tid;
     RPrep p = prep[min(g, K - 1)];
     srow[tid] = p; qx[0][tid] = p.cx; qy[0][tid] = p.cy; qr[0][tid] = p.reach;
+    qw[0][tid] = p.w; qh[0][tid] = p.h; qc[0][tid] = p.c2; qs[0][tid] = p.s2; qa[0][tid] = p.area;
     tmask[tid] = 0ull;
   } else if (tid < 2 * kTile) {
     int t = tid - kTile, g = cb * kTile + t;
     RPrep p = prep[min(g, K - 1)];
     scol[t] = p; qx[1][t] = p.cx; qy[1][t] = p.cy; qr[1][t] = p.reach;
+    qw[1][t] = p.w; qh[1][t] = p.h; qc[1][t] = p.c2; qs[1][t] = p.s2; qa[1][t] = p.area;
   }
   if (tid == 0) qn = 0;
   __syncthreads();
 
   const bool use_reject = thr >= 0.f;  // IoU==0 pairs only matter when thr < 0
+  const bool use_bounds = thr >= 1e-6f; // area-ratio bound + separating-axis test (see rbox_cannot_exceed)
   const int lane = tid & 31;
 #pragma unroll 4
   for (int p = tid; p < kTile * kTile; p += 256) {
@@ -88,6 +92,9 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
     if (live && use_reject) {
       float dx = qx[0][i] - qx[1][j], dy = qy[0][i] - qy[1][j], rr = qr[0][i] + qr[1][j];
       live = !(dx * dx + dy * dy > rr * rr);
+      if (live && use_bounds)
+        live = !rbox_cannot_exceed(qx[0][i], qy[0][i], qw[0][i], qh[0][i], qc[0][i], qs[0][i], qa[0][i], qx[1][j],
+                                   qy[1][j], qw[1][j], qh[1][j], qc[1][j], qs[1][j], qa[1][j], thr);
     }
     unsigned b = __ballot_sync(0xffffffffu, live);
     if (b) {

@@ -51,6 +51,45 @@ __device__ __forceinline__ bool rbox_far(const RPrep& a, const RPrep& b) {
   return dx * dx + dy * dy > rr * rr;
 }
 
+// Sound early-outs for the NMS decision  IoU(A,B) > thr  (thr >= 1e-6): true => the reference IoU certainly does not
+// exceed thr, so the pair can skip the polygon clip.
+//   (1) area bound: IoU <= min(area)/max(area); 0.1 % margin covers fp32 rounding of the clipped area
+//   (2) separating-axis test on the four box axes with a margin far above the +-EPS slack of Appendix B step 3
+//       (a disjoint pair can only produce a sliver of IoU << 1e-6)
+__device__ __forceinline__ bool rbox_cannot_exceed(float acx, float acy, float aw, float ah, float ac2, float as2,
+                                                   float aarea, float bcx, float bcy, float bw, float bh, float bc2,
+                                                   float bs2, float barea, float thr) {
+  const float amin = fminf(aarea, barea), amax = fmaxf(aarea, barea);
+  if (amin < thr * 0.999f * amax) return true;
+  const float dx = bcx - acx, dy = bcy - acy;
+  // half-extent vectors: w-axis (c2*w, -s2*w), h-axis (s2*h, c2*h)   [c2 = cos/2, s2 = sin/2]
+  const float awx = ac2 * aw, awy = -as2 * aw, ahx = as2 * ah, ahy = ac2 * ah;
+  const float bwx = bc2 * bw, bwy = -bs2 * bw, bhx = bs2 * bh, bhy = bc2 * bh;
+  const float margin = 0.01f + 1e-4f * (fabsf(aw) + fabsf(ah) + fabsf(bw) + fabsf(bh));
+  // unit axes of A: (2*ac2, -2*as2) and (2*as2, 2*ac2); of B likewise
+  {
+    const float nx = 2.f * ac2, ny = -2.f * as2;
+    const float sep = fabsf(nx * dx + ny * dy) - (0.5f * fabsf(aw) + fabsf(nx * bwx + ny * bwy) + fabsf(nx * bhx + ny * bhy));
+    if (sep > margin) return true;
+  }
+  {
+    const float nx = 2.f * as2, ny = 2.f * ac2;
+    const float sep = fabsf(nx * dx + ny * dy) - (0.5f * fabsf(ah) + fabsf(nx * bwx + ny * bwy) + fabsf(nx * bhx + ny * bhy));
+    if (sep > margin) return true;
+  }
+  {
+    const float nx = 2.f * bc2, ny = -2.f * bs2;
+    const float sep = fabsf(nx * dx + ny * dy) - (0.5f * fabsf(bw) + fabsf(nx * awx + ny * awy) + fabsf(nx * ahx + ny * ahy));
+    if (sep > margin) return true;
+  }
+  {
+    const float nx = 2.f * bs2, ny = 2.f * bc2;
+    const float sep = fabsf(nx * dx + ny * dy) - (0.5f * fabsf(bh) + fabsf(nx * awx + ny * awy) + fabsf(nx * ahx + ny * ahy));
+    if (sep > margin) return true;
+  }
+  return false;
+}
+
 __device__ __forceinline__ void rcorners(float cx, float cy, const RPrep& b, V2 (&p)[4]) {
   p[0].x = fa(fa(cx, fm(b.s2, b.h)), fm(b.c2, b.w));
   p[0].y = fs(fa(cy, fm(b.c2, b.h)), fm(b.s2, b.w));

@@ -42,6 +42,42 @@ def _run_loss(cfg, targets, levels, need_grad):
     return items, grads
 
 
+class _KFLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target):
+        L.require_cuda(pred, "pred")
+        p, t = pred.detach().contiguous().float(), target.detach().contiguous().float()
+        N = p.shape[0]
+        dev = p.device
+        kfiou = torch.empty(N, dtype=torch.float32, device=dev)
+        grad = torch.empty_like(p) if ctx.needs_input_grad[0] else None
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        ws = L.workspace(16, dev, "kfloss")
+        L.check(L.lib().ryolo_kfloss(L.ptr(p), L.ptr(t), N, L.ptr(kfiou), L.ptr(grad), L.ptr(loss), L.ptr(ws), 16,
+                                     L.stream()))
+        L.count(2)
+        ctx.grad = grad
+        ctx.mark_non_differentiable(kfiou)
+        return loss.reshape(()), kfiou
+
+    @staticmethod
+    def backward(ctx, gloss, _gk):
+        g = ctx.grad
+        ctx.grad = None
+        return (g * gloss if g is not None else None), None
+
+
+class KFLoss(torch.nn.Module):
+    """Drop-in for lib/loss.py:81-150 (fun='exp', alpha=3): forward(pred[N,5], target[N,5]) -> (loss, KFIoU[N])."""
+
+    def __init__(self, fun='exp', alpha=3.0):
+        super().__init__()
+        assert fun == 'exp' and alpha == 3.0, "only the reference's live configuration (exp, alpha=3) is implemented"
+
+    def forward(self, pred, target):
+        return _KFLossFn.apply(pred, target)
+
+
 class _FusedLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cfg, targets, *levels):

@@ -121,3 +121,28 @@ def test_loss_vs_oracle_bigger(mode, nc, S, bs, per_img):
     for ix, s in zip(bt[-2], asg):
         for a, b in zip(ix, (s["b"], s["a"], s["gj"], s["gi"])):
             assert torch.equal(a.cpu(), b)
+
+
+def test_kfloss_standalone_golden_and_scale():
+    """KFLoss drop-in (lib/loss.py:81-150): golden from the reference's N x N form; then BASELINE config 4 size
+    (50k pairs x 32 images) against the O(N) oracle."""
+    import ryolo_b200 as R
+    g = load("kfloss.pt")
+    p = g["pred"].clone().cuda().requires_grad_(True)
+    loss, kfiou = R.KFLoss()(p, g["target"].cuda())
+    loss.backward()
+    assert rel_err(kfiou.cpu(), g["kfiou"]) < TOL
+    assert abs(float(loss) - float(g["loss"])) <= TOL * abs(float(g["loss"]))
+    assert rel_err(p.grad.cpu(), g["grad"]) < 2e-4
+    gen = torch.Generator().manual_seed(9)
+    N = 50000 * 32 + 3                                      # ragged tail on purpose
+    pr = torch.cat((torch.rand(N, 2, generator=gen) * 2 - 0.5, torch.rand(N, 2, generator=gen) * 8 + 0.5,
+                    (torch.rand(N, 1, generator=gen) - 0.5) * 3.14), 1)
+    tg = torch.cat((torch.rand(N, 2, generator=gen), torch.rand(N, 2, generator=gen) * 8 + 0.5,
+                    (torch.rand(N, 1, generator=gen) - 0.5) * 3.14), 1)
+    ref_loss, ref_k = hp.kf_loss(pr, tg)
+    loss, kfiou = R.KFLoss()(pr.cuda(), tg.cuda())
+    assert abs(float(loss) - float(ref_loss)) <= TOL * abs(float(ref_loss))
+    assert rel_err(kfiou.cpu(), ref_k) < TOL
+    empty = R.KFLoss()(torch.zeros(0, 5).cuda(), torch.zeros(0, 5).cuda())
+    assert float(empty[0]) == 0.0 and empty[1].numel() == 0
