@@ -36,6 +36,29 @@ if __name__ == "__main__":
         ms = float(np.median(ts))
         out[f"nc{nc}_conf{conf}_iou{iou}"] = dict(ms=ms, boxes_per_s=64 * 100000 / ms * 1e3, survivors=float(n.float().mean()))
         del pred
+    # ---- BASELINE config 4: KFIoU loss on 50k pairs/image x 256 images (563 MB of pairs: larger than L2)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    N = 50000 * 256
+    pr = torch.cat((torch.rand(N, 2, device="cuda") * 2 - 0.5, torch.rand(N, 2, device="cuda") * 8 + 0.5,
+                    (torch.rand(N, 1, device="cuda") - 0.5) * 3.14), 1).contiguous()
+    tg = torch.cat((torch.rand(N, 2, device="cuda"), torch.rand(N, 2, device="cuda") * 8 + 0.5,
+                    (torch.rand(N, 1, device="cuda") - 0.5) * 3.14), 1).contiguous()
+    kf = R.KFLoss()
+    for grad, bpp in ((False, 44), (True, 64)):
+        p = pr.clone().requires_grad_(grad)
+        ts = []
+        for i in range(iters + 2):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize(); a.record()
+            loss, k = kf(p, tg)
+            b.record(); torch.cuda.synchronize()
+            if i >= 2:
+                ts.append(a.elapsed_time(b))
+        ms = float(np.median(ts))
+        out["kfloss_fwd_bwd" if grad else "kfloss_fwd"] = dict(ms=ms, pairs=N, gbs=N * bpp / ms / 1e6,
+                                                                frac_hbm=N * bpp / ms / 1e6 / peaks["hbm_gbs"])
     print(json.dumps(out, indent=1))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(out, open(os.path.join(ROOT, "gpurun_out", "nms_bench.json"), "w"), indent=1)
