@@ -206,6 +206,53 @@ __device__ __noinline__ float rbox_iou_full(const RPrep& A, const RPrep& B) {
   return __fdiv_rn(inter, fs(fa(A.area, B.area), inter));
 }
 
+// Fast fp32 estimate of the same skew IoU by Sutherland-Hodgman clipping of A's rectangle against B's four edges
+// (<= 8 vertices, no sort, no fp64).  It is NOT bit-identical with Appendix B; the NMS kernel only trusts it when the
+// estimate is far (> 2e-3) from the threshold and re-runs rbox_iou_full otherwise, so decisions stay exact.
+__device__ __forceinline__ float rbox_iou_fast(const RPrep& A, const RPrep& B) {
+  if (A.area < 1e-12f || B.area < 1e-12f) return 0.f;
+  // work in A-centred coordinates
+  V2 pa[4], pb[4];
+  rcorners(0.f, 0.f, A, pa);
+  rcorners(B.cx - A.cx, B.cy - A.cy, B, pb);
+  float px[9], py[9], qx[9], qy[9];
+  int n = 4;
+#pragma unroll
+  for (int i = 0; i < 4; i++) { px[i] = pa[i].x; py[i] = pa[i].y; }
+  const float orient = (pb[1].x - pb[0].x) * (pb[2].y - pb[1].y) - (pb[1].y - pb[0].y) * (pb[2].x - pb[1].x);
+  const float sgn = orient >= 0.f ? 1.f : -1.f;
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    const float ex = pb[(e + 1) & 3].x - pb[e].x, ey = pb[(e + 1) & 3].y - pb[e].y;
+    const float bx = pb[e].x, by = pb[e].y;
+    int m = 0;
+    float sx = px[n - 1], sy = py[n - 1];
+    float ds = sgn * (ex * (sy - by) - ey * (sx - bx));
+    for (int i = 0; i < n; i++) {
+      const float cx = px[i], cy = py[i];
+      const float dc = sgn * (ex * (cy - by) - ey * (cx - bx));
+      if ((dc >= 0.f) != (ds >= 0.f)) {            // edge s->c crosses the clip line
+        const float t = ds / (ds - dc);
+        qx[m] = sx + t * (cx - sx);
+        qy[m] = sy + t * (cy - sy);
+        m++;
+      }
+      if (dc >= 0.f) { qx[m] = cx; qy[m] = cy; m++; }
+      sx = cx; sy = cy; ds = dc;
+    }
+    n = m;
+    if (n == 0) return 0.f;
+    for (int i = 0; i < n; i++) { px[i] = qx[i]; py[i] = qy[i]; }
+  }
+  float a2 = 0.f;
+  for (int i = 0; i < n; i++) {
+    const int j = (i + 1 == n) ? 0 : i + 1;
+    a2 += px[i] * py[j] - px[j] * py[i];
+  }
+  const float inter = 0.5f * fabsf(a2);
+  return inter / (A.area + B.area - inter);
+}
+
 // IoU(A, B) with A = the higher-scored ("row") box, B = the candidate ("column") box.
 __device__ __forceinline__ float rbox_iou(const RPrep& A, const RPrep& B) {
   if (rbox_far(A, B)) return 0.f;
