@@ -140,3 +140,17 @@ def test_train_steps_reduce_loss_and_keep_state_dict_contract():
     with torch.no_grad():
         lv, infer = m(img, training=False)
     assert torch.isfinite(infer).all()
+
+
+def test_baseline_config1_train_step_416_bs2():
+    """BASELINE configs[0] shape (yolov4 csl nc=2, 416x416, bs=2, 20 targets/img): one native training step runs,
+    every parameter moves, loss items are finite, state-dict contract intact."""
+    R, m, img, tg, crit = _model_and_batch("yolov4", "csl", 2, S=416, bs=2)
+    tg = make_targets(1, 2, 20, 2, True).cuda()
+    before = {k: v.clone() for k, v in m.state_dict().items() if v.is_floating_point()}
+    step = R.TrainStep(m, crit, lr=0.01)
+    items = step(img, tg)
+    assert torch.isfinite(items).all() and float(items[4]) > 0
+    after = m.state_dict()
+    moved = sum(int(not torch.equal(after[k], v)) for k, v in before.items())
+    assert moved == len(before), (moved, len(before))
