@@ -95,12 +95,23 @@ def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
         bn = seq[1]
         ops.bn_act_bwd(ds, raw, aff[0], aff[1], aff[2], aff[3], "linear", sums[:2 * C] if first else sums[2 * C:],
                      raw, param_grads[id(bn.weight)], param_grads[id(bn.bias)])
-        ops.conv2d_wgrad(x, raw, C, k, mod.s, sink.buffer(seq[0].weight))
+        sink.wgrad(x, raw, C, k, mod.s, seq[0].weight)
         gx, acc = G.writable(x)
         ops.conv2d_dgrad(raw, packed_t.get(seq[0].weight, transpose=True), x.C, k, mod.s, gx, acc)
         G.mark(x)
         first = False
 
+
+
+_SIDE = {}
+
+
+def _side_stream(dev):
+    """One extra stream per device for the weight-gradient GEMMs (see run_backward)."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(dev)
+    return _SIDE[key]
 
 
 class _WgradSink:
@@ -113,9 +124,24 @@ class _WgradSink:
             param_grads is getattr(model, "_grad_views", None)
         self.model = model
         self.pending = []
+        self.keep = []
+        self.side = _side_stream(next(iter(param_grads.values())).device)
         if self.fused:
             self.views = model.wgrad_scratch()
             model._wg_flat.zero_()
+
+    def wgrad(self, x, dy, Cout, k, stride, weight, stem=False, keep=()):
+        """Launch conv_wgrad on the side stream: it only reads x and dy (= d raw, final once the BN backward of this
+        layer has run), so it overlaps the dgrad of this layer and the HBM-bound BN backward of the next one instead
+        of serialising with them (its CTAs leave most of an SM's bandwidth idle)."""
+        buf = self.buffer(weight, stem)
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ev)
+            ops.conv2d_wgrad(x, dy, Cout, k, stride, buf)
+        self.keep.extend(keep)               # temporaries the side stream still reads: freed after the join
 
     def buffer(self, weight, stem=False):
         if self.fused:
@@ -126,6 +152,8 @@ class _WgradSink:
         return buf
 
     def finish(self):
+        torch.cuda.current_stream().wait_stream(self.side)      # join before anything the GEMMs read is released
+        self.keep.clear()
         if self.fused:
             self.model.unpack_wgrads()
             return
@@ -167,7 +195,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             if mul is not None:        # yolov7: y = im * (conv(x + ia) + b)   (model/neck.py:201,208,215)
                 _implicit_head_grads(model, mod, gl, y, mul, param_grads)
             dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias))
-            ops.conv2d_wgrad(x, dpre, Cout, 1, 1, sink.buffer(conv.weight))
+            sink.wgrad(x, dpre, Cout, 1, 1, conv.weight, keep=(dpre,))
             w = conv.weight.data
             if Cpad != Cout:
                 w = torch.cat((w, w.new_zeros(Cpad - Cout, *w.shape[1:])), 0)
@@ -188,7 +216,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
                            pg(bn.weight), pg(bn.bias))     # d raw overwrites raw in place
             soff += 2 * C
             k = 1 if mod.stem else mod.k
-            ops.conv2d_wgrad(x, raw, C, k, mod.s, sink.buffer(mod.conv[0].weight, mod.stem))
+            sink.wgrad(x, raw, C, k, mod.s, mod.conv[0].weight, mod.stem)
             if not mod.stem:
                 gx, acc = G.writable(x)
                 ops.conv2d_dgrad(raw, mod.weight_t(), x.C, mod.k, mod.s, gx, acc)
