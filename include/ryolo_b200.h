@@ -157,10 +157,11 @@ int ryolo_maxpool(const void* x, long long xp, int N, int H, int W, int C, int k
 /* nn.Upsample(scale_factor=factor, nearest) (model/neck.py:9,19) / strided copy into a concat slice     */
 int ryolo_resize_copy(const void* x, long long xp, int N, int H, int W, int C, int factor, void* y, long long yp,
                       void* stream);
-/* fp32 NCHW image [N,3,H,W] -> bf16 [N,H,W,64] 3x3 patches (27 taps + zero pad) for the stem conv       */
-int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stream);
-/* state-dict OIHW fp32 -> bf16: layout 0 [Cout][kh][kw][Cin]; 1 (stem) [Cout][64] in the im2col channel
- * order; 2 (dgrad) [Cin][kh][kw][Cout]                                                                     */
+/* fp32 NCHW image [N,3,H,W] -> bf16 [N,Ho,Wo,Kpad] k x k / stride patches (3*k*k values + zero pad), pad=(k-1)/2:
+ * the 3-channel stem conv (3x3/s1 in yolov4/v7, 6x6/s2 in yolov5) becomes a Kpad-channel 1x1 conv             */
+int ryolo_stem_im2col(const float* img, int N, int H, int W, int k, int stride, int Kpad, void* y, void* stream);
+/* state-dict OIHW fp32 -> bf16: layout 0 [Cout][kh][kw][Cin]; 2 (dgrad) [Cin][kh][kw][Cout]; >= 8 (stem)
+ * [Cout][Kpad = layout] in the im2col channel order                                                                     */
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream);
 /* all conv weights of a model in one launch.  table (DEVICE array, sorted by `first`): tensor i holds flat
  * elements [first, first + Cout*Cin*k*k) of the launch; dst = layout 0 (or the stem's [Cout][64], padding
@@ -207,6 +208,9 @@ int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch,
  *   g = grad + wd*p;  buf = first ? g : momentum*buf + g;  p -= lr * (nesterov ? g + momentum*buf : buf)      */
 int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, float lr, float momentum,
                    float weight_decay, int nesterov, int first, void* stream);
+/* torch.optim.Adam step (train.py:153-154) on flat fp32 buffers; step counts from 1 (bias correction)           */
+int ryolo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream);
 
 #ifdef __cplusplus
 }

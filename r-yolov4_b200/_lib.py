@@ -64,7 +64,7 @@ SIGNATURES.update({
     "ryolo_scale_shift_act": (_i32, [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i32, _vp, _ll, _vp, _ll, _ll, _i32, _vp]),
     "ryolo_maxpool": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
     "ryolo_resize_copy": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
-    "ryolo_stem_im2col": (_i32, [_vp, _i32, _i32, _i32, _vp, _vp]),
+    "ryolo_stem_im2col": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ryolo_pack_weights": (_i32, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ryolo_pack_weights_multi": (_i32, [_vp, _i32, _ll, _vp]),
     "ryolo_conv2d_dgrad": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _ll, _i32, _vp]),
@@ -78,6 +78,7 @@ SIGNATURES.update({
     "ryolo_upsample2x_bwd": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _vp, _ll, _i32, _vp]),
     "ryolo_head_grad_pack": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ryolo_sgd_step": (_i32, [_vp, _vp, _vp, _ll, _f32, _f32, _f32, _i32, _i32, _vp]),
+    "ryolo_adam_step": (_i32, [_vp, _vp, _vp, _vp, _ll, _f32, _f32, _f32, _f32, _f32, _i32, _vp]),
 })
 
 _lib = None

@@ -350,6 +350,20 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
   }
 }
 
+// torch.optim.Adam (train.py:154): m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            long long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gi = g[i] + wd * p[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= (lr / bc1) * mi / (sqrtf(vi) / sqrtf(bc2) + eps);
+  }
+}
+
 inline int grid_for(long long total, int block) {
   long long g = (total + block - 1) / block;
   const long long cap = 148ll * 32;
@@ -461,6 +475,17 @@ int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, flo
   if (n <= 0) return RYOLO_OK;
   sgd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, buf, n, lr, momentum, weight_decay,
                                                                 nesterov, first);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                    float beta1, float beta2, float eps, float weight_decay, int step, void* stream) {
+  RY_CHECK_ARG(step >= 1, "adam_step: step counts from 1");
+  if (n <= 0) return RYOLO_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                 eps, weight_decay, bc1, bc2);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

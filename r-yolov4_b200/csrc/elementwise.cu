@@ -220,46 +220,40 @@ resize_copy_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int
 }
 
 // ------------------------------------------------------------------------------------ stem im2col
-// img fp32 NCHW [N,3,H,W] -> bf16 [N,H,W,64]: channel (kh*3+kw)*3 + ci holds img[ci, h+kh-1, w+kw-1] (zero
-// padded), channels 27..63 are zero.  The 3->32 3x3 stem then runs as a K=64 1x1 conv on the tensor cores.
+// img fp32 NCHW [N,3,H,W] -> bf16 [N,Ho,Wo,Kpad]: channel (kh*k+kw)*3 + ci holds img[ci, ho*s+kh-pad, wo*s+kw-pad]
+// (zero padded), channels 3*k*k..Kpad-1 are zero.  The 3-channel stem (3x3/s1 of yolov4/v7, 6x6/s2 of yolov5) then
+// runs as a K=Kpad 1x1 conv on the tensor cores.  One thread per (pixel, 8 channels).
 __global__ void __launch_bounds__(256)
-stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
-  const long long total = (long long)N * H * W;
-  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
-       pix += (long long)gridDim.x * blockDim.x) {
-    const int w = (int)(pix % W), h = (int)((pix / W) % H), n = (int)(pix / ((long long)W * H));
-    float f[32];
+stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, int k, int s, int pad, int Kpad, int Ho, int Wo,
+                   __nv_bfloat16* __restrict__ y) {
+  const int groups = Kpad >> 3;
+  const long long total = (long long)N * Ho * Wo * groups;
+  const int kreal = 3 * k * k;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long pix = i / groups;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float f[8];
 #pragma unroll
-    for (int j = 0; j < 32; j++) f[j] = 0.f;
-#pragma unroll
-    for (int kh = 0; kh < 3; kh++) {
-      const int hi = h + kh - 1;
-#pragma unroll
-      for (int kw = 0; kw < 3; kw++) {
-        const int wi = w + kw - 1;
-        if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
-#pragma unroll
-          for (int ci = 0; ci < 3; ci++)
-            f[(kh * 3 + kw) * 3 + ci] = __ldg(img + (((long long)n * 3 + ci) * H + hi) * W + wi);
-        }
+    for (int j = 0; j < 8; j++) {
+      const int kk = 8 * g + j;
+      float v = 0.f;
+      if (kk < kreal) {
+        const int tap = kk / 3, ci = kk - 3 * tap;
+        const int kh = tap / k, kw = tap - kh * k;
+        const int hi = ho * s + kh - pad, wi = wo * s + kw - pad;
+        if (hi >= 0 && hi < H && wi >= 0 && wi < W) v = __ldg(img + (((long long)n * 3 + ci) * H + hi) * W + wi);
       }
+      f[j] = v;
     }
-    uint4* o = reinterpret_cast<uint4*>(y + pix * 64);
-#pragma unroll
-    for (int g = 0; g < 4; g++) {
-      const float t[8] = {f[8 * g], f[8 * g + 1], f[8 * g + 2], f[8 * g + 3], f[8 * g + 4], f[8 * g + 5], f[8 * g + 6],
-                          f[8 * g + 7]};
-      o[g] = pack8(t);
-    }
-    const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int g = 4; g < 8; g++) o[g] = z;
+    *reinterpret_cast<uint4*>(y + pix * Kpad + 8 * g) = pack8(f);
   }
 }
 
 // ------------------------------------------------------------------------------------ weight packing
-// OIHW fp32 -> [Cout][kh][kw][Cin] bf16.  stem == 1: [Cout,3,3,3] -> [Cout][64] in the im2col channel order.
-// stem == 2 (transpose, for dgrad): -> [Cin][kh][kw][Cout].
+// OIHW fp32 -> [Cout][kh][kw][Cin] bf16 (stem == 0).  stem == 2 (transpose, for dgrad): -> [Cin][kh][kw][Cout].
+// stem >= 8: the 3-channel stem, [Cout,3,k,k] -> [Cout][Kpad = stem] in the im2col channel order (zero padded).
 __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int Cin, int k, int stem,
                                     __nv_bfloat16* __restrict__ out) {
   if (stem == 2) {
@@ -273,16 +267,16 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
     }
     return;
   }
-  const int Kp = stem == 1 ? 64 : k * k * Cin;
+  const int Kp = stem >= 8 ? stem : k * k * Cin;
   const long long total = (long long)Cout * Kp;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int co = (int)(i / Kp), kk = (int)(i % Kp);
     float v = 0.f;
-    if (stem == 1) {
-      if (kk < 27) {
+    if (stem >= 8) {
+      if (kk < 3 * k * k) {
         const int tap = kk / 3, ci = kk % 3;
-        v = w[((long long)co * 3 + ci) * 9 + tap];
+        v = w[((long long)co * 3 + ci) * k * k + tap];
       }
     } else {
       const int tap = kk / Cin, ci = kk % Cin;
@@ -312,7 +306,7 @@ pack_weights_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, lon
     __nv_bfloat16* dst = (__nv_bfloat16*)e.dst;
     __nv_bfloat16* dst_t = (__nv_bfloat16*)e.dst_t;
     if (e.stem) {
-      dst[(long long)co * 64 + tap * 3 + ci] = v;                       // [Cout][64] im2col order (pad pre-zeroed)
+      dst[(long long)co * e.stem + tap * 3 + ci] = v;                   // [Cout][Kpad] im2col order (pad pre-zeroed)
     } else {
       dst[((long long)co * kk + tap) * e.Cin + ci] = v;                 // [Cout][kh][kw][Cin]
       if (dst_t) dst_t[((long long)ci * kk + tap) * e.Cout + co] = v;   // [Cin][kh][kw][Cout]
@@ -338,7 +332,7 @@ unpack_wgrad_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, lon
     const int ci = (int)((r / kk) % e.Cin);
     const int co = (int)(r / ((long long)kk * e.Cin));
     const float* src = e.src;
-    const float v = e.stem ? src[(long long)co * 64 + tap * 3 + ci] : src[((long long)co * kk + tap) * e.Cin + ci];
+    const float v = e.stem ? src[(long long)co * e.stem + tap * 3 + ci] : src[((long long)co * kk + tap) * e.Cin + ci];
     ((float*)e.dst)[r] += v;
   }
 }
@@ -427,10 +421,14 @@ int ryolo_resize_copy(const void* x, long long xp, int N, int H, int W, int C, i
   return RYOLO_OK;
 }
 
-int ryolo_stem_im2col(const float* img, int N, int H, int W, void* y, void* stream) {
-  const long long total = (long long)N * H * W;
+int ryolo_stem_im2col(const float* img, int N, int H, int W, int k, int stride, int Kpad, void* y, void* stream) {
+  RY_CHECK_ARG((k == 3 || k == 6) && stride >= 1 && Kpad % 8 == 0 && Kpad >= 3 * k * k, "stem_im2col: bad arguments");
+  const int pad = (k - 1) / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const long long total = (long long)N * Ho * Wo * (Kpad / 8);
   if (total == 0) return RYOLO_OK;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W, (__nv_bfloat16*)y);
+  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W, k, stride, pad, Kpad, Ho, Wo,
+                                                                            (__nv_bfloat16*)y);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }
@@ -451,8 +449,9 @@ int ryolo_unpack_wgrad_multi(const ryolo_pack_entry* table_dev, int n, long long
 
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream) {
   RY_CHECK_ARG(Cout > 0 && Cin > 0 && k > 0, "pack_weights: bad shape");
-  RY_CHECK_ARG(stem != 1 || (Cin == 3 && k == 3), "pack_weights: the stem layout is for 3-channel 3x3 convs");
-  const long long total = (long long)Cout * (stem == 1 ? 64 : k * k * Cin);
+  RY_CHECK_ARG(stem == 0 || stem == 2 || (stem >= 8 && Cin == 3 && stem >= 3 * k * k),
+               "pack_weights: the stem layout is for 3-channel convs with Kpad >= 3*k*k");
+  const long long total = (long long)Cout * (stem >= 8 ? stem : k * k * Cin);
   pack_weights_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(w, Cout, Cin, k, stem,
                                                                              (__nv_bfloat16*)out);
   RY_CHECK_LAUNCH();

@@ -3,7 +3,7 @@ ELAN backbone (model/backbone.py:69-101).  Attribute names follow the reference 
 import torch.nn as nn
 
 from .. import ops
-from .blocks import CSP, ELAN1, SPP, SPPCSPC, Conv, MaxConv
+from .blocks import C3, CSP, ELAN1, SPP, SPPCSPC, SPPF, Conv, MaxConv
 
 
 class Backbonev4(nn.Module):
@@ -17,7 +17,7 @@ class Backbonev4(nn.Module):
         self.spp = SPP(1024, 512)
 
     def forward(self, ctx, img):
-        x = self.cbm0(ctx, ops.stem_im2col(img))
+        x = self.cbm0(ctx, ops.stem_im2col(img, 3, 1))
         feats = []
         for i in range(1, 6):
             x = getattr(self, f"csp{i}")(ctx, getattr(self, f"cbm{i}")(ctx, x))
@@ -42,7 +42,7 @@ class Backbonev7(nn.Module):
         self.spp = SPPCSPC(1024, 512)
 
     def forward(self, ctx, img):
-        x = self.cbs0(ctx, ops.stem_im2col(img))
+        x = self.cbs0(ctx, ops.stem_im2col(img, 3, 1))
         x = self.cbs3(ctx, self.cbs2(ctx, self.cbs1(ctx, x)))
         x = self.elan1(ctx, x)
         d3 = self.elan2(ctx, self.mc1(ctx, x))
@@ -52,7 +52,25 @@ class Backbonev7(nn.Module):
 
 
 class Backbonev5(nn.Module):
+    """yolov5 backbone (model/backbone.py:39-66): 6x6/s2 stem, C3 stages, SPPF."""
+
     def __init__(self):
         super().__init__()
-        raise NotImplementedError("yolov5 (6x6/s2 stem, C3, SPPF) is outside the BASELINE.json configs; "
-                                  "scheduled after the yolov4/yolov7 paths (SURVEY.md §8f N4)")
+        self.cbs0 = Conv(3, 64, 6, 2, "swish")
+        self.cbs1 = Conv(64, 128, 3, 2, "swish")
+        self.csp1 = C3(128, 128, 3)
+        self.cbs2 = Conv(128, 256, 3, 2, "swish")
+        self.csp2 = C3(256, 256, 6)
+        self.cbs3 = Conv(256, 512, 3, 2, "swish")
+        self.csp3 = C3(512, 512, 9)
+        self.cbs4 = Conv(512, 1024, 3, 2, "swish")
+        self.csp4 = C3(1024, 1024, 3)
+        self.spp = SPPF(1024, 1024)
+
+    def forward(self, ctx, img):
+        x = self.cbs0(ctx, ops.stem_im2col(img, 6, 2))
+        x = self.csp1(ctx, self.cbs1(ctx, x))
+        d3 = self.csp2(ctx, self.cbs2(ctx, x))
+        d4 = self.csp3(ctx, self.cbs3(ctx, d3))
+        d5 = self.csp4(ctx, self.cbs4(ctx, d4))
+        return d3, d4, self.spp(ctx, d5)

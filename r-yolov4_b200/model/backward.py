@@ -147,7 +147,8 @@ class _WgradSink:
         if self.fused:
             return self.views[id(weight)]
         Cout, Cin, k, _ = weight.shape
-        buf = torch.zeros(Cout * (64 if stem else k * k * Cin), dtype=torch.float32, device=weight.device)
+        buf = torch.zeros(Cout * (ops.stem_kpad(k) if stem else k * k * Cin), dtype=torch.float32,
+                          device=weight.device)
         self.pending.append((weight, buf, stem))
         return buf
 
@@ -215,8 +216,8 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             ops.bn_act_bwd(dout, raw, scale, shift, mean, invstd, mod.act, sums[soff:soff + 2 * C], raw,
                            pg(bn.weight), pg(bn.bias))     # d raw overwrites raw in place
             soff += 2 * C
-            k = 1 if mod.stem else mod.k
-            sink.wgrad(x, raw, C, k, mod.s, mod.conv[0].weight, mod.stem)
+            k, st = (1, 1) if mod.stem else (mod.k, mod.s)
+            sink.wgrad(x, raw, C, k, st, mod.conv[0].weight, mod.stem)
             if not mod.stem:
                 gx, acc = G.writable(x)
                 ops.conv2d_dgrad(raw, mod.weight_t(), x.C, mod.k, mod.s, gx, acc)

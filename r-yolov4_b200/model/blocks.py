@@ -95,22 +95,22 @@ class Conv(nn.Module):
 
     def forward(self, ctx, x, out=None, residual=None, head=None, head_scale=None, head_shift=None):
         w = self.weight()
-        k = 1 if self.stem else self.k
+        k, st = (1, 1) if self.stem else (self.k, self.s)     # the stem's k x k / stride lives in its im2col
         if head is not None:                       # biased linear 1x1 -> fp32 [B,na,gs,gs,ch]
-            y = ops.conv2d(x, w, self.c2, k, self.s, scale=head_scale, shift=head_shift, act="linear", head=head)
+            y = ops.conv2d(x, w, self.c2, k, st, scale=head_scale, shift=head_shift, act="linear", head=head)
             if ctx.tape is not None:
                 ctx.tape.append(("head", self, x, y, head_scale))
             return y
         bn = self.conv[1]
         if not ctx.training:
             scale, shift = _bn_eval_affine(bn, self._affine)
-            return ops.conv2d(x, w, self.c2, k, self.s, out=out, scale=scale, shift=shift, act=self.act,
+            return ops.conv2d(x, w, self.c2, k, st, out=out, scale=scale, shift=shift, act=self.act,
                               residual=residual)
         part, ctr = ctx.stat_slot(self.c2)
         aff = torch.empty(4 * self.c2, dtype=torch.float32, device=ctx.device)
         scale, shift, mean, invstd = aff[:self.c2], aff[self.c2:2 * self.c2], aff[2 * self.c2:3 * self.c2], \
             aff[3 * self.c2:]
-        raw = ops.conv2d(x, w, self.c2, k, self.s, bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
+        raw = ops.conv2d(x, w, self.c2, k, st, bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
         if out is None:
             out = ctx.new(raw.N, raw.H, raw.W, self.c2)
         ops.scale_shift_act(raw, scale, shift, self.act, out, residual=residual)
@@ -204,6 +204,51 @@ class SPP(nn.Module):
         self.cv3(ctx, self.cv2(ctx, self.cv1(ctx, x)), out=src)
         _spp_pools(ctx, src, [(cat.slice(2 * c_, c_), 5), (cat.slice(c_, c_), 9), (cat.slice(0, c_), 13)])
         return self.cv6(ctx, self.cv5(ctx, self.cv4(ctx, cat)), out=out)
+
+
+class C3(nn.Module):
+    """yolov5 CSP bottleneck with 3 convs (model/utils.py:83-95)."""
+
+    def __init__(self, c1, c2, n=1, shortcut=True, e=0.5):
+        super().__init__()
+        c_ = int(c1 * e)
+        self.cv1 = Conv(c1, c_, 1, 1, "swish")
+        self.cv2 = Conv(c1, c_, 1, 1, "swish")
+        self.cv3 = Conv(2 * c_, c2, 1, 1, "swish")
+        self.m = nn.Sequential(*(Bottleneck(c_, c_, shortcut, e=1.0, act="swish") for _ in range(n)))
+        self.c_ = c_
+
+    def forward(self, ctx, x, out=None):
+        cat = ctx.new(x.N, x.H, x.W, 2 * self.c_)                 # [m(cv1(x)) | cv2(x)]
+        y = self.cv1(ctx, x)
+        for i, b in enumerate(self.m):
+            y = b(ctx, y, out=cat.slice(0, self.c_) if i == len(self.m) - 1 else None)
+        self.cv2(ctx, x, out=cat.slice(self.c_, self.c_))
+        return self.cv3(ctx, cat, out=out)
+
+
+class SPPF(nn.Module):
+    """yolov5 SPP-Fast (model/utils.py:247-261): three chained 5x5 pools."""
+
+    def __init__(self, c1, c2, k=5):
+        super().__init__()
+        c_ = c1 // 2
+        self.cv1 = Conv(c1, c_, 1, 1, "swish")
+        self.cv2 = Conv(c_ * 4, c2, 1, 1, "swish")
+        self.m = nn.MaxPool2d(kernel_size=k, stride=1, padding=k // 2)
+        self.c_, self.k = c_, k
+
+    def forward(self, ctx, x, out=None):
+        c_, k = self.c_, self.k
+        cat = ctx.new(x.N, x.H, x.W, 4 * c_)                      # [x, y1, y2, y3]
+        src = self.cv1(ctx, x, out=cat.slice(0, c_))
+        for i in range(1, 4):
+            dst = cat.slice(i * c_, c_)
+            ops.maxpool(src, k, 1, k // 2, out=dst)
+            if ctx.tape is not None:
+                ctx.tape.append(("maxpool", src, dst, k, 1, k // 2))
+            src = dst
+        return self.cv2(ctx, cat, out=out)
 
 
 class SPPCSPC(nn.Module):

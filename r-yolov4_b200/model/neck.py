@@ -5,7 +5,7 @@ import torch
 import torch.nn as nn
 
 from .. import ops
-from .blocks import C5, ELAN2, Conv, ImplicitA, ImplicitM, MaxConv, RepConv
+from .blocks import C3, C5, ELAN2, Conv, ImplicitA, ImplicitM, MaxConv, RepConv
 
 
 def _copy_into(ctx, src, dst, factor=1):
@@ -117,6 +117,46 @@ class Neckv7(nn.Module):
 
 
 class Neckv5(nn.Module):
+    """yolov5 PAN neck (model/neck.py:84-147)."""
+
     def __init__(self, output_ch):
         super().__init__()
-        raise NotImplementedError("yolov5 neck: see Backbonev5")
+        self.conv7 = Conv(1024, 512, 1, 1, 'swish')
+        self.up1 = nn.Upsample(scale_factor=2, mode='nearest')
+        self.csp1 = C3(1024, 512, 3, shortcut=False)
+        self.conv14 = Conv(512, 256, 1, 1, 'swish')
+        self.up2 = nn.Upsample(scale_factor=2, mode='nearest')
+        self.csp2 = C3(512, 256, 3, shortcut=False)
+        self.conv15 = Conv(256, output_ch, 1, 1, 'linear', bn=False, bias=True)
+        self.conv16 = Conv(256, 256, 3, 2, 'swish')
+        self.csp3 = C3(512, 512, 3, shortcut=False)
+        self.conv17 = Conv(512, output_ch, 1, 1, 'linear', bn=False, bias=True)
+        self.conv18 = Conv(512, 512, 3, 2, 'swish')
+        self.csp4 = C3(1024, 1024, 3, shortcut=False)
+        self.conv19 = Conv(1024, output_ch, 1, 1, 'linear', bn=False, bias=True)
+
+    @staticmethod
+    def _head(ctx, head, x, na, ch):
+        return head(ctx, x, head=(na, ch), head_shift=head.conv[0].bias.data)
+
+    def forward(self, ctx, x1, x2, x3, na, ch):
+        N = x1.N
+        pan32 = ctx.new(N, x1.H, x1.W, 1024)                      # [conv7(d5) | conv18(n16)]
+        t32 = self.conv7(ctx, x1, out=pan32.slice(0, 512))
+        cat16 = ctx.new(N, x2.H, x2.W, 1024)                      # [d4 | up(t32)]
+        _copy_into(ctx, x2, cat16.slice(0, 512))
+        _copy_into(ctx, t32, cat16.slice(512, 512), 2)
+        pan16 = ctx.new(N, x2.H, x2.W, 512)                       # [conv14(csp1) | conv16(p8)]
+        t16 = self.conv14(ctx, self.csp1(ctx, cat16), out=pan16.slice(0, 256))
+        cat8 = ctx.new(N, x3.H, x3.W, 512)                        # [d3 | up(t16)]
+        _copy_into(ctx, x3, cat8.slice(0, 256))
+        _copy_into(ctx, t16, cat8.slice(256, 256), 2)
+        p8 = self.csp2(ctx, cat8)
+        h8 = self._head(ctx, self.conv15, p8, na, ch)
+        self.conv16(ctx, p8, out=pan16.slice(256, 256))
+        n16 = self.csp3(ctx, pan16)
+        h16 = self._head(ctx, self.conv17, n16, na, ch)
+        self.conv18(ctx, n16, out=pan32.slice(512, 512))
+        n32 = self.csp4(ctx, pan32)
+        h32 = self._head(ctx, self.conv19, n32, na, ch)
+        return h8, h16, h32

@@ -114,6 +114,7 @@ class Yolo(nn.Module):
         """Pre-allocates the bf16 operand copies of every conv weight and refreshes ALL of them with one kernel
         launch (repack_weights) instead of one launch per layer and layout."""
         import numpy as np_
+        from .. import ops as ops_
         from .blocks import Conv, RepConv
         dev = next(self.parameters()).device
         ents, first = [], 0
@@ -126,14 +127,14 @@ class Yolo(nn.Module):
                 todo.append((m.rbr_1x1[0].weight, m._p1, m._p1t, False))
             for w, pk, pkt, stem in todo:
                 Cout, Cin, k, _ = w.shape
-                pk.w = torch.zeros((Cout, 64 if stem else k * k * Cin), dtype=torch.bfloat16, device=dev)
+                pk.w = torch.zeros((Cout, ops_.stem_kpad(k) if stem else k * k * Cin), dtype=torch.bfloat16, device=dev)
                 pk.pinned = True
                 dt = 0
                 if pkt is not None:
                     pkt.w = torch.empty((Cin, k * k * Cout), dtype=torch.bfloat16, device=dev)
                     pkt.pinned = True
                     dt = pkt.w.data_ptr()
-                ents.append((w, pk.w.data_ptr(), dt, first, Cout, Cin, k, 1 if stem else 0))
+                ents.append((w, pk.w.data_ptr(), dt, first, Cout, Cin, k, ops_.stem_kpad(k) if stem else 0))
                 first += w.numel()
         self._pack_params = [e[0] for e in ents]
         self._pack_meta = [e[1:] for e in ents]
@@ -149,12 +150,12 @@ class Yolo(nn.Module):
             dev = self._flat_grad.device
             sizes = []
             for p, (_, _, _, Cout, Cin, k, stem) in zip(self._pack_params, self._pack_meta):
-                sizes.append((Cout * (64 if stem else k * k * Cin) + 3) // 4 * 4)
+                sizes.append((Cout * (stem if stem else k * k * Cin) + 3) // 4 * 4)
             self._wg_flat = torch.zeros(sum(sizes), dtype=torch.float32, device=dev)
             rows = np_.zeros((len(sizes), 6), dtype=np_.int64)
             self._wg_views, off = {}, 0
             for i, (p, (_, _, first, Cout, Cin, k, stem), n) in enumerate(zip(self._pack_params, self._pack_meta, sizes)):
-                v = self._wg_flat[off:off + Cout * (64 if stem else k * k * Cin)]
+                v = self._wg_flat[off:off + Cout * (stem if stem else k * k * Cin)]
                 self._wg_views[id(p)] = v
                 rows[i, 0], rows[i, 1], rows[i, 3] = v.data_ptr(), self._grad_views[id(p)].data_ptr(), first
                 rows[i, 4], rows[i, 5] = Cout | (Cin << 32), k | (stem << 32)

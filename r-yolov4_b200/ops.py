@@ -133,25 +133,32 @@ def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear"
     return out
 
 
+def stem_kpad(k):
+    """K of the 1x1 conv the 3-channel k x k stem turns into (3*k*k values padded to a multiple of 64)."""
+    return (3 * k * k + 63) // 64 * 64
+
+
 def pack_weights(w_oihw, stem=False, transpose=False):
-    """fp32 OIHW (state-dict layout) -> bf16 [Cout, kh*kw*Cin] ([Cout, 64] for the stem;
+    """fp32 OIHW (state-dict layout) -> bf16 [Cout, kh*kw*Cin] ([Cout, stem_kpad(k)] for the stem;
     [Cin, kh*kw*Cout] with transpose=True, the dgrad operand)."""
     w = w_oihw.detach().contiguous().float()
     Cout, Cin, k, _ = w.shape
-    shape = (Cin, k * k * Cout) if transpose else (Cout, 64 if stem else k * k * Cin)
+    kp = stem_kpad(k) if stem else 0
+    shape = (Cin, k * k * Cout) if transpose else (Cout, kp if stem else k * k * Cin)
     out = torch.empty(shape, dtype=torch.bfloat16, device=w.device)
-    L.check(L.lib().ryolo_pack_weights(_tp(w), Cout, Cin, k, 2 if transpose else (1 if stem else 0), _tp(out),
-                                       L.stream()))
+    L.check(L.lib().ryolo_pack_weights(_tp(w), Cout, Cin, k, 2 if transpose else kp, _tp(out), L.stream()))
     L.count(1)
     return out
 
 
-def stem_im2col(img):
+def stem_im2col(img, k=3, stride=1):
     img = img.contiguous().float()
     N, C, H, W = img.shape
     assert C == 3
-    out = Act.empty(N, H, W, 64, img.device)
-    L.check(L.lib().ryolo_stem_im2col(_tp(img), N, H, W, _vp(out.ptr), L.stream()))
+    Ho, Wo = out_hw(H, W, k, stride)
+    kp = stem_kpad(k)
+    out = Act.empty(N, Ho, Wo, kp, img.device)
+    L.check(L.lib().ryolo_stem_im2col(_tp(img), N, H, W, k, stride, kp, _vp(out.ptr), L.stream()))
     L.count(1)
     return out
 
@@ -228,7 +235,7 @@ def conv2d_wgrad(x, dy, Cout, k, stride, dwk):
 def wgrad_to_oihw(dwk, Cout, Cin, k, stem=False):
     """K-major wgrad scratch -> OIHW tensor (torch glue for the non-fused paths / tests)."""
     if stem:
-        return dwk.view(Cout, 64)[:, :27].reshape(Cout, 3, 3, 3).permute(0, 3, 1, 2).contiguous()
+        return dwk.view(Cout, stem_kpad(k))[:, :3 * k * k].reshape(Cout, k, k, 3).permute(0, 3, 1, 2).contiguous()
     return dwk.view(Cout, k * k, Cin).permute(0, 2, 1).reshape(Cout, Cin, k, k).contiguous()
 
 
@@ -277,4 +284,11 @@ def head_grad_pack(glev, Cpad, mul, dbias):
 def sgd_step(param, grad, buf, lr, momentum, weight_decay, nesterov, first):
     L.check(L.lib().ryolo_sgd_step(_tp(param), _tp(grad), _tp(buf), param.numel(), float(lr), float(momentum),
                                    float(weight_decay), 1 if nesterov else 0, 1 if first else 0, L.stream()))
+    L.count(1)
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+    L.check(L.lib().ryolo_adam_step(_tp(param), _tp(grad), _tp(exp_avg), _tp(exp_avg_sq), param.numel(), float(lr),
+                                    float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),
+                                    L.stream()))
     L.count(1)

@@ -17,9 +17,12 @@ from .model import blocks
 
 class TrainStep:
     def __init__(self, model, compute_loss, lr=0.01, momentum=0.937, nesterov=True, weight_decay=0.0,
-                 process_group=None):
-        self.model, self.crit = model, compute_loss
+                 process_group=None, optimizer="SGD"):
+        if optimizer not in ("SGD", "Adam"):
+            raise NotImplementedError("The specified optimizer is not implemented.")      # train.py:158
+        self.model, self.crit, self.optimizer = model, compute_loss, optimizer
         self.lr, self.momentum, self.nesterov, self.wd = lr, momentum, nesterov, weight_decay
+        self.nstep = 0
         model.autograd = False
         self.flat, self.grad = model.flatten_parameters()
         self.buf = torch.zeros_like(self.flat)
@@ -43,7 +46,13 @@ class TrainStep:
     def step(self):
         if self.world > 1:
             allreduce_mean(self.grad, self.pg)
-        ops.sgd_step(self.flat, self.grad, self.buf, self.lr, self.momentum, self.wd, self.nesterov, self.first)
+        self.nstep += 1
+        if self.optimizer == "Adam":                 # torch.optim.Adam(lr) defaults (train.py:154)
+            if self.first:
+                self.buf2 = torch.zeros_like(self.flat)
+            ops.adam_step(self.flat, self.grad, self.buf, self.buf2, self.lr, self.nstep, weight_decay=self.wd)
+        else:
+            ops.sgd_step(self.flat, self.grad, self.buf, self.lr, self.momentum, self.wd, self.nesterov, self.first)
         self.first = False
         blocks.WEIGHT_EPOCH[0] += 1          # BN-eval affine caches are stale now
         self.model.repack_weights()          # refresh every bf16 operand copy in one launch

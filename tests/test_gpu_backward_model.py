@@ -38,6 +38,9 @@ BLOCKS = [
     ("maxconv", lambda B: B.MaxConv(128), lambda n, x: n.maxconv(x, "blk"), 128, 12),
     ("sppcspc", lambda B: B.SPPCSPC(128, 64), lambda n, x: n.sppcspc(x, "blk"), 128, 13),
     ("repconv", lambda B: B.RepConv(64, 128), lambda n, x: n.repconv(x, "blk"), 64, 12),
+    ("c3", lambda B: B.C3(128, 128, 2), lambda n, x: n.c3(x, "blk", 2, True), 128, 16),
+    ("c3_noshortcut", lambda B: B.C3(256, 128, 2, shortcut=False), lambda n, x: n.c3(x, "blk", 2, False), 256, 12),
+    ("sppf", lambda B: B.SPPF(128, 128), lambda n, x: n.sppf(x, "blk"), 128, 13),
 ]
 
 
@@ -89,7 +92,8 @@ def _model_and_batch(ver="yolov4", mode="csl", nc=2, S=96, bs=2):
     return R, m, img, tg, crit
 
 
-@pytest.mark.parametrize("ver,mode,nc", [("yolov4", "csl", 2), ("yolov4", "kfiou", 2), ("yolov7", "csl", 16)])
+@pytest.mark.parametrize("ver,mode,nc", [("yolov4", "csl", 2), ("yolov4", "kfiou", 2), ("yolov7", "csl", 16),
+                                         ("yolov5", "csl", 2)])
 def test_autograd_dropin_equals_native_and_reaches_all_params(ver, mode, nc):
     R, m, img, tg, crit = _model_and_batch(ver, mode, nc)
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}

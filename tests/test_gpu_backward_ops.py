@@ -88,6 +88,13 @@ def test_wgrad_stem():
     dwk = torch.zeros(32 * 64, device="cuda")
     ops.conv2d_wgrad(ops.stem_im2col(img.cuda()), ops.Act(dy.cuda()), 32, 1, 1, dwk)
     assert (ops.wgrad_to_oihw(dwk, 32, 3, 3, stem=True).cpu() - w.grad).abs().max() < 1e-2 * w.grad.abs().max()
+    # 6x6 / stride-2 stem of yolov5
+    w6 = torch.zeros(64, 3, 6, 6, requires_grad=True)
+    dy6 = torch.randn(2, 20, 18, 64, generator=gen).bfloat16()
+    F.conv2d(img.bfloat16().float(), w6, None, 2, 2).backward(dy6.float().permute(0, 3, 1, 2))
+    dwk6 = torch.zeros(64 * 128, device="cuda")
+    ops.conv2d_wgrad(ops.stem_im2col(img.cuda(), 6, 2), ops.Act(dy6.cuda()), 64, 1, 1, dwk6)
+    assert (ops.wgrad_to_oihw(dwk6, 64, 3, 6, stem=True).cpu() - w6.grad).abs().max() < 1e-2 * w6.grad.abs().max()
 
 
 @pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
@@ -180,4 +187,19 @@ def test_sgd_step():
         ref.grad = g.clone()
         opt.step()
         ops.sgd_step(p, g.cuda(), buf, 0.01, 0.937, 5e-4, True, it == 0)
+    assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+def test_adam_step():
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(7)
+    p0 = torch.randn(5003, generator=gen)
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    p, m, v = p0.clone().cuda(), torch.zeros(5003, device="cuda"), torch.zeros(5003, device="cuda")
+    for it in range(1, 4):
+        g = torch.randn(5003, generator=gen)
+        ref.grad = g.clone()
+        opt.step()
+        ops.adam_step(p, g.cuda(), m, v, 1e-3, it)
     assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)

@@ -99,6 +99,13 @@ def test_stem_im2col_conv():
     cols = ops.stem_im2col(img.cuda())
     out = ops.conv2d(cols, ops.pack_weights(w.cuda(), stem=True), 32, 1, 1)
     assert (out.torch().float().cpu() - ref).abs().max() < 2e-2 * ref.abs().max()
+    # yolov5 stem: 6x6 / stride 2 / pad 2 (model/backbone.py:42)
+    w6 = torch.randn(64, 3, 6, 6, generator=gen) * 0.1
+    ref6 = F.conv2d(img.bfloat16().float(), w6.bfloat16().float(), None, 2, 2).permute(0, 2, 3, 1)
+    cols6 = ops.stem_im2col(img.cuda(), 6, 2)
+    assert (cols6.H, cols6.W, cols6.C) == (24, 20, 128)
+    out6 = ops.conv2d(cols6, ops.pack_weights(w6.cuda(), stem=True), 64, 1, 1)
+    assert (out6.torch().float().cpu() - ref6).abs().max() < 2e-2 * ref6.abs().max()
 
 
 def test_bn_train_stats_apply():

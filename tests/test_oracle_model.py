@@ -7,7 +7,7 @@ import torch
 from oracle import model_cpu
 from tests.util import CFG, det_init, load, rel_err
 
-CASES = [("yolov4", "csl", 2), ("yolov4", "kfiou", 2), ("yolov7", "csl", 16)]
+CASES = [("yolov4", "csl", 2), ("yolov4", "kfiou", 2), ("yolov7", "csl", 16), ("yolov5", "csl", 2)]
 
 
 def _product_model(ver, mode, nc):
@@ -25,7 +25,7 @@ def test_state_dict_contract_and_init(ver, mode, nc):
         if "running" in k or "num_batches" in k:             # probed after the reference's train-mode forward
             continue
         assert abs(float(sd[k].double().sum()) - v) <= 1e-6 * max(1.0, abs(v)), k
-    assert len(sd) == {"yolov4": 648, "yolov7": 564}[ver]
+    assert len(sd) == {"yolov4": 648, "yolov7": 564, "yolov5": 612}[ver]
 
 
 @pytest.mark.parametrize("ver,mode,nc", CASES)
@@ -46,9 +46,7 @@ def test_oracle_model_matches_reference(ver, mode, nc):
     assert rel_err(infer[..., :4], g["eval_infer"][..., :4]) < 1e-3
 
 
-def test_unknown_mode_and_v5():
+def test_unknown_mode():
     import ryolo_b200 as R
     with pytest.raises(NotImplementedError):
         R.Yolo(2, CFG, "smoothl1", "yolov4")
-    with pytest.raises(NotImplementedError):
-        R.Yolo(2, CFG, "csl", "yolov5")
