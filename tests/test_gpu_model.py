@@ -120,7 +120,7 @@ def test_every_layer_teacher_forced(ver, mode, nc, train):
     for pre, x, y in trace:
         mod = mods[pre]
         if isinstance(mod, Conv) and mod.stem:
-            xin = ops.stem_im2col(x.cuda())
+            xin = ops.stem_im2col(x.cuda(), mod.k, mod.s)
         else:
             xin = ops.Act(x.permute(0, 2, 3, 1).contiguous().bfloat16().cuda())
         if isinstance(mod, Conv) and not mod.has_bn:                       # head: fp32 [B,na,gs,gs,ch]
