@@ -4,6 +4,7 @@ from ._lib import RyoloError, SO_PATH, lib
 from .lib.general import (nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
                           post_process_device)
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
+from .lib.metrics import ap_per_class, compute_ap, get_batch_statistics
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
 from .train_step import TrainStep
 
@@ -21,4 +22,4 @@ def compute_loss(model, hyp, mode="csl"):
 
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
-           "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "RyoloError", "SO_PATH", "lib"]
+           "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "get_batch_statistics", "ap_per_class", "compute_ap", "RyoloError", "SO_PATH", "lib"]

@@ -103,8 +103,65 @@ def make_model_goldens(Yolo):
         print("model", ver, mode, nc, len(keys), [tuple(t.shape) for t in tr])
 
 
+def make_metrics_golden():
+    """Runs the reference's get_batch_statistics / ap_per_class / compute_ap (test.py:14-149).  test.py cannot be
+    imported here (it pulls lib.load -> datasets), so the three function definitions are compiled from its
+    source text into a namespace that provides numpy/torch and the restated detectron2 op."""
+    import ast
+    src = open(os.path.join(REF, "test.py")).read()
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef)
+            and n.name in ("get_batch_statistics", "ap_per_class", "compute_ap")]
+    if not hasattr(np, "trapz"):
+        np.trapz = np.trapezoid
+    ns = {"np": np, "torch": torch, "pairwise_iou_rotated": orot.pairwise_iou_rotated}
+    exec(compile(ast.Module(body=keep, type_ignores=[]), "reference_test_py", "exec"), ns)
+    gen = torch.Generator().manual_seed(99)
+    B, nc = 4, 3
+    targets, outputs = [], []
+    for b in range(B):
+        nt = [6, 0, 9, 5][b]
+        t = torch.zeros(nt, 7)
+        t[:, 0] = b
+        t[:, 1] = torch.randint(0, nc, (nt,), generator=gen).float()
+        t[:, 2:4] = torch.rand(nt, 2, generator=gen) * 300 + 50
+        t[:, 4] = torch.rand(nt, generator=gen) * 40 + 10
+        t[:, 5] = t[:, 4] * (1 + 2 * torch.rand(nt, generator=gen))
+        t[:, 6] = (torch.rand(nt, generator=gen) - 0.5) * np.pi * 0.99
+        targets.append(t)
+        npred = [14, 5, 0, 11][b]
+        d = torch.zeros(npred, 7)
+        for i in range(npred):
+            if nt and i < 2 * nt:                 # jittered copies of targets (some duplicates -> claimed once)
+                src_t = t[i % nt]
+                d[i, :5] = src_t[2:7] + torch.randn(5, generator=gen) * torch.tensor([3, 3, 2, 2, 0.05])
+                d[i, 6] = src_t[1] if i % 5 else (src_t[1] + 1) % nc
+            else:
+                d[i, :2] = torch.rand(2, generator=gen) * 300 + 50
+                d[i, 2] = torch.rand(1, generator=gen) * 40 + 10
+                d[i, 3] = d[i, 2] * 2
+                d[i, 4] = (torch.rand(1, generator=gen) - 0.5) * 3
+                d[i, 6] = float(torch.randint(0, nc, (1,), generator=gen))
+            d[i, 5] = torch.rand(1, generator=gen)
+        d = d[d[:, 5].argsort(descending=True)] if npred else d
+        outputs.append(d)
+    targets = torch.cat(targets, 0)
+    iouv = torch.linspace(0.5, 0.95, 10)
+    stats = ns["get_batch_statistics"]([o.clone() for o in outputs], targets.clone(), iouv, 10)
+    tp, conf, pcls, tcls = [np.concatenate(x, 0) for x in zip(*stats)]
+    p, r, ap, f1, ucls = ns["ap_per_class"](tp, conf, pcls, tcls)
+    torch.save(dict(outputs=outputs, targets=targets, iouv=iouv,
+                    stats=[(torch.as_tensor(np.asarray(a)), torch.as_tensor(np.asarray(b)), torch.as_tensor(np.asarray(c)), d)
+                           for a, b, c, d in stats],
+                    p=p, r=r, ap=ap, f1=f1, ucls=ucls), os.path.join(HERE, "metrics.pt"))
+    print("metrics: images with stats", len(stats), "mAP50", float(ap[:, 0].mean()))
+
+
 def main():
     _install_stubs()
+    if "--only-metrics" in sys.argv:
+        make_metrics_golden()
+        return
     if "--only-model" in sys.argv:
         from model.yolo import Yolo
         make_model_goldens(Yolo)
@@ -211,6 +268,8 @@ def main():
 
     # ---- conv stack ---------------------------------------------------------------------
     make_model_goldens(Yolo)
+    make_metrics_golden()
+    make_metrics_golden()
 
     for f in sorted(os.listdir(HERE)):
         if f.endswith(".pt"):
