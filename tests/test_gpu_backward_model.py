@@ -158,3 +158,15 @@ def test_baseline_config1_train_step_416_bs2():
     after = m.state_dict()
     moved = sum(int(not torch.equal(after[k], v)) for k, v in before.items())
     assert moved == len(before), (moved, len(before))
+
+
+@pytest.mark.parametrize("mode", ["csl", "kfiou"])
+def test_train_step_with_no_targets(mode):
+    """Empty label set (lib/loss.py:311-313): only the objectness term is live; the step must still run and move
+    the weights that feed the objectness channel."""
+    R, m, img, tg, crit = _model_and_batch("yolov4", mode, 2, S=96, bs=2)
+    empty = torch.zeros((0, 187 if mode == "csl" else 7), device="cuda")
+    w0 = m.neck.conv38.conv[0].bias.detach().clone()
+    items = R.TrainStep(m, crit, lr=0.01)(img, empty)
+    assert torch.isfinite(items).all() and float(items[0]) == 0.0 and float(items[2]) > 0
+    assert not torch.equal(w0, m.neck.conv38.conv[0].bias.detach())
