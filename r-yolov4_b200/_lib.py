@@ -19,6 +19,8 @@ SIGNATURES = {
     "ryolo_last_error": (ctypes.c_char_p, []),
     "ryolo_set_error": (None, [ctypes.c_char_p]),
     "ryolo_check_device": (_i32, [_i32]),
+    "ryolo_tune": (_i32, [ctypes.c_char_p, _i32]),
+    "ryolo_knob": (_i32, [_i32]),
     "ryolo_pairwise_iou_rotated_workspace": (_sz, [_i64, _i64]),
     "ryolo_pairwise_iou_rotated": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "ryolo_nms_rotated_workspace": (_sz, [_i64]),
@@ -116,6 +118,12 @@ def count(n):
 def check(rc):
     if rc != 0:
         raise RyoloError(f"libryolo_b200 error {rc}: {lib().ryolo_last_error().decode()}")
+
+
+def tune(**kw):
+    """Set process-wide tuning knobs of the library (ryolo_tune), e.g. tune(halo=1, wg_split=0)."""
+    for k, v in kw.items():
+        check(lib().ryolo_tune(k.encode(), int(v)))
 
 
 def ptr(t):

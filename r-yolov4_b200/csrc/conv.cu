@@ -67,6 +67,28 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// smem -> global tile store / reduction through TMA (bulk async-group completion)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void group_bar(uint32_t id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+  return (uint32_t)v;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -149,8 +171,10 @@ struct ConvKernelParams {
   int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
+  int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads
   int halo;                        // 0 | 1 | 2: 3x3 stride-1 taps read shifted views of ONE (TH+2)x(TW+2) halo box (2: base_offset set)
   int a_slots; uint32_t a_slot_bytes;
+  int epi_tma;                     // bf16 epilogue stages 64-channel slabs in smem and stores them with TMA (2: reduce-add)
   int out_s, out_oh, out_ow, OutH, OutW;   // output lattice: pixel (ho*out_s + out_oh, wo*out_s + out_ow) of an OutH x OutW map
   int mode, act;
   void* out;
@@ -182,13 +206,14 @@ enum { EPI_RAW = 0, EPI_AFFINE = 1, EPI_HEAD = 2 };
 template <int EPI, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const ConvKernelParams p) {
+                const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
   const int BN = p.BN, STAGES = p.stages;
   const uint32_t kABytes = kBM * kBK * 2, kBBytes = (uint32_t)BN * kBK * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + (p.halo ? (uint32_t)p.a_slots * p.a_slot_bytes : (uint32_t)STAGES * kABytes);
+  const uint32_t sStage = sB + (uint32_t)STAGES * kBBytes;   // epi_tma: one 128-row x 64-channel bf16 slab per epilogue group
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4 + 8];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
@@ -204,6 +229,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA);
     prefetch_tmap(&tmB);
+    if (p.epi_tma) prefetch_tmap(&tmO);
     for (int s = 0; s < STAGES; s++) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -268,8 +294,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (kb >= KB) kb -= KB;
           const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
           mbar_wait(bar_empty + 8 * s, phase ^ 1u);
-          mbar_expect_tx(bar_full + 8 * s, a_bytes + kBBytes);
-          tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
+          mbar_expect_tx(bar_full + 8 * s, ((p.dbg & 8) ? 0u : a_bytes) + kBBytes);
+          if (!(p.dbg & 8))
+            tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
           tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * kBK, n0);
           if (++s == STAGES) { s = 0; phase ^= 1u; }
         }
@@ -317,10 +344,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(bar_full + 8 * s, phase);
           tc_fence_after();
           const uint32_t a0 = sA + s * kABytes, b0 = sB + s * kBBytes;
+          if (!(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < kBK / 16; k++) {
-            umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                      (kb | k) ? 1u : 0u);
+            for (int k = 0; k < kBK / 16; k++) {
+              umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
+                        (kb | k) ? 1u : 0u);
+            }
           }
           umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
           if (++s == STAGES) { s = 0; phase ^= 1u; }
@@ -345,7 +374,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    const bool do_stats = (EPI == EPI_RAW) && (p.bn.partial != nullptr);
+    const bool do_stats = (EPI == EPI_RAW) && (p.bn.partial != nullptr) && !(p.dbg & 2);
+    const bool tma = (EPI != EPI_HEAD) && p.epi_tma != 0;
+    const bool leader = ((warp - 2) & 3) == 0 && lane == 0;   // issues this epilogue group's TMA stores
+    const uint32_t stg = sStage + eg * 16384u;
     float st_s[8], st_q[8];                  // per-lane channel partial sums, one slot per 32-channel chunk
 #pragma unroll
     for (int i = 0; i < 8; i++) { st_s[i] = 0.f; st_q[i] = 0.f; }
@@ -358,7 +390,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ph = mt % p.tiles_h;
       const int img = mt / p.tiles_h;
       const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
-      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo);
+      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo) && !(p.dbg & 1);
       const long long pix = ((long long)img * p.OutH + ho * p.out_s + p.out_oh) * p.OutW + wo * p.out_s + p.out_ow;
       const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
       mbar_wait(bar_acc_full + 8 * buf, aphase);
@@ -410,6 +442,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               const __nv_bfloat16* res = (EPI == EPI_AFFINE && p.residual)
                                              ? p.residual + pix * p.res_cpitch + n0 + c0 : nullptr;
               const int ng = min(4, (nvalid - c0) >> 3);   // Cout is a multiple of 8
+              // epi_tma: the tile leaves through smem, one [128 rows x 64 channels] SWIZZLE_128B slab per TMA store
+              // (full 128-byte lines per request instead of 32 scattered 16-byte pieces per warp instruction)
+              const bool slab_first = tma && !(ci & 1);
+              const bool slab_last = tma && ((ci & 1) || c0 + 32 >= min(BN, nvalid));
+              if (slab_first) {
+                if (leader) bulk_wait_read0();           // the previous store has finished reading the slab
+                group_bar(2u + eg);
+              }
 #pragma unroll
               for (int g = 0; g < 4; g++) {
                 float f[8];
@@ -439,29 +479,58 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                 __nv_bfloat162* pb = reinterpret_cast<__nv_bfloat162*>(&pk);
 #pragma unroll
                 for (int j = 0; j < 4; j++) pb[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-                if (row_ok && g < ng) *reinterpret_cast<uint4*>(o + 8 * g) = pk;
-                if (do_stats) {              // statistics of the values as stored (bf16-rounded, packed pairs)
-                  const bool live = row_ok && g < ng;
-                  uint32_t* tw32 = reinterpret_cast<uint32_t*>(tw) + lane * 17 + 4 * g;
-                  tw32[0] = live ? pk.x : 0u;
-                  tw32[1] = live ? pk.y : 0u;
-                  tw32[2] = live ? pk.z : 0u;
-                  tw32[3] = live ? pk.w : 0u;
+                const bool live = row_ok && g < ng;
+                if (tma) {
+                  // dead rows / channels are stored as zeros: TMA clips them, the statistics read them
+                  const uint32_t piece = (uint32_t)(((ci & 1) * 4 + g) ^ (r & 7));
+                  sts128(stg + (uint32_t)r * 128u + piece * 16u, live ? pk : make_uint4(0u, 0u, 0u, 0u));
+                } else {
+                  if (live) *reinterpret_cast<uint4*>(o + 8 * g) = pk;
+                  if (do_stats) {              // statistics of the values as stored (bf16-rounded, packed pairs)
+                    uint32_t* tw32 = reinterpret_cast<uint32_t*>(tw) + lane * 17 + 4 * g;
+                    tw32[0] = live ? pk.x : 0u;
+                    tw32[1] = live ? pk.y : 0u;
+                    tw32[2] = live ? pk.z : 0u;
+                    tw32[3] = live ? pk.w : 0u;
+                  }
                 }
               }
               if (do_stats) {
                 __syncwarp();
                 float a = 0.f, b = 0.f;
+                if (tma) {
+                  // channel c0 + lane of this warp's own 32 rows, read back from the slab
+                  const uint32_t cpiece = (uint32_t)((ci & 1) * 4 + (lane >> 3));
+                  const uint32_t cbyte = (uint32_t)(lane & 7) * 2u;
 #pragma unroll 8
-                for (int rr = 0; rr < 32; rr++) {
-                  const uint32_t w2 = reinterpret_cast<const uint32_t*>(tw)[rr * 17 + (lane >> 1)];
-                  const float x = __uint_as_float((lane & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
-                  a += x;
-                  b += x * x;
+                  for (int rr = 0; rr < 32; rr++) {
+                    const uint32_t R = (uint32_t)(sub * 32 + rr);
+                    const float x = __uint_as_float(lds_u16(stg + R * 128u + ((cpiece ^ (R & 7u)) * 16u) + cbyte) << 16);
+                    a += x;
+                    b += x * x;
+                  }
+                } else {
+#pragma unroll 8
+                  for (int rr = 0; rr < 32; rr++) {
+                    const uint32_t w2 = reinterpret_cast<const uint32_t*>(tw)[rr * 17 + (lane >> 1)];
+                    const float x = __uint_as_float((lane & 1) ? (w2 & 0xffff0000u) : (w2 << 16));
+                    a += x;
+                    b += x * x;
+                  }
                 }
                 st_s[ci] += a;
                 st_q[ci] += b;
                 __syncwarp();
+              }
+              if (slab_last) {
+                fence_proxy_async();
+                group_bar(2u + eg);
+                if (leader && !(p.dbg & 1)) {
+                  const int cc = n0 + (ci >> 1) * 64;
+                  if (p.epi_tma == 2) tma_reduce_add_4d(&tmO, stg, cc, pw * p.TW, ph * p.TH, img);
+                  else tma_store_4d(&tmO, stg, cc, pw * p.TW, ph * p.TH, img);
+                  bulk_commit();
+                }
               }
             }
           }
@@ -526,6 +595,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
     }
   }
+  if (p.epi_tma && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) bulk_wait0();   // stores complete before exit
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
@@ -606,11 +676,7 @@ void pick_patch(int Ho, int Wo, int stride, int* TH, int* TW) {
 // patch row and the groups sit a constant (TW+2)*128 bytes apart).  Used when the 16x8 patch grid wastes little.
 // RYOLO_HALO=0 disables it, 2 sets the descriptor's base_offset field (bring-up switch).
 void maybe_enable_halo(ConvKernelParams* p) {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("RYOLO_HALO");
-    mode = e ? atoi(e) : 0;
-  }
+  const int mode = ryolo_knob(RYOLO_KNOB_HALO);
   p->halo = 0;
   if (!mode || p->ntaps != 9 || p->stride != 1 || p->ksize != 3) return;
   const double tiles = (double)((p->Ho + 15) / 16) * ((p->Wo + 7) / 8);
@@ -684,6 +750,33 @@ int sm_count() {
 constexpr size_t kSmemBudget = 204 * 1024;   // dynamic; + ~20 KB static (transpose tile, scale/shift, barriers)
 
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, cudaStream_t st) {
+  p.dbg = ryolo_knob(RYOLO_KNOB_DBG);
+  p.n_tiles = (p.Cout + p.BN - 1) / p.BN;
+  // TMA-store epilogue (knob epi_tma: 1 store, 2 also turns dgrad's read-add-write accumulation into a TMA reduce-add).
+  // A slab is 64 channels wide, so a tile whose width is not a multiple of 64 may only be the last one of its row.
+  CUtensorMap tmO = tmA;
+  p.epi_tma = 0;
+  const int knob = ryolo_knob(RYOLO_KNOB_EPI_TMA);
+  if (knob && p.mode == RYOLO_OUT_NHWC_BF16 && p.BN <= ryolo_knob(RYOLO_KNOB_EPI_MAXBN) &&
+      (p.BN % 64 == 0 || p.n_tiles == 1)) {
+    p.epi_tma = 1;
+    if (knob == 2 && p.residual == (const __nv_bfloat16*)p.out && p.res_cpitch == p.out_cpitch && !p.scale && !p.shift &&
+        p.act == RYOLO_ACT_LINEAR) {
+      p.epi_tma = 2;
+      p.residual = nullptr;
+    }
+    const long long pitch = p.out_cpitch;
+    __nv_bfloat16* base = (__nv_bfloat16*)p.out + ((long long)p.out_oh * p.OutW + p.out_ow) * pitch;
+    cuuint64_t dims[4] = {(cuuint64_t)p.Cout, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)p.N};
+    cuuint64_t strides[3] = {(cuuint64_t)p.out_s * pitch * 2, (cuuint64_t)p.out_s * p.OutW * pitch * 2,
+                             (cuuint64_t)p.OutH * p.OutW * pitch * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)p.TW, (cuuint32_t)p.TH, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = get_encode()(&tmO, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the output operand"); return RYOLO_ERR_CUDA; }
+  }
   size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2, fixed = 0;
   if (p.halo) {
     p.a_slots = 3;
@@ -691,14 +784,15 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
     fixed = (size_t)p.a_slots * p.a_slot_bytes;
     stage_bytes = (size_t)p.BN * kBK * 2;
   }
-  int stages = (int)((kSmemBudget - 1024 - fixed) / stage_bytes);
+  const size_t slab_bytes = p.epi_tma ? 2 * 16384 : 0;      // one slab per epilogue group, after the ring
+  int stages = (int)((kSmemBudget - 1024 - fixed - slab_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
-  const size_t smem = fixed + (size_t)stages * stage_bytes + 1024;
+  const size_t smem = fixed + (size_t)stages * stage_bytes + slab_bytes + 1024;
   uint32_t cols = 32;
   while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;
-  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const ConvKernelParams);
+  typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKernelParams);
   KernelFn fn = nullptr;
   const bool affine = p.scale || p.shift || p.act != RYOLO_ACT_LINEAR || p.residual;
   if (p.mode == RYOLO_OUT_HEAD_F32) fn = conv_fwd_kernel<EPI_HEAD, 0>;
@@ -718,14 +812,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
     }
     configured = true;
   }
-  p.n_tiles = (p.Cout + p.BN - 1) / p.BN;
   const long long tiles = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   RY_CHECK_ARG(tiles > 0 && tiles < (1ll << 31), "conv: tile count out of range");
   RY_CHECK_ARG(p.n_tiles <= sm_count(), "conv: too many output-channel tiles");
   int grid = sm_count();
   grid -= grid % p.n_tiles;                          // a CTA always sees the same n-tile
   if (tiles < grid) grid = (int)tiles;               // tiles is a multiple of n_tiles, so this keeps the property
-  fn<<<grid, kThreads, smem, st>>>(tmA, tmB, p);
+  fn<<<grid, kThreads, smem, st>>>(tmA, tmB, tmO, p);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

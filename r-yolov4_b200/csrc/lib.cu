@@ -1,5 +1,6 @@
 // Library-wide pieces of libryolo_b200.so: error string, version, device sanity.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 static thread_local char g_err[512] = "";
@@ -14,6 +15,39 @@ void ryolo_set_error(const char* msg) {
 const char* ryolo_last_error(void) { return g_err; }
 
 int ryolo_abi_version(void) { return 1; }
+
+// Tuning / timing-experiment switches (process-wide).  Defaults come from the environment variable RYOLO_<KEY>
+// (upper case) the first time a knob is read; ryolo_tune overrides them at run time.
+//   halo      conv: 3x3/s1 taps read shifted views of one halo box (0 off | 1 | 2)
+//   dbg       conv timing experiments, results are WRONG: 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads
+//   wg_split  wgrad: 1 = split-K shares proportional to the tap groups' tap counts, 0 = uniform
+//   wg_dbg    wgrad timing experiments, results are WRONG: 1 no MMAs, 2 no X loads
+static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 0, 64};
+static int g_knobs[RYOLO_KNOB_COUNT];
+static bool g_knob_set[RYOLO_KNOB_COUNT];
+
+int ryolo_knob(int id) {
+  if (id < 0 || id >= RYOLO_KNOB_COUNT) return 0;
+  if (!g_knob_set[id]) {
+    char env[64] = "RYOLO_";
+    size_t n = strlen(env);
+    for (const char* c = kKnobNames[id]; *c && n + 1 < sizeof(env); c++) env[n++] = (char)((*c >= 'a' && *c <= 'z') ? *c - 32 : *c);
+    env[n] = 0;
+    const char* e = getenv(env);
+    g_knobs[id] = e ? atoi(e) : kKnobDefaults[id];
+    g_knob_set[id] = true;
+  }
+  return g_knobs[id];
+}
+
+int ryolo_tune(const char* key, int value) {
+  for (int i = 0; i < RYOLO_KNOB_COUNT; i++) {
+    if (key && strcmp(key, kKnobNames[i]) == 0) { g_knobs[i] = value; g_knob_set[i] = true; return RYOLO_OK; }
+  }
+  ryolo_set_error("ryolo_tune: unknown key");
+  return RYOLO_ERR_INVALID;
+}
 
 // Returns RYOLO_OK only on a compute-capability 10.x device (the library ships sm_100a SASS only).
 int ryolo_check_device(int device) {

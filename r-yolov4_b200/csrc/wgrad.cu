@@ -11,13 +11,15 @@
 // of every tap reuses the same tensor map as the forward pass (element strides = conv stride, OOB = padding).
 //
 //   work item   (128-channel Cout tile) x (64*nb-channel Cin tile) x (group of taps that fits TMEM: tg*64*nb <= 512)
-//   split-K     the patches of an item are dealt round-robin to `ksplit` CTAs; every CTA keeps its partial dW in TMEM
+//   split-K     the patches of an item are dealt round-robin to its CTAs (the SMs are shared out between the items in
+//               proportion to their tap counts); every CTA keeps its partial dW in TMEM
 //               for its whole life and adds it to the fp32 OIHW gradient with atomics once at the end
 //   pipeline    warp 0 TMA producer (dY ring of 2, X ring of b_stages) | warp 1 MMA issuer | warps 2-5 epilogue
 #include "common.cuh"
 #include "ryolo_b200.h"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -111,10 +113,13 @@ struct WgradParams {
   int TH, TW, tiles_h, tiles_w;
   int ksize, stride, pad, ntaps;
   int nb, tg;                               // X boxes per item (N = 64*nb), taps per item
-  int n_co_tiles, n_ci_tiles, n_tap_groups, ksplit;
+  int n_co_tiles, n_ci_tiles, n_tap_groups;
+  int ks_total;                             // CTAs per (Cout tile, Cin tile) pair = sum of the tap groups' split counts
+  int ks_first[10];                         // tap group g owns CTAs [ks_first[g], ks_first[g+1]) of a pair's ks_total
   int b_stages;
   int slot_rows;                            // rows per smem box slot: 128, or 64 for wide Cin tiles (deeper ring)
   uint32_t tmem_cols;
+  int dbg;                                  // RYOLO_WG_DBG timing experiments: 1 = no MMAs, 2 = no X loads (results are wrong)
   float* dw;                                // fp32 K-major [Cout][k*k][Cin] (16-byte aligned)
 };
 
@@ -133,11 +138,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
                  bar_acc = smem_u32(&bars[2 * kMaxBStages + 4]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int split = blockIdx.x % p.ksplit;
-  int item = blockIdx.x / p.ksplit;
-  const int tgi = item % p.n_tap_groups; item /= p.n_tap_groups;
-  const int cit = item % p.n_ci_tiles;
-  const int cot = item / p.n_ci_tiles;
+  // split-K shares are proportional to the taps a group carries (a 9-tap layer with tg = 8 has groups of 8 and 1 taps)
+  const int pr = blockIdx.x % p.ks_total;
+  const int pair = blockIdx.x / p.ks_total;
+  int tgi = 0;
+  while (tgi + 1 < p.n_tap_groups && pr >= p.ks_first[tgi + 1]) tgi++;
+  const int split = pr - p.ks_first[tgi];
+  const int ksplit = p.ks_first[tgi + 1] - p.ks_first[tgi];
+  const int cit = pair % p.n_ci_tiles;
+  const int cot = pair / p.n_ci_tiles;
   const int tap0 = tgi * p.tg, ntap = min(p.tg, p.ntaps - tap0);
   const int co0 = cot * 128, ci0 = cit * 64 * p.nb;
   const int CIT = 64 * p.nb;
@@ -184,7 +193,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     if (lane == 0) {
       int s = 0;
       uint32_t bphase = 0, pit = 0;
-      for (int patch = split; patch < n_patches; patch += p.ksplit, pit++) {
+      for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
         const int pw = patch % p.tiles_w;
         const int ph = (patch / p.tiles_w) % p.tiles_h;
         const int img = patch / (p.tiles_w * p.tiles_h);
@@ -198,8 +207,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           const int tap = tap0 + ti;
           const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
           mbar_wait(bar_bempty + 8 * s, bphase ^ 1u);
-          mbar_expect_tx(bar_bfull + 8 * s, (uint32_t)p.nb * box_bytes);
-          for (int j = 0; j < p.nb; j++)
+          mbar_expect_tx(bar_bfull + 8 * s, (p.dbg & 2) ? 0u : (uint32_t)p.nb * box_bytes);
+          for (int j = 0; j < ((p.dbg & 2) ? 0 : p.nb); j++)
             tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + 64 * j,
                         w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
           if (++s == p.b_stages) { s = 0; bphase ^= 1u; }
@@ -212,7 +221,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       const int ksteps = (rows + 15) / 16;
       int s = 0;
       uint32_t bphase = 0, pit = 0;
-      for (int patch = split; patch < n_patches; patch += p.ksplit, pit++) {
+      for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
         const uint32_t ab = pit & 1u, aphase = (pit >> 1) & 1u;
         mbar_wait(bar_afull + 8 * ab, aphase);
         tc_fence_after();
@@ -221,7 +230,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           mbar_wait(bar_bfull + 8 * s, bphase);
           tc_fence_after();
           const uint32_t b0 = sB + (uint32_t)(s * p.nb) * kBoxBytes;
-          for (int kk = 0; kk < ksteps; kk++) {
+          for (int kk = 0; kk < ((p.dbg & 1) ? 0 : ksteps); kk++) {
             umma_bf16(tmem_base + (uint32_t)(ti * CIT), umma_desc_mn_sw128(a0 + kk * 2048, kBoxBytes),
                       umma_desc_mn_sw128(b0 + kk * 2048, kBoxBytes), idesc, (pit | (uint32_t)kk) ? 1u : 0u);
           }
@@ -360,10 +369,34 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   const int items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
   const long long n_patches = (long long)N * p.tiles_h * p.tiles_w;
   RY_CHECK_ARG(n_patches < (1ll << 31), "wgrad: too many patches");
-  int ksplit = sm_count() / items;
-  if (ksplit < 1) ksplit = 1;
-  if (ksplit > n_patches) ksplit = (int)n_patches;
-  p.ksplit = ksplit;
+  // CTAs per (Cout tile, Cin tile) pair, dealt to the tap groups in proportion to their tap counts (greedy: the
+  // group with the most taps per CTA gets the next one).  RYOLO_WG_SPLIT=0 restores the uniform split (A/B switch).
+  const int prop = ryolo_knob(RYOLO_KNOB_WG_SPLIT);
+  const int pairs = p.n_co_tiles * p.n_ci_tiles;
+  int ks[9], gt[9];
+  for (int g = 0; g < p.n_tap_groups; g++) {
+    ks[g] = 1;
+    gt[g] = p.ntaps - g * p.tg < p.tg ? p.ntaps - g * p.tg : p.tg;
+  }
+  if (prop) {
+    int budget_ctas = sm_count() / pairs;
+    for (int used = p.n_tap_groups; used < budget_ctas; used++) {
+      int best = 0;
+      for (int g = 1; g < p.n_tap_groups; g++)
+        if ((long long)gt[g] * ks[best] > (long long)gt[best] * ks[g]) best = g;
+      ks[best]++;
+    }
+  } else {
+    int u = sm_count() / items;
+    if (u < 1) u = 1;
+    for (int g = 0; g < p.n_tap_groups; g++) ks[g] = u;
+  }
+  p.ks_first[0] = 0;
+  for (int g = 0; g < p.n_tap_groups; g++) {
+    if (ks[g] > n_patches) ks[g] = (int)n_patches;
+    p.ks_first[g + 1] = p.ks_first[g] + ks[g];
+  }
+  p.ks_total = p.ks_first[p.n_tap_groups];
   const size_t budget = 200 * 1024;
   const size_t kBoxBytes = (size_t)p.slot_rows * 128;
   int bst = (int)((budget - 1024 - 4 * kBoxBytes) / ((size_t)p.nb * kBoxBytes));
@@ -372,6 +405,7 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   p.b_stages = bst;
   const size_t smem = 1024 + 4 * kBoxBytes + (size_t)bst * p.nb * kBoxBytes;
   p.dw = dwk;
+  p.dbg = ryolo_knob(RYOLO_KNOB_WG_DBG);
   CUtensorMap tmG, tmX;
   if (encode_nhwc(enc, &tmG, dy, N, p.Ho, p.Wo, Cdy, dy_cpitch, p.TH, p.TW, 1) ||
       encode_nhwc(enc, &tmX, x, N, H, W, Cin, x_cpitch, p.TH, p.TW, stride)) {
@@ -384,7 +418,7 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
     if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     configured = true;
   }
-  conv_wgrad_kernel<<<items * ksplit, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
+  conv_wgrad_kernel<<<pairs * p.ks_total, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

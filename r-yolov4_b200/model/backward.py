@@ -104,6 +104,7 @@ def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
 
 
 _SIDE = {}
+WGRAD_SIDE_STREAM = True      # False: weight-gradient GEMMs on the main stream (clean per-launch timings in tools/)
 
 
 def _side_stream(dev):
@@ -135,6 +136,9 @@ class _WgradSink:
         layer has run), so it overlaps the dgrad of this layer and the HBM-bound BN backward of the next one instead
         of serialising with them (its CTAs leave most of an SM's bandwidth idle)."""
         buf = self.buffer(weight, stem)
+        if not WGRAD_SIDE_STREAM:
+            ops.conv2d_wgrad(x, dy, Cout, k, stride, buf)
+            return
         main = torch.cuda.current_stream()
         ev = torch.cuda.Event()
         ev.record(main)

@@ -15,3 +15,15 @@ def pytest_configure(config):
 @pytest.fixture(scope="session")
 def golden_dir():
     return os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(params=["direct", "tma", "tma_red"])
+def epi(request):
+    """Runs a conv test under each bf16 epilogue of the conv kernel: per-thread 16-byte stores, TMA slab stores,
+    TMA slab stores + TMA reduce-add for dgrad's accumulation (library knobs epi_tma / epi_maxbn)."""
+    from ryolo_b200 import _lib as L
+    mode = {"direct": 0, "tma": 1, "tma_red": 2}[request.param]
+    old = (L.lib().ryolo_knob(4), L.lib().ryolo_knob(5))
+    L.tune(epi_tma=mode, epi_maxbn=256)
+    yield request.param
+    L.tune(epi_tma=old[0], epi_maxbn=old[1])

@@ -35,7 +35,7 @@ def _case(shape, seed=0):
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_dgrad(shape):
+def test_dgrad(shape, epi):
     from ryolo_b200 import ops
     N, H, W, Cin, Cout, k, s = shape
     x, w, dy, dx_ref, _ = _case(shape)
@@ -47,6 +47,12 @@ def test_dgrad(shape):
     assert (got - dx_ref).abs().max() < tol
     ops.conv2d_dgrad(ops.Act(dy.cuda()), wt, Cin, k, s, dx, accumulate=True)      # dx += same thing
     assert (dx.torch().float().cpu() - 2 * dx_ref).abs().max() < 2 * tol
+    # gradient into a channel slice of a wider (concat) buffer: the neighbours stay untouched
+    big = torch.full((N, H, W, Cin + 48), 5.0).bfloat16().cuda()
+    ops.conv2d_dgrad(ops.Act(dy.cuda()), wt, Cin, k, s, ops.Act(big, Cin, 16), accumulate=False)
+    b = big.float().cpu()
+    assert (b[..., 16:16 + Cin] - dx_ref).abs().max() < tol
+    assert (b[..., :16] == 5).all() and (b[..., 16 + Cin:] == 5).all()
 
 
 @pytest.mark.parametrize("shape", SHAPES)

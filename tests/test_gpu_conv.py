@@ -36,7 +36,7 @@ SHAPES = [  # N, H, W, Cin, Cout, k, stride
 
 
 @pytest.mark.parametrize("shape", SHAPES)
-def test_conv_raw(shape):
+def test_conv_raw(shape, epi):
     from ryolo_b200 import ops
     N, H, W, Cin, Cout, k, s = shape
     gen = torch.Generator().manual_seed(sum(shape))
@@ -55,7 +55,7 @@ def test_conv_raw(shape):
 
 
 @pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
-def test_conv_epilogue_scale_shift_act_residual_concat_slice(act):
+def test_conv_epilogue_scale_shift_act_residual_concat_slice(act, epi):
     from ryolo_b200 import ops
     gen = torch.Generator().manual_seed(5)
     N, H, W, Cin, Cout = 2, 20, 20, 64, 64
@@ -88,6 +88,40 @@ def test_conv_head_layout(na, ch, gs, Cin):
     out = ops.conv2d(ops.Act(x.cuda()), ops.pack_weights(w.cuda()), Cout, 1, 1, shift=bias.cuda(), head=(na, ch))
     assert out.shape == ref.shape and out.dtype == torch.float32
     assert (out.cpu() - ref).abs().max() < 5e-3 * ref.abs().max()
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 40, 32, 32, 3, 1), (3, 25, 25, 128, 96, 1, 1), (2, 26, 30, 64, 160, 3, 2),
+                                   (1, 50, 50, 64, 320, 1, 1)])
+def test_conv_fused_bn_statistics(shape, epi):
+    """Train-mode BatchNorm statistics + finalize fused into the conv epilogue (EPI_RAW): scale/shift/mean/invstd and
+    the running statistics equal nn.BatchNorm2d's on the stored (bf16) conv output."""
+    from ryolo_b200 import ops
+    N, H, W, Cin, Cout, k, s = shape
+    gen = torch.Generator().manual_seed(11 + sum(shape))
+    x, w = _mk(gen, N, H, W, Cin, Cout, k)
+    bn = torch.nn.BatchNorm2d(Cout)
+    bn.weight.data = torch.rand(Cout, generator=gen) + 0.5
+    bn.bias.data = torch.randn(Cout, generator=gen)
+    bn = bn.cuda().train()
+    part = torch.empty(ops.BN_PARTIAL_ROWS * 2 * Cout, device="cuda")
+    ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
+    scale, shift, mean, invstd = (torch.empty(Cout, device="cuda") for _ in range(4))
+    raw = ops.conv2d(ops.Act(x.cuda()), ops.pack_weights(w.cuda()), Cout, k, s,
+                     bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
+    torch.cuda.synchronize()
+    y = raw.torch().float().cpu()                                  # [N,Ho,Wo,Cout] as stored
+    ref = _ref_conv(x, w, s)
+    assert (y - ref).abs().max() < 2e-2 * ref.abs().max()
+    m = y.reshape(-1, Cout).mean(0)
+    v = y.reshape(-1, Cout).var(0, unbiased=False)
+    assert torch.allclose(mean.cpu(), m, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(invstd.cpu(), (v + bn.eps).rsqrt(), rtol=1e-4, atol=1e-5)
+    sc = bn.weight.data.cpu() * (v + bn.eps).rsqrt()
+    assert torch.allclose(scale.cpu(), sc, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(shift.cpu(), bn.bias.data.cpu() - m * sc, rtol=1e-3, atol=1e-4)
+    cnt = y.numel() // Cout
+    assert torch.allclose(bn.running_mean.cpu(), 0.1 * m, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(bn.running_var.cpu(), 0.9 + 0.1 * v * cnt / (cnt - 1), rtol=1e-4, atol=1e-5)
 
 
 def test_stem_im2col_conv():

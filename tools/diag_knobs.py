@@ -1,0 +1,84 @@
+"""A/B timing of the library's tuning knobs inside one process (ryolo_tune): per-launch CUDA-event times of the
+conv / dgrad / wgrad kernels of a yolov4 800x800 train step under each knob setting (wgrad on the main stream so the
+per-launch times are clean).  dbg / wg_dbg settings produce wrong results on purpose: they remove one pipeline stage to
+show what the kernel is waiting for.  Writes gpurun_out/diag_knobs.json + a text table."""
+import json, os, sys
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+sys.path.insert(0, ROOT)
+import torch
+import ryolo_b200 as R
+from ryolo_b200 import ops, _lib as L
+from ryolo_b200.model import backward as BW
+from bench import CFG, HYP, S, make_targets, weights_init_normal
+
+bs = int(sys.argv[1]) if len(sys.argv) > 1 else 32
+which = sys.argv[2].split(",") if len(sys.argv) > 2 else None
+BW.WGRAD_SIDE_STREAM = False
+torch.manual_seed(42)
+m = R.Yolo(2, CFG, "csl", "yolov4")
+m.apply(weights_init_normal)
+m = m.cuda().train()
+crit = R.ComputeCSLLoss(m, HYP)
+crit.sync_items = False
+step = R.TrainStep(m, crit)
+img = torch.rand(bs, 3, S, S, device="cuda")
+tg = make_targets(0, bs, 2).cuda()
+flat0 = step.flat.clone()
+BASE = dict(halo=0, dbg=0, wg_split=1, wg_dbg=0, epi_tma=0, epi_maxbn=64)
+VARIANTS = [
+    ("base", {}),
+    ("wg_uniform", dict(wg_split=0)),
+    ("wg_nomma", dict(wg_dbg=1)),
+    ("wg_noload", dict(wg_dbg=2)),
+    ("nostore", dict(dbg=1)),
+    ("nostats", dict(dbg=2)),
+    ("nostore_nostats", dict(dbg=3)),
+    ("nomma", dict(dbg=4)),
+    ("noaload", dict(dbg=8)),
+    ("tma64", dict(epi_tma=1, epi_maxbn=64)),
+    ("tma128", dict(epi_tma=1, epi_maxbn=128)),
+    ("tma256", dict(epi_tma=1, epi_maxbn=256)),
+    ("tmared256", dict(epi_tma=2, epi_maxbn=256)),
+    ("halo", dict(halo=1)),
+]
+res = {}
+for name, kn in VARIANTS:
+    if which and name not in which:
+        continue
+    L.tune(**{**BASE, **kn})
+    step.flat.copy_(flat0)                      # dbg variants may write garbage: restart from the same weights
+    step.buf.zero_(); step.first = True
+    m.repack_weights()
+    try:
+        step(img, tg)
+        torch.cuda.synchronize()
+        ops.PROFILE = []
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(img, tg)
+        b.record()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+    except Exception as e:                      # keep going: one broken variant must not lose the others
+        ops.PROFILE = None
+        res[name] = {"error": repr(e)}
+        print(name, "ERROR", e, flush=True)
+        continue
+    rows = [(t[0], t[1], t[2], t[3], s.elapsed_time(e)) for t, s, e in prof]
+    tot = {}
+    for k, M, N, K, ms in rows:
+        tot[k] = tot.get(k, 0.0) + ms
+    res[name] = {"step_ms": a.elapsed_time(b), "totals": tot, "rows": rows}
+    print(f"{name:16s} step {a.elapsed_time(b):7.2f} ms  " + "  ".join(f"{k} {v:6.2f}" for k, v in tot.items()), flush=True)
+L.tune(**BASE)
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"diag_knobs_bs{bs}.json"), "w"))
+# per-layer table for the variants that ran
+names = [n for n in res if "rows" in res[n]]
+if names:
+    n0 = names[0]
+    with open(os.path.join(ROOT, "gpurun_out", f"diag_knobs_bs{bs}.txt"), "w") as f:
+        f.write("kind        M      N     K  " + " ".join(f"{n[:9]:>9s}" for n in names) + "\n")
+        for i, r in enumerate(res[n0]["rows"]):
+            f.write(f"{r[0]:6s} {r[1]:9d} {r[2]:5d} {r[3]:5d} " +
+                    " ".join(f"{res[n]['rows'][i][4]:9.3f}" if i < len(res[n]['rows']) else "        -" for n in names) + "\n")
