@@ -22,9 +22,15 @@ const char* ryolo_last_error(void);
 void ryolo_set_error(const char* msg);
 int ryolo_check_device(int device); /* 0 only on a compute-capability 10.x device */
 /* Process-wide tuning / timing-experiment switch (no reference counterpart).  Keys: "halo", "dbg", "wg_split",
- * "wg_dbg", "epi_tma", "epi_maxbn" (see csrc/lib.cu); defaults come from the environment variable RYOLO_<KEY>. */
+ * "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd" (see csrc/lib.cu); defaults come from the environment
+ * variable RYOLO_<KEY>. */
 int ryolo_tune(const char* key, int value);
 int ryolo_knob(int id);
+
+/* ---- label encoding ---------------------------------------------------------------------------
+ * datasets/base_dataset.py:137-154: xyxyxyxy2xywha (lib/general.py:70-104) + gaussian_label (base_dataset.py:13-31).
+ * polys fp32 [T,10] = (image index, class, x1,y1,..,x4,y4 clockwise); out fp32 [T,187] (csl) or [T,7].          */
+int ryolo_encode_labels(const float* polys, long long T, int csl, float* out, void* stream);
 
 /* ---- rotated IoU / NMS ------------------------------------------------------------------------
  * detectron2.layers.rotated_boxes.pairwise_iou_rotated  (reference call site test.py:7,135)
@@ -100,10 +106,12 @@ enum { RYOLO_OUT_NHWC_BF16 = 0, RYOLO_OUT_HEAD_F32 = 1 };
 /* Fused train-mode BatchNorm2d statistics (model/utils.py:16-17): the raw-output conv epilogue accumulates the
  * per-channel sum / sum of squares of what it stores, and the last CTA to finish turns them into
  * scale = gamma*rsqrt(var+eps), shift = beta-mean*scale, updates the running statistics (momentum, unbiased
- * variance) and num_batches_tracked.  The reduction order is fixed (bit-reproducible run to run, like the
- * reference's cudnn.deterministic).  partial = fp32 scratch of RYOLO_BN_PARTIAL_ROWS*2*Cout floats (no init
- * needed); counter (u32) must be zero on entry; sum / sumsq (fp32[Cout]) are optional outputs.               */
-#define RYOLO_BN_PARTIAL_ROWS 160   /* >= number of SMs (one partial row per persistent CTA) */
+ * variance) and num_batches_tracked.  The result is bit-reproducible run to run (like the reference's
+ * cudnn.deterministic): within a CTA the order is fixed, across CTAs the sums are 64-bit fixed point.
+ * partial = scratch of >= 4*Cout floats (2*Cout 64-bit accumulators), 8-byte aligned, ZERO on entry and left zero on
+ * exit (so one zero-initialised scratch serves every layer of a stream); counter (u32) must be zero on entry;
+ * sum / sumsq (fp32[Cout]) are optional outputs.                                                              */
+#define RYOLO_BN_PARTIAL_ROWS 160   /* legacy sizing constant: callers allocate RYOLO_BN_PARTIAL_ROWS*2*Cout floats */
 typedef struct ryolo_bn_fuse {
   float* partial; float* sum; float* sumsq; unsigned int* counter;
   const float* gamma; const float* beta;
@@ -168,7 +176,7 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, int k, int stride, 
  * [Cout][Kpad = layout] in the im2col channel order                                                                     */
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream);
 /* all conv weights of a model in one launch.  table (DEVICE array, sorted by `first`): tensor i holds flat
- * elements [first, first + Cout*Cin*k*k) of the launch; dst = layout 0 (or the stem's [Cout][64], padding
+ * elements [first, first + Cout*Cin*k*k) of the launch; dst = layout 0 (or the stem's [Cout][Kpad], padding
  * pre-zeroed by the caller), dst_t = layout 2 or NULL.                                                         */
 typedef struct ryolo_pack_entry {
   const float* src; void* dst; void* dst_t;
@@ -179,14 +187,15 @@ int ryolo_pack_weights_multi(const ryolo_pack_entry* table_dev, int n, long long
 int ryolo_unpack_wgrad_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream);
 
 /* ---- conv stack backward (autograd's backward of the reference, train.py:198) ------------------------------
- * dwk (fp32, K-major [Cout][kh*kw][Cin] like the packed forward weights; stem: x = the 64-channel im2col tensor,
- * dwk = [Cout][64]) += conv_backward_weight(x, dy).  x bf16 NHWC view [N,H,W,Cin]; dy bf16 NHWC view
+ * dwk (fp32, K-major [Cout][kh*kw][Cin] like the packed forward weights; stem: x = the Kpad-channel im2col tensor,
+ * dwk = [Cout][Kpad]) += conv_backward_weight(x, dy).  x bf16 NHWC view [N,H,W,Cin]; dy bf16 NHWC view
  * [N,Ho,Wo,Cdy], Cdy >= Cout.  tcgen05 GEMM over pixels with MN-major operands, split-K across CTAs, vector fp32
  * atomics into dwk (csrc/wgrad.cu).  ryolo_unpack_wgrad_multi then adds every dwk into its OIHW gradient
  * (table as for ryolo_pack_weights_multi with src = dwk (fp32), dst = OIHW fp32 gradient, dst_t unused).       */
 int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
                        long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, float* dwk, void* stream);
-/* d raw = backward of act(BatchNorm2d_train(raw)) given d out; also d gamma, d beta (fp32[C], nullable).
+/* d raw = backward of act(BatchNorm2d_train(raw)) given d out; d gamma, d beta (fp32[C], nullable) are ACCUMULATED
+ * into (autograd .grad semantics: gradient accumulation over micro-batches, reference train.py:198-202).
  * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.  dout is overwritten
  * with dout*act'(.) (dead afterwards).                                                                        */
 int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,

@@ -19,6 +19,7 @@ SIGNATURES = {
     "ryolo_last_error": (ctypes.c_char_p, []),
     "ryolo_set_error": (None, [ctypes.c_char_p]),
     "ryolo_check_device": (_i32, [_i32]),
+    "ryolo_encode_labels": (_i32, [_vp, ctypes.c_longlong, _i32, _vp, _vp]),
     "ryolo_tune": (_i32, [ctypes.c_char_p, _i32]),
     "ryolo_knob": (_i32, [_i32]),
     "ryolo_pairwise_iou_rotated_workspace": (_sz, [_i64, _i64]),

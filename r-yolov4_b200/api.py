@@ -1,11 +1,12 @@
 """Public call surface: the three Python callables the reference's train.py /
 test.py / detect.py use, under their real names plus the aliases BASELINE.json's north_star uses."""
 from ._lib import RyoloError, SO_PATH, lib
-from .lib.general import (nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
+from .lib.general import (encode_labels, xyxyxyxy2xywha, nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
                           post_process_device)
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
 from .lib.metrics import ap_per_class, compute_ap, get_batch_statistics
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
+from .schedule import Schedule, one_cycle
 from .train_step import TrainStep
 
 try:  # the conv stack is built on top of the kernels above
@@ -22,4 +23,4 @@ def compute_loss(model, hyp, mode="csl"):
 
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
-           "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "get_batch_statistics", "ap_per_class", "compute_ap", "RyoloError", "SO_PATH", "lib"]
+           "encode_labels", "xyxyxyxy2xywha", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle", "get_batch_statistics", "ap_per_class", "compute_ap", "RyoloError", "SO_PATH", "lib"]

@@ -23,6 +23,7 @@ SOURCES = {
     "nms.cu": ["--fmad=false"],
     "decode.cu": ["--fmad=false"],
     "loss.cu": ["--fmad=false"],
+    "labels.cu": ["--fmad=false"],
 }
 for _opt in ("conv.cu", "elementwise.cu", "wgrad.cu", "backward.cu"):
     if os.path.exists(os.path.join(CSRC, _opt)):

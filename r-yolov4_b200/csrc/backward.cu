@@ -115,8 +115,90 @@ bn_act_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, long long dp, const _
   }
 }
 
+// Same pass, leaner: mean / invstd are not live in the loop (it accumulates sum dY and sum dY*raw; each thread turns its
+// own short partial into sum dY*xhat = invstd * (sum dY*raw - mean * sum dY) afterwards, so no long-range cancellation),
+// and mish' uses  t + 4 y e (e+1) r^2  with r = 1/(e^2+2e+2), t = 1-2r  (one exp, one reciprocal, ~12 flops).  Three
+// blocks per SM instead of two: the pass is latency-bound (ncu: 24 % warps active, stalls = wait + long scoreboard).
+template <int ACT>
+__device__ __forceinline__ float act_grad2(float y) {
+  if (ACT == RYOLO_ACT_MISH) {
+    const float e = __expf(fminf(y, 20.f));
+    const float r = __fdividef(1.f, fmaf(e, e + 2.f, 2.f));
+    const float t = fmaf(-2.f, r, 1.f);
+    return fmaf(4.f * y, e * (e + 1.f) * (r * r), t);
+  }
+  return act_grad<ACT>(y);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_reduce2_kernel(__nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
+                          float* __restrict__ sums) {
+  extern __shared__ float red[];   // [rows][C] x 2
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int c = 8 * g;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < rows) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; }
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long pix0 = (long long)blockIdx.x * rows + r; pix0 < P; pix0 += 2 * stride) {
+      uint4 vd[2], vr[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const long long pix = pix0 + u * stride;
+        if (pix < P) {
+          vd[u] = *reinterpret_cast<const uint4*>(dout + pix * dp + c);
+          vr[u] = *reinterpret_cast<const uint4*>(raw + pix * rp + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const long long pix = pix0 + u * stride;
+        if (pix < P) {
+          float d[8], x[8];
+          unpack8(vd[u], d);
+          unpack8(vr[u], x);
+          if (ACT != RYOLO_ACT_LINEAR) {
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[j] *= act_grad2<ACT>(fmaf(x[j], sc[j], sh[j]));
+            const uint4 pk = pack8(d);
+            *reinterpret_cast<uint4*>(dout + pix * dp + c) = pk;
+            unpack8(pk, d);                       // statistics of dY as stored
+          }
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            s1[j] += d[j];
+            s2[j] = fmaf(d[j], x[j], s2[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) s2[j] = invstd[c + j] * (s2[j] - mean[c + j] * s1[j]);
+  }
+  float* r1 = red;
+  float* r2 = red + (size_t)rows * C;
+  if (r < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { r1[r * C + c + j] = s1[j]; r2[r * C + c + j] = s2[j]; }
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; rr++) { a += r1[rr * C + cc]; b += r2[rr * C + cc]; }
+    atomicAdd(sums + cc, a);
+    atomicAdd(sums + C + cc, b);
+  }
+}
+
 // Pass 2: d raw = scale * (dY - s1/P - xhat * s2/P) with dY read back from pass 1;  block 0 also emits
-// d gamma = s2, d beta = s1.
+// d gamma += s2, d beta += s1.
 __global__ void __launch_bounds__(256)
 bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
                         long long rp, const float* __restrict__ scale, const float* __restrict__ mean,
@@ -128,8 +210,8 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, co
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
   if (blockIdx.x == 0) {
     for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
-      if (dbeta) dbeta[cc] = sums[cc];
-      if (dgamma) dgamma[cc] = sums[C + cc];
+      if (dbeta) dbeta[cc] += sums[cc];          // accumulate like autograd's .grad (train.py:198-202)
+      if (dgamma) dgamma[cc] += sums[C + cc];
     }
   }
   if (r >= rows) return;
@@ -377,7 +459,7 @@ extern "C" {
 // Backward of act(BatchNorm2d_train(raw)) (+ gradient already flowing to a residual is the caller's business).
 // NOTE: dout is overwritten with dY = dout * act'(.) (it is dead afterwards).
 //   dout, raw: bf16 NHWC views over P pixels x C channels; scale/shift/mean/invstd: fp32[C] saved by the forward pass
-//   sums: fp32[2C] scratch, zeroed;  draw: bf16 view;  dgamma / dbeta: fp32[C] outputs (nullable)
+//   sums: fp32[2C] scratch, zeroed;  draw: bf16 view;  dgamma / dbeta: fp32[C], accumulated into (nullable)
 int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
                      float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream) {
@@ -394,8 +476,13 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
   __nv_bfloat16* d = (__nv_bfloat16*)dout;
   const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
   __nv_bfloat16* o = (__nv_bfloat16*)draw;
-#define RY_BWD(ACT) \
-  bn_act_bwd_reduce_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C, sums);
+  const bool lean = ryolo_knob(RYOLO_KNOB_BN_BWD) != 0 && threads == 256;
+#define RY_BWD(ACT)                                                                                                  \
+  if (lean)                                                                                                          \
+    bn_act_bwd_reduce2_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C,    \
+                                                                 sums);                                              \
+  else                                                                                                               \
+    bn_act_bwd_reduce_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C, sums);
   switch (act) {
     case RYOLO_ACT_LEAKY: RY_BWD(RYOLO_ACT_LEAKY) break;
     case RYOLO_ACT_MISH: RY_BWD(RYOLO_ACT_MISH) break;

@@ -28,6 +28,9 @@ constexpr int kBM = 128;        // UMMA M (rows of the patch tile, TH*TW <= 128)
 constexpr int kBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kThreads = 320;   // 10 warps: TMA, MMA, 2 x 4 epilogue
 constexpr int kMaxStages = 12;
+// fused BatchNorm statistics: fixed-point scales of the cross-CTA accumulators (|sum| < 2^39, sum of squares < 2^43)
+constexpr float kSumScale = 16777216.f;   // 2^24
+constexpr float kSqScale = 1048576.f;     // 2^20
 
 // ------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -539,8 +542,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     if (do_stats) {
       // Deterministic reduction (the reference runs with cudnn.deterministic, train.py:24): the 8 epilogue warps
-      // combine through smem in a fixed order, every CTA stores ONE partial row, and the last CTA to arrive sums the
-      // rows of each channel in CTA order before turning them into scale/shift + running statistics.
+      // combine through smem in a fixed order; across CTAs the sums are fixed-point (see below); the last CTA to
+      // arrive turns the totals into scale/shift + running statistics.
       const int n0c = (blockIdx.x % p.n_tiles) * BN;
       float* comb = s_tr;                                  // reused as [8 warps][2][256]
       asm volatile("bar.sync 1, 256;" ::: "memory");       // every warp is done with its transpose tile
@@ -552,14 +555,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      float* prow = p.bn.partial + (size_t)blockIdx.x * 2 * p.Cout;
+      // Every CTA adds its per-channel partials to ONE pair of 64-bit fixed-point accumulators per channel: integer
+      // addition is associative, so the totals do not depend on the order the CTAs arrive in.
+      unsigned long long* acc = reinterpret_cast<unsigned long long*>(p.bn.partial);   // [2][Cout], zero between launches
       for (int i = et; i < 2 * BN; i += 256) {
         const int q = i / BN, cl = i - q * BN, c = n0c + cl;
         if (c < p.Cout) {
           float a = 0.f;
 #pragma unroll
           for (int w = 0; w < 8; w++) a += comb[(w * 2 + q) * 256 + cl];
-          prow[(size_t)q * p.Cout + c] = a;
+          atomicAdd(acc + (size_t)q * p.Cout + c, (unsigned long long)__float2ll_rn(a * (q ? kSqScale : kSumScale)));
         }
       }
       __threadfence();
@@ -570,15 +575,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         __threadfence();
         if (et == 0 && p.bn.num_batches) *p.bn.num_batches += 1;
         for (int c = et; c < p.Cout; c += 256) {
-          float fs = 0.f, fq = 0.f;
-          for (int b = c / BN; b < (int)gridDim.x; b += p.n_tiles) {   // CTAs whose n-tile holds channel c
-            fs += __ldcg(p.bn.partial + ((size_t)b * 2 + 0) * p.Cout + c);
-            fq += __ldcg(p.bn.partial + ((size_t)b * 2 + 1) * p.Cout + c);
-          }
+          const long long is = (long long)__ldcg(acc + c), iq = (long long)__ldcg(acc + p.Cout + c);
+          acc[c] = 0ull;                                   // leave the scratch zeroed for the next launch
+          acc[p.Cout + c] = 0ull;
+          const double ds = (double)is * (1.0 / kSumScale), dq = (double)iq * (1.0 / kSqScale);
+          const float fs = (float)ds, fq = (float)dq;
           if (p.bn.sum) p.bn.sum[c] = fs;
           if (p.bn.sumsq) p.bn.sumsq[c] = fq;
-          const double mean = (double)fs / p.bn_count;
-          double var = (double)fq / p.bn_count - mean * mean;
+          const double mean = ds / p.bn_count;
+          double var = dq / p.bn_count - mean * mean;
           if (var < 0.0) var = 0.0;
           const float invstd = (float)(1.0 / sqrt(var + (double)p.bn.eps));
           const float sc = p.bn.gamma[c] * invstd;
@@ -757,11 +762,14 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   CUtensorMap tmO = tmA;
   p.epi_tma = 0;
   const int knob = ryolo_knob(RYOLO_KNOB_EPI_TMA);
-  if (knob && p.mode == RYOLO_OUT_NHWC_BF16 && p.BN <= ryolo_knob(RYOLO_KNOB_EPI_MAXBN) &&
-      (p.BN % 64 == 0 || p.n_tiles == 1)) {
+  // Measured per layer (profiles/r01_diag_knobs_bs32.txt): the slab costs 32 KB of the operand ring, which only the
+  // deep-K BN=256 tiles miss; everything else gains, and dgrad's accumulation always does (no read-add-write).
+  const bool reducible = knob == 2 && p.residual == (const __nv_bfloat16*)p.out && p.res_cpitch == p.out_cpitch &&
+                         !p.scale && !p.shift && p.act == RYOLO_ACT_LINEAR;
+  const bool fits = p.BN <= ryolo_knob(RYOLO_KNOB_EPI_MAXBN) || p.ntaps * p.kb_per_tap * kBK <= 1152 || reducible;
+  if (knob && p.mode == RYOLO_OUT_NHWC_BF16 && fits && (p.BN % 64 == 0 || p.n_tiles == 1)) {
     p.epi_tma = 1;
-    if (knob == 2 && p.residual == (const __nv_bfloat16*)p.out && p.res_cpitch == p.out_cpitch && !p.scale && !p.shift &&
-        p.act == RYOLO_ACT_LINEAR) {
+    if (reducible) {
       p.epi_tma = 2;
       p.residual = nullptr;
     }

@@ -251,6 +251,45 @@ stem_im2col_kernel(const float* __restrict__ img, int N, int H, int W, int k, in
   }
 }
 
+// 3x3 / stride-1 stem (yolov4, yolov7), Kpad = 32: one thread per pixel gathers its 27 inputs (coalesced along W for
+// every (tap, channel), 9x reuse out of L1) and writes one 64-byte row.  The generic kernel above spends its time in
+// per-element integer divisions.
+__global__ void __launch_bounds__(256)
+stem_im2col_k3_kernel(const float* __restrict__ img, int N, int H, int W, __nv_bfloat16* __restrict__ y) {
+  const long long total = (long long)N * H * W;
+  const long long plane = (long long)H * W;
+  for (long long pix = blockIdx.x * (long long)blockDim.x + threadIdx.x; pix < total;
+       pix += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(pix % W), ho = (int)((pix / W) % H);
+    const long long n = pix / plane;
+    const float* base = img + n * 3 * plane;
+    float f[32];
+#pragma unroll
+    for (int kh = 0; kh < 3; kh++) {
+      const int hi = ho + kh - 1;
+      const bool hok = hi >= 0 && hi < H;
+#pragma unroll
+      for (int kw = 0; kw < 3; kw++) {
+        const int wi = wo + kw - 1;
+        const bool ok = hok && wi >= 0 && wi < W;
+#pragma unroll
+        for (int ci = 0; ci < 3; ci++)
+          f[(kh * 3 + kw) * 3 + ci] = ok ? __ldg(base + ci * plane + (long long)hi * W + wi) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 27; j < 32; j++) f[j] = 0.f;
+    uint4* o = reinterpret_cast<uint4*>(y + pix * 32);
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+      float t[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++) t[j] = f[8 * g + j];
+      o[g] = pack8(t);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ weight packing
 // OIHW fp32 -> [Cout][kh][kw][Cin] bf16 (stem == 0).  stem == 2 (transpose, for dgrad): -> [Cin][kh][kw][Cout].
 // stem >= 8: the 3-channel stem, [Cout,3,k,k] -> [Cout][Kpad = stem] in the im2col channel order (zero padded).
@@ -315,7 +354,7 @@ pack_weights_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, lon
 }
 
 // Reverse of pack_weights_multi for gradients: grad_oihw[first + r] += dwk[K-major index of r]  (dst = OIHW fp32
-// gradient, src = K-major fp32 scratch written by ryolo_conv2d_wgrad; stem: src is [Cout][64] im2col order).
+// gradient, src = K-major fp32 scratch written by ryolo_conv2d_wgrad; stem: src is [Cout][Kpad] im2col order).
 __global__ void __launch_bounds__(256)
 unpack_wgrad_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, long long total) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -427,8 +466,12 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, int k, int stride, 
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (Kpad / 8);
   if (total == 0) return RYOLO_OK;
-  stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W, k, stride, pad, Kpad, Ho, Wo,
-                                                                            (__nv_bfloat16*)y);
+  if (k == 3 && stride == 1 && Kpad == 32)
+    stem_im2col_k3_kernel<<<grid_for((long long)N * H * W, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W,
+                                                                                                 (__nv_bfloat16*)y);
+  else
+    stem_im2col_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(img, N, H, W, k, stride, pad, Kpad, Ho,
+                                                                              Wo, (__nv_bfloat16*)y);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -113,6 +113,7 @@ struct WgradParams {
   int TH, TW, tiles_h, tiles_w;
   int ksize, stride, pad, ntaps;
   int nb, tg;                               // X boxes per item (N = 64*nb), taps per item
+  int tap_grp;                              // taps issued per MMA (tap_grp * 64 * nb <= 256)
   int n_co_tiles, n_ci_tiles, n_tap_groups;
   int ks_total;                             // CTAs per (Cout tile, Cin tile) pair = sum of the tap groups' split counts
   int ks_first[10];                         // tap group g owns CTAs [ks_first[g], ks_first[g+1]) of a pair's ks_total
@@ -183,6 +184,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     }
     fence_proxy_async();
   }
+  const bool a_two = co0 + 64 < p.Cout;   // Cout tile reaches into its upper 64 channels; otherwise that box stays zero
+  if (!a_two) {
+    uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
+    for (int i = threadIdx.x; i < 2 * (int)(kBoxBytes / 16); i += kThreads) {
+      const int slot = i / (int)(kBoxBytes / 16), w = i - slot * (int)(kBoxBytes / 16);
+      *reinterpret_cast<uint4*>(base + (size_t)(slot * 2 + 1) * kBoxBytes + (size_t)w * 16) = make_uint4(0, 0, 0, 0);
+    }
+    fence_proxy_async();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -200,9 +210,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const int h0 = ph * p.TH, w0 = pw * p.TW;
         const uint32_t ab = pit & 1u, aphase = (pit >> 1) & 1u;
         mbar_wait(bar_aempty + 8 * ab, aphase ^ 1u);
-        mbar_expect_tx(bar_afull + 8 * ab, 2 * box_bytes);
+        mbar_expect_tx(bar_afull + 8 * ab, a_two ? 2 * box_bytes : box_bytes);
         tma_load_4d(sA + (ab * 2 + 0) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0, w0, h0, img);
-        tma_load_4d(sA + (ab * 2 + 1) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0 + 64, w0, h0, img);
+        if (a_two) tma_load_4d(sA + (ab * 2 + 1) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0 + 64, w0, h0, img);
         for (int ti = 0; ti < ntap; ti++) {
           const int tap = tap0 + ti;
           const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
@@ -217,7 +227,6 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_bf16_mn(CIT);
       const int ksteps = (rows + 15) / 16;
       int s = 0;
       uint32_t bphase = 0, pit = 0;
@@ -226,23 +235,31 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         mbar_wait(bar_afull + 8 * ab, aphase);
         tc_fence_after();
         const uint32_t a0 = sA + ab * 2 * kBoxBytes;
-        for (int ti = 0; ti < ntap; ti++) {
-          mbar_wait(bar_bfull + 8 * s, bphase);
+        // An M=128 MMA spends >= 128 cycles fetching its A operand from smem whatever N is, so narrow Cin tiles are
+        // issued several taps at a time: consecutive ring slots are consecutive 64-channel N atoms (LBO = one box)
+        // and the taps' accumulators are consecutive TMEM columns, so ONE N = g*CIT MMA covers g taps.
+        for (int ti = 0; ti < ntap;) {
+          int g = min(p.tap_grp, ntap - ti);
+          g = min(g, p.b_stages - s);                            // a group never wraps around the ring
+          for (int i = 0; i < g; i++) mbar_wait(bar_bfull + 8 * (s + i), bphase);
           tc_fence_after();
           const uint32_t b0 = sB + (uint32_t)(s * p.nb) * kBoxBytes;
+          const uint32_t idesc_g = umma_idesc_bf16_mn(g * CIT);
           for (int kk = 0; kk < ((p.dbg & 1) ? 0 : ksteps); kk++) {
             umma_bf16(tmem_base + (uint32_t)(ti * CIT), umma_desc_mn_sw128(a0 + kk * 2048, kBoxBytes),
-                      umma_desc_mn_sw128(b0 + kk * 2048, kBoxBytes), idesc, (pit | (uint32_t)kk) ? 1u : 0u);
+                      umma_desc_mn_sw128(b0 + kk * 2048, kBoxBytes), idesc_g, (pit | (uint32_t)kk) ? 1u : 0u);
           }
-          umma_commit(bar_bempty + 8 * s);
-          if (++s == p.b_stages) { s = 0; bphase ^= 1u; }
+          for (int i = 0; i < g; i++) umma_commit(bar_bempty + 8 * (s + i));
+          ti += g;
+          s += g;
+          if (s == p.b_stages) { s = 0; bphase ^= 1u; }
         }
         umma_commit(bar_aempty + 8 * ab);
       }
       umma_commit(bar_acc);
     }
   } else if (has_work) {
-    // dw is K-major like the packed forward weights: [Cout][tap][Cin] (stem: [Cout][64]).  A lane owns one Cout row
+    // dw is K-major like the packed forward weights: [Cout][tap][Cin] (stem: [Cout][Kpad]).  A lane owns one Cout row
     // and adds 4 consecutive Cin values per vector atomic (red.global.add.v4.f32).
     const int sub = warp & 3;
     const int co = co0 + sub * 32 + lane;
@@ -329,8 +346,8 @@ int encode_nhwc(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int N, int 
 
 extern "C" {
 
-// dwk (fp32, K-major [Cout][kh*kw][Cin] = the layout of the packed forward weights; for the stem x is the 64-channel
-// im2col tensor and dwk is [Cout][64]) += conv_backward_weight(x, dy).   x: bf16 NHWC view [N,H,W,Cin]; dy: bf16 NHWC
+// dwk (fp32, K-major [Cout][kh*kw][Cin] = the layout of the packed forward weights; for the stem x is the Kpad-channel
+// im2col tensor and dwk is [Cout][Kpad]) += conv_backward_weight(x, dy).   x: bf16 NHWC view [N,H,W,Cin]; dy: bf16 NHWC
 // view [N,Ho,Wo,Cdy] with Cdy >= Cout channels readable (extra channels are ignored).  dwk must be zeroed (or hold a
 // running sum) on entry and be 16-byte aligned; ryolo_unpack_wgrad_multi adds it into the OIHW gradients.
 int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
@@ -363,6 +380,7 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   p.tg = 512 / CIT;
   if (p.tg > p.ntaps) p.tg = p.ntaps;
   p.n_tap_groups = (p.ntaps + p.tg - 1) / p.tg;
+  p.tap_grp = ryolo_knob(RYOLO_KNOB_WG_TAPGRP) ? (256 / CIT > 0 ? 256 / CIT : 1) : 1;
   uint32_t cols = 32;
   while (cols < (uint32_t)(p.tg * CIT)) cols <<= 1;
   p.tmem_cols = cols;

@@ -100,3 +100,26 @@ def post_process(predictions, conf_thres=0.5, iou_thres=0.4, return_indices=Fals
 
 
 non_max_suppression = post_process      # north_star alias
+
+
+def encode_labels(polys, csl=True):
+    """Polygon targets -> loss-ready label rows on the device (datasets/base_dataset.py:137-154 in one launch).
+
+    polys: CUDA fp32 [T, 10] rows (image index, class, x1, y1, ..., x4, y4), vertices clockwise, i.e. the reference's
+    `targets` after `collate_fn` stamped the sample index (base_dataset.py:161-167).  Returns [T, 187] rows
+    (image, class, x, y, w, h, theta, csl[180]) when `csl`, else [T, 7]; T == 0 gives the reference's empty
+    zeros((0, 187)) / zeros((0, 7))."""
+    L.require_cuda(polys, "polys")
+    assert polys.dim() == 2 and polys.shape[1] == 10, "polys must be [T, 10]"
+    p = polys.contiguous().float()
+    out = torch.empty((p.shape[0], 187 if csl else 7), dtype=torch.float32, device=p.device)
+    L.check(L.lib().ryolo_encode_labels(L.ptr(p), p.shape[0], 1 if csl else 0, L.ptr(out), L.stream()))
+    L.count(1)
+    return out
+
+
+def xyxyxyxy2xywha(boxes):
+    """Drop-in for lib/general.py:70-104 on the device: [N, 8] clockwise vertices -> [N, 5] (x, y, w, h, theta)."""
+    L.require_cuda(boxes, "boxes")
+    polys = torch.cat((boxes.new_zeros(boxes.shape[0], 2), boxes.float()), 1)
+    return encode_labels(polys, csl=False)[:, 2:]

@@ -25,9 +25,9 @@ class Ctx:
         self.device = device
         self.model = model
         self.tape = [] if training else None
-        # one scratch for the per-CTA BN partial rows (layers run back to back on one stream) + a zeroed counter each
-        self._partial = torch.empty(ops.BN_PARTIAL_ROWS * 2 * 2048, dtype=torch.float32, device=device) \
-            if training else None
+        # one zeroed scratch for the cross-CTA BN accumulators (every launch leaves it zeroed again; layers run back
+        # to back on one stream) + a zeroed counter each
+        self._partial = torch.zeros(4 * 2048, dtype=torch.float32, device=device) if training else None
         self._counters = torch.zeros(model._bn_layers, dtype=torch.int32, device=device) if training else None
         self._ctr_off = 0
 

@@ -81,9 +81,9 @@ BN_PARTIAL_ROWS = 160   # RYOLO_BN_PARTIAL_ROWS
 
 def bn_fuse(partial, counter, bn, scale, shift, save_mean=None, save_invstd=None):
     """ryolo_bn_fuse for an nn.BatchNorm2d `bn` (fused statistics + finalize in the conv epilogue).
-    partial: fp32 scratch with >= BN_PARTIAL_ROWS*2*C elements; counter: zeroed int32[1]."""
+    partial: ZEROED fp32 scratch with >= 4*C elements (left zeroed by the kernel); counter: zeroed int32[1]."""
     f = L.BnFuse()
-    assert partial.numel() >= BN_PARTIAL_ROWS * 2 * bn.num_features
+    assert partial.numel() >= 4 * bn.num_features and partial.data_ptr() % 8 == 0
     f.partial, f.sum, f.sumsq, f.counter = partial.data_ptr(), None, None, counter.data_ptr()
     f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
     f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
@@ -134,8 +134,8 @@ def conv2d(x, w, Cout, k, stride, out=None, scale=None, shift=None, act="linear"
 
 
 def stem_kpad(k):
-    """K of the 1x1 conv the 3-channel k x k stem turns into (3*k*k values padded to a multiple of 64)."""
-    return (3 * k * k + 63) // 64 * 64
+    """K of the 1x1 conv the 3-channel k x k stem turns into (3*k*k values padded to a multiple of 32)."""
+    return (3 * k * k + 31) // 32 * 32
 
 
 def pack_weights(w_oihw, stem=False, transpose=False):

@@ -62,3 +62,14 @@ class TrainStep:
         items = self.forward_backward(imgs, targets)
         self.step()
         return items
+
+    def train_batch(self, imgs, targets, schedule, epoch, batch):
+        """One iteration of the reference's inner loop (train.py:183-202) under a `schedule.Schedule`: warm-up lr /
+        accumulate interpolation, loss.backward() accumulating into the flat gradient buffer, and optimizer.step() +
+        zero_grad() only when global_step % accumulate == 0.  Returns (loss items, stepped)."""
+        self.lr, _, do_step = schedule.batch(epoch, batch)
+        items = self.forward_backward(imgs, targets)
+        if do_step:
+            self.step()
+            self.zero_grad()
+        return items, do_step

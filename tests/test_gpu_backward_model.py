@@ -170,3 +170,43 @@ def test_train_step_with_no_targets(mode):
     items = R.TrainStep(m, crit, lr=0.01)(img, empty)
     assert torch.isfinite(items).all() and float(items[0]) == 0.0 and float(items[2]) > 0
     assert not torch.equal(w0, m.neck.conv38.conv[0].bias.detach())
+
+
+def test_gradient_accumulation_and_schedule():
+    """train.py:150-151,189-202: gradients of consecutive micro-batches add up in the flat buffer (conv weights, BN
+    gamma/beta, head bias alike) and TrainStep.train_batch only steps when global_step % accumulate == 0."""
+    R, m, img, tg, crit = _model_and_batch("yolov4", "csl", 2, S=96, bs=2)
+    img2 = torch.rand_like(img)
+    step = R.TrainStep(m, crit, lr=0.01)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    gs = []
+    for x in (img, img2):
+        m.load_state_dict(sd0)            # identical BN running statistics / weights for every pass
+        step.zero_grad()
+        step.forward_backward(x, tg)
+        gs.append(step.grad.clone())
+    m.load_state_dict(sd0)
+    step.zero_grad()
+    step.forward_backward(img, tg)
+    step.forward_backward(img2, tg)       # no zero_grad in between: accumulates
+    want = gs[0] + gs[1]
+    assert _l2(step.grad, want) < 1e-3, _l2(step.grad, want)
+    off = 0
+    for k, p in m.named_parameters():     # per tensor too (BN affine and bias gradients are small next to the convs')
+        n = p.numel()
+        w = want[off:off + n].view(p.shape)
+        if float(w.abs().max()) > 0:
+            assert _l2(p.grad, w) < 5e-3, (k, _l2(p.grad, w))
+        off += (n + 3) // 4 * 4
+    # schedule: bs=32 -> nominal accumulate 2; warm-up interpolates 1 -> 2 over nw=1000 steps
+    m.load_state_dict(sd0)
+    step.zero_grad()
+    sch = R.Schedule(epochs=1, iters_per_epoch=2000, batch_size=32, lr=0.01)
+    assert sch.accumulate == 2 and sch.nw == 1000
+    w0 = step.flat.clone()
+    items, stepped = step.train_batch(img, tg, sch, 0, 0)           # global_step 1: accumulate 1 -> steps
+    assert stepped and not torch.equal(w0, step.flat) and 0 < step.lr <= 0.01 / 1000 + 1e-12
+    assert float(step.grad.abs().max()) == 0.0                        # zero_grad after the step
+    sch.accumulate_probe = [sch.batch(0, b)[1:] for b in (998, 999, 1000, 1001)]
+    assert [int(a) for a, _ in sch.accumulate_probe] == [2, 2, 2, 2]
+    assert [s for _, s in sch.accumulate_probe] == [False, True, False, True]

@@ -123,7 +123,7 @@ def test_bn_act_backward(act):
     shift = beta.detach() - mean * scale
     sums = torch.zeros(2 * C, device="cuda")
     draw = ops.Act.empty(N, H, W, C, "cuda")
-    dg, db = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")     # gradients accumulate
     ops.bn_act_bwd(ops.Act(dout.cuda()), ops.Act(raw.cuda()), scale.cuda(), shift.cuda(), mean.cuda(), invstd.cuda(), act,
                    sums, draw, dg, db)
     ref = xr.grad.permute(0, 2, 3, 1)

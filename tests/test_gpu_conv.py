@@ -103,12 +103,13 @@ def test_conv_fused_bn_statistics(shape, epi):
     bn.weight.data = torch.rand(Cout, generator=gen) + 0.5
     bn.bias.data = torch.randn(Cout, generator=gen)
     bn = bn.cuda().train()
-    part = torch.empty(ops.BN_PARTIAL_ROWS * 2 * Cout, device="cuda")
+    part = torch.zeros(4 * Cout, device="cuda")
     ctr = torch.zeros(1, dtype=torch.int32, device="cuda")
     scale, shift, mean, invstd = (torch.empty(Cout, device="cuda") for _ in range(4))
     raw = ops.conv2d(ops.Act(x.cuda()), ops.pack_weights(w.cuda()), Cout, k, s,
                      bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
     torch.cuda.synchronize()
+    assert float(part.abs().max()) == 0.0                          # the scratch is handed back zeroed
     y = raw.torch().float().cpu()                                  # [N,Ho,Wo,Cout] as stored
     ref = _ref_conv(x, w, s)
     assert (y - ref).abs().max() < 2e-2 * ref.abs().max()

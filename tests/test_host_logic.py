@@ -1,5 +1,6 @@
 """CPU tests of host-side logic that needs no kernel: gradient-buffer bookkeeping of the backward executor,
 the stem/packing helpers' shapes, patch/bucket helpers."""
+import pytest
 import torch
 
 from ryolo_b200 import ops
@@ -36,9 +37,44 @@ def test_gradstore_union_of_slices_covers_the_buffer():
 
 
 def test_stem_kpad_and_views():
-    assert ops.stem_kpad(3) == 64 and ops.stem_kpad(6) == 128
+    assert ops.stem_kpad(3) == 32 and ops.stem_kpad(6) == 128
     a = _act(32, 16, 96)
     s = a.slice(8, 16)
     assert (s.coff, s.C, s.pitch) == (24, 16, 96) and s.ptr == a.buf.data_ptr() + 2 * 24
     assert ops.out_hw(800, 800, 3, 2) == (400, 400) and ops.out_hw(25, 25, 1, 1) == (25, 25)
     assert ops.out_hw(96, 96, 6, 2) == (48, 48)
+
+
+@pytest.mark.parametrize("epochs,ipe,bs,lr", [(3, 700, 8, 0.01), (2, 40, 32, 0.02), (5, 1000, 64, 0.001), (4, 300, 2, 0.01)])
+def test_schedule_matches_reference_loop(epochs, ipe, bs, lr):
+    """Schedule reproduces the lr / accumulate / step decisions of the reference loop (train.py:150-163,184-202,219-220)
+    executed here with the real torch SGD + LambdaLR objects."""
+    import numpy as np
+    import torch
+    from torch.optim.lr_scheduler import LambdaLR
+    import ryolo_b200 as R
+    lrf, warmup_prop = 0.1, 0.05
+    w = torch.nn.Parameter(torch.zeros(1))
+    nbs = 64
+    accumulate = max(round(nbs / bs), 1)
+    optimizer = torch.optim.SGD([w], lr=lr, momentum=0.937, nesterov=True)
+    nw = max(int((epochs * ipe) * warmup_prop), 1000)
+    lf = R.one_cycle(1, lrf, int(epochs))
+    scheduler = LambdaLR(optimizer, lr_lambda=lf)
+    initial_lr = optimizer.param_groups[0]['initial_lr']
+    sch = R.Schedule(epochs, ipe, bs, lr, lrf, warmup_prop)
+    assert sch.nw == nw
+    for epoch in range(epochs):
+        for batch in range(ipe):
+            global_step = ipe * epoch + batch + 1
+            if global_step <= nw:
+                xi = [0, nw]
+                accumulate = max(1, np.interp(global_step, xi, [1, nbs / bs]).round())
+                optimizer.param_groups[0]['lr'] = np.interp(global_step, xi, [0.0, initial_lr * lf(epoch)])
+            got_lr, got_acc, got_step = sch.batch(epoch, batch)
+            assert got_acc == accumulate and got_step == (global_step % accumulate == 0)
+            assert abs(got_lr - optimizer.param_groups[0]['lr']) <= 1e-12
+        w.grad = torch.zeros(1)
+        optimizer.step()
+        scheduler.step()
+        assert abs(sch.epoch_end() - optimizer.param_groups[0]['lr']) <= 1e-12

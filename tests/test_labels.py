@@ -1,0 +1,85 @@
+"""Label encoding: the oracle restatement is pinned to outputs of the reference's own
+xyxyxyxy2xywha / gaussian_label (tests/golden/labels.pt, made by tests/golden/make_golden_labels.py); the CUDA kernel
+is checked against the oracle through the public API."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import labels as olab
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "labels.pt")
+
+
+def test_oracle_matches_reference_golden():
+    g = torch.load(GOLD)
+    got = olab.encode_labels(g["targets"], csl=True)
+    assert got.shape == g["labels_csl"].shape == (600, 187)
+    assert torch.equal(got[:, :2], g["labels_csl"][:, :2])
+    # boxes: same float32 formulas; allow 1 ulp-level differences of norm/atan2 between code paths
+    assert (got[:, 2:7] - g["labels_csl"][:, 2:7]).abs().max() <= 2e-6
+    same_theta = got[:, 6] == g["labels_csl"][:, 6]
+    assert same_theta.float().mean() > 0.98
+    assert torch.equal(got[same_theta][:, 7:], g["labels_csl"][same_theta][:, 7:])      # CSL rows bit-exact
+    kf = olab.encode_labels(g["targets"], csl=False)
+    assert kf.shape == (600, 7) and (kf - g["labels_kfiou"]).abs().max() <= 2e-6
+    assert olab.encode_labels(torch.zeros((0, 10)), True).shape == (0, 187)
+
+
+def test_oracle_label_properties():
+    g = torch.load(GOLD)
+    lab = g["labels_csl"]
+    assert (lab[:, 5] >= lab[:, 4]).all()                                  # h is the long side
+    assert ((lab[:, 6] >= -np.pi / 2) & (lab[:, 6] < np.pi / 2)).all()     # norm_angle range
+    assert (lab[:, 7:].max(1).values == 1.0).all()                         # the gaussian peaks at 1 on its own bin
+    peak = lab[:, 7:].argmax(1).float()
+    deg = lab[:, 6] * 180 / np.pi + 90
+    d = (peak - deg).abs()
+    assert (torch.minimum(d, 180 - d) <= 1.0).all()                        # peak bin = angle class
+
+
+@pytest.mark.gpu
+def test_gpu_encode_labels_matches_oracle():
+    import ryolo_b200 as R
+    g = torch.load(GOLD)
+    t = g["targets"]
+    got = R.encode_labels(t.cuda(), csl=True).cpu()
+    ref = olab.encode_labels(t, csl=True)
+    assert got.shape == ref.shape
+    assert torch.equal(got[:, :2], ref[:, :2])
+    assert (got[:, 2:7] - ref[:, 2:7]).abs().max() <= 2e-6               # fp32 box values (tolerance: 1e-4 rel >> this)
+    # CSL row: bit-exact against the oracle's gaussian_label evaluated at the kernel's own theta
+    for i in range(0, len(t), 7):
+        row = olab.gaussian_label(got[i, 6] * 180 / np.pi + 90, 180, 0, 6)
+        assert np.array_equal(got[i, 7:].numpy(), row.astype(np.float32)), i
+    same = got[:, 6] == ref[:, 6]
+    assert same.float().mean() > 0.95 and torch.equal(got[same][:, 7:], ref[same][:, 7:])
+    kf = R.encode_labels(t.cuda(), csl=False).cpu()
+    assert (kf - olab.encode_labels(t, csl=False)).abs().max() <= 2e-6
+    assert R.encode_labels(torch.zeros((0, 10), device="cuda"), True).shape == (0, 187)
+    boxes = R.xyxyxyxy2xywha(t[:, 2:].cuda()).cpu()
+    assert torch.equal(boxes, kf[:, 2:])
+
+
+@pytest.mark.gpu
+def test_gpu_labels_feed_the_loss():
+    """encode_labels output is a valid `targets` tensor for ComputeCSLLoss (same values as oracle-made labels)."""
+    import ryolo_b200 as R
+    from oracle import hotpath as hp
+    from tests.util import CFG, HYP
+    g = torch.load(GOLD)
+    t = g["targets"][:64].clone()
+    t[:, 0] = torch.arange(64) % 2
+    lab = R.encode_labels(t.cuda(), csl=True)
+    gen = torch.Generator().manual_seed(3)
+    levels = [torch.randn(2, 3, s, s, 187 + 16, generator=gen) for s in (16, 8, 4)]
+
+    class M:
+        anchors, nc = hp.make_anchors(CFG["anchors"]), 16
+        def parameters(self):
+            return iter([torch.nn.Parameter(torch.zeros(1, device="cuda"))])
+    crit = R.ComputeCSLLoss(M(), HYP)
+    loss, items = crit([l.cuda().requires_grad_(True) for l in levels], lab)
+    ref_loss, ref_items = hp.csl_loss([l.clone().requires_grad_(True) for l in levels], lab.cpu(), M.anchors, 16, HYP)
+    assert abs(items["total_loss"] - ref_items["total_loss"]) <= 1e-4 * abs(ref_items["total_loss"])

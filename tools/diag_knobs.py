@@ -24,22 +24,24 @@ step = R.TrainStep(m, crit)
 img = torch.rand(bs, 3, S, S, device="cuda")
 tg = make_targets(0, bs, 2).cuda()
 flat0 = step.flat.clone()
-BASE = dict(halo=0, dbg=0, wg_split=1, wg_dbg=0, epi_tma=0, epi_maxbn=64)
+KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd"]
+BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the library's defaults
 VARIANTS = [
     ("base", {}),
     ("wg_uniform", dict(wg_split=0)),
+    ("wg_tap1", dict(wg_tapgrp=0)),
     ("wg_nomma", dict(wg_dbg=1)),
     ("wg_noload", dict(wg_dbg=2)),
+    ("bn_old", dict(bn_bwd=0)),
+    ("epi_direct", dict(epi_tma=0)),
+    ("epi_tma1", dict(epi_tma=1)),
+    ("epi_bn64", dict(epi_maxbn=64)),
+    ("epi_bn256", dict(epi_maxbn=256)),
     ("nostore", dict(dbg=1)),
     ("nostats", dict(dbg=2)),
     ("nostore_nostats", dict(dbg=3)),
     ("nomma", dict(dbg=4)),
     ("noaload", dict(dbg=8)),
-    ("tma64", dict(epi_tma=1, epi_maxbn=64)),
-    ("tma128", dict(epi_tma=1, epi_maxbn=128)),
-    ("tma256", dict(epi_tma=1, epi_maxbn=256)),
-    ("tmared256", dict(epi_tma=2, epi_maxbn=256)),
-    ("halo", dict(halo=1)),
 ]
 res = {}
 for name, kn in VARIANTS:
