@@ -14,7 +14,8 @@
 //   split-K     the patches of an item are dealt round-robin to its CTAs (the SMs are shared out between the items in
 //               proportion to their tap counts); every CTA keeps its partial dW in TMEM
 //               for its whole life and adds it to the fp32 OIHW gradient with atomics once at the end
-//   pipeline    warp 0 TMA producer (dY ring of 2, X ring of b_stages) | warp 1 MMA issuer | warps 2-5 epilogue
+//   pipeline    warp 0 TMA producer (dY ring of 2-6 slots, X ring of 2-12 stages: 14 boxes of smem shared out per CTA
+//               by the length of its tap group) | warp 1 MMA issuer | warps 2-5 epilogue
 #include "common.cuh"
 #include "ryolo_b200.h"
 #include <cuda.h>
@@ -24,7 +25,9 @@
 namespace {
 
 constexpr int kThreads = 192;
-constexpr int kMaxBStages = 8;
+constexpr int kMaxBStages = 12;
+constexpr int kMaxASlots = 6;
+constexpr int kSmemBoxes = 14;              // 14 x 16 KB boxes + 1 KB alignment slack = 225 KB of the 227 KB a CTA may own
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -117,7 +120,7 @@ struct WgradParams {
   int n_co_tiles, n_ci_tiles, n_tap_groups;
   int ks_total;                             // CTAs per (Cout tile, Cin tile) pair = sum of the tap groups' split counts
   int ks_first[10];                         // tap group g owns CTAs [ks_first[g], ks_first[g+1]) of a pair's ks_total
-  int b_stages;
+  int a_boxes;                              // 64-channel dY boxes per A slot: 2, or 1 when Cout <= 64 (upper atom = a shared zero box)
   int slot_rows;                            // rows per smem box slot: 128, or 64 for wide Cin tiles (deeper ring)
   uint32_t tmem_cols;
   int dbg;                                  // RYOLO_WG_DBG timing experiments: 1 = no MMAs, 2 = no X loads (results are wrong)
@@ -130,13 +133,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t kBoxBytes = (uint32_t)p.slot_rows * 128u;         // one [slot_rows pixels x 64 channels] bf16 box
-  const uint32_t sA = smem_base;                                   // 2 slots x 2 boxes (dY, 128 channels)
-  const uint32_t sB = smem_base + 4 * kBoxBytes;                   // b_stages slots x nb boxes (X)
-  __shared__ __align__(8) uint64_t bars[2 * kMaxBStages + 5];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxBStages + 2 * kMaxASlots + 1];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_bfull = smem_u32(&bars[0]), bar_bempty = smem_u32(&bars[kMaxBStages]),
-                 bar_afull = smem_u32(&bars[2 * kMaxBStages]), bar_aempty = smem_u32(&bars[2 * kMaxBStages + 2]),
-                 bar_acc = smem_u32(&bars[2 * kMaxBStages + 4]);
+                 bar_afull = smem_u32(&bars[2 * kMaxBStages]), bar_aempty = smem_u32(&bars[2 * kMaxBStages + kMaxASlots]),
+                 bar_acc = smem_u32(&bars[2 * kMaxBStages + 2 * kMaxASlots]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // split-K shares are proportional to the taps a group carries (a 9-tap layer with tg = 8 has groups of 8 and 1 taps)
@@ -151,6 +152,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int tap0 = tgi * p.tg, ntap = min(p.tg, p.ntaps - tap0);
   const int co0 = cot * 128, ci0 = cit * 64 * p.nb;
   const int CIT = 64 * p.nb;
+  // smem partition of THIS CTA (in 16 KB boxes): [A ring: a_slots x a_boxes][zero box when a_boxes == 1][B ring].  A patch
+  // costs a_boxes + ntap*nb boxes; a CTA whose tap group is short keeps more patches in flight (with two A slots a
+  // one-tap item ran at two patches per memory round trip).
+  const int zero_box = p.a_boxes == 1 ? 1 : 0;
+  int a_slots = (kSmemBoxes - zero_box) / (p.a_boxes + ntap * p.nb);
+  a_slots = max(2, min(kMaxASlots, a_slots));
+  const int b_stages = min(kMaxBStages, (kSmemBoxes - zero_box - a_slots * p.a_boxes) / p.nb);
+  const uint32_t sA = smem_base;
+  const uint32_t sZ = sA + (uint32_t)(a_slots * p.a_boxes) * kBoxBytes;           // all-zero box (a_boxes == 1)
+  const uint32_t sB = sZ + (uint32_t)zero_box * kBoxBytes;
   const int n_patches = p.N * p.tiles_h * p.tiles_w;
   const int rows = p.TH * p.TW;
   const uint32_t box_bytes = (uint32_t)rows * 128u;
@@ -158,11 +169,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmG);
     prefetch_tmap(&tmX);
-    for (int s = 0; s < p.b_stages; s++) {
+    for (int s = 0; s < b_stages; s++) {
       mbar_init(bar_bfull + 8 * s, 1);
       mbar_init(bar_bempty + 8 * s, 1);
     }
-    for (int s = 0; s < 2; s++) {
+    for (int s = 0; s < a_slots; s++) {
       mbar_init(bar_afull + 8 * s, 1);
       mbar_init(bar_aempty + 8 * s, 1);
     }
@@ -173,21 +184,27 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     tmem_alloc(smem_u32(&tmem_slot), p.tmem_cols);
     tmem_relinquish();
   }
-  if (rows < ((rows + 15) & ~15)) {   // rows the TMA boxes never write but the last K step reads must be zeros
-    const int nbox = 4 + p.b_stages * p.nb;
-    const int tail16 = (p.slot_rows - rows) * 8;                   // 16-byte words per box tail
+  {
+    // rows the TMA boxes never write but the last K step reads must be zeros; so must the whole shared zero box
     uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
-    for (int i = threadIdx.x; i < nbox * tail16; i += kThreads) {
-      const int b = i / tail16, w = i - b * tail16;
-      *reinterpret_cast<uint4*>(base + (size_t)b * kBoxBytes + (size_t)rows * 128 + (size_t)w * 16) =
-          make_uint4(0, 0, 0, 0);
+    const int tail16 = (p.slot_rows - rows) * 8;                   // 16-byte words per box tail
+    if (rows < ((rows + 15) & ~15)) {
+      for (int i = threadIdx.x; i < kSmemBoxes * tail16; i += kThreads) {
+        const int b = i / tail16, w = i - b * tail16;
+        *reinterpret_cast<uint4*>(base + (size_t)b * kBoxBytes + (size_t)rows * 128 + (size_t)w * 16) =
+            make_uint4(0, 0, 0, 0);
+      }
+    }
+    if (zero_box) {
+      for (int i = threadIdx.x; i < (int)(kBoxBytes / 16); i += kThreads)
+        *reinterpret_cast<uint4*>(base + (size_t)(sZ - smem_base) + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
     }
     fence_proxy_async();
   }
-  const bool a_two = co0 + 64 < p.Cout;   // Cout tile reaches into its upper 64 channels; otherwise that box stays zero
-  if (!a_two) {
+  const bool a_two = p.a_boxes == 2 && co0 + 64 < p.Cout;   // the tile's upper 64 channels exist
+  if (p.a_boxes == 2 && !a_two) {                            // last Cout tile of a wide layer: its upper boxes stay zero
     uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
-    for (int i = threadIdx.x; i < 2 * (int)(kBoxBytes / 16); i += kThreads) {
+    for (int i = threadIdx.x; i < a_slots * (int)(kBoxBytes / 16); i += kThreads) {
       const int slot = i / (int)(kBoxBytes / 16), w = i - slot * (int)(kBoxBytes / 16);
       *reinterpret_cast<uint4*>(base + (size_t)(slot * 2 + 1) * kBoxBytes + (size_t)w * 16) = make_uint4(0, 0, 0, 0);
     }
@@ -201,18 +218,18 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 
   if (warp == 0) {
     if (lane == 0) {
-      int s = 0;
-      uint32_t bphase = 0, pit = 0;
-      for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
+      int s = 0, ab = 0;
+      uint32_t bphase = 0, aphase = 0;
+      for (int patch = split; patch < n_patches; patch += ksplit) {
         const int pw = patch % p.tiles_w;
         const int ph = (patch / p.tiles_w) % p.tiles_h;
         const int img = patch / (p.tiles_w * p.tiles_h);
         const int h0 = ph * p.TH, w0 = pw * p.TW;
-        const uint32_t ab = pit & 1u, aphase = (pit >> 1) & 1u;
+        const uint32_t a_dst = sA + (uint32_t)(ab * p.a_boxes) * kBoxBytes;
         mbar_wait(bar_aempty + 8 * ab, aphase ^ 1u);
         mbar_expect_tx(bar_afull + 8 * ab, a_two ? 2 * box_bytes : box_bytes);
-        tma_load_4d(sA + (ab * 2 + 0) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0, w0, h0, img);
-        if (a_two) tma_load_4d(sA + (ab * 2 + 1) * kBoxBytes, &tmG, bar_afull + 8 * ab, co0 + 64, w0, h0, img);
+        tma_load_4d(a_dst, &tmG, bar_afull + 8 * ab, co0, w0, h0, img);
+        if (a_two) tma_load_4d(a_dst + kBoxBytes, &tmG, bar_afull + 8 * ab, co0 + 64, w0, h0, img);
         for (int ti = 0; ti < ntap; ti++) {
           const int tap = tap0 + ti;
           const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
@@ -221,40 +238,42 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           for (int j = 0; j < ((p.dbg & 2) ? 0 : p.nb); j++)
             tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + 64 * j,
                         w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
-          if (++s == p.b_stages) { s = 0; bphase ^= 1u; }
+          if (++s == b_stages) { s = 0; bphase ^= 1u; }
         }
+        if (++ab == a_slots) { ab = 0; aphase ^= 1u; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       const int ksteps = (rows + 15) / 16;
-      int s = 0;
-      uint32_t bphase = 0, pit = 0;
+      int s = 0, ab = 0;
+      uint32_t bphase = 0, aphase = 0, pit = 0;
       for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
-        const uint32_t ab = pit & 1u, aphase = (pit >> 1) & 1u;
         mbar_wait(bar_afull + 8 * ab, aphase);
         tc_fence_after();
-        const uint32_t a0 = sA + ab * 2 * kBoxBytes;
+        const uint32_t a0 = sA + (uint32_t)(ab * p.a_boxes) * kBoxBytes;
+        const uint32_t a_lbo = p.a_boxes == 2 ? kBoxBytes : sZ - a0;      // upper 64 channels: next box, or the zero box
         // An M=128 MMA spends >= 128 cycles fetching its A operand from smem whatever N is, so narrow Cin tiles are
         // issued several taps at a time: consecutive ring slots are consecutive 64-channel N atoms (LBO = one box)
         // and the taps' accumulators are consecutive TMEM columns, so ONE N = g*CIT MMA covers g taps.
         for (int ti = 0; ti < ntap;) {
           int g = min(p.tap_grp, ntap - ti);
-          g = min(g, p.b_stages - s);                            // a group never wraps around the ring
+          g = min(g, b_stages - s);                              // a group never wraps around the ring
           for (int i = 0; i < g; i++) mbar_wait(bar_bfull + 8 * (s + i), bphase);
           tc_fence_after();
           const uint32_t b0 = sB + (uint32_t)(s * p.nb) * kBoxBytes;
           const uint32_t idesc_g = umma_idesc_bf16_mn(g * CIT);
           for (int kk = 0; kk < ((p.dbg & 1) ? 0 : ksteps); kk++) {
-            umma_bf16(tmem_base + (uint32_t)(ti * CIT), umma_desc_mn_sw128(a0 + kk * 2048, kBoxBytes),
+            umma_bf16(tmem_base + (uint32_t)(ti * CIT), umma_desc_mn_sw128(a0 + kk * 2048, a_lbo),
                       umma_desc_mn_sw128(b0 + kk * 2048, kBoxBytes), idesc_g, (pit | (uint32_t)kk) ? 1u : 0u);
           }
           for (int i = 0; i < g; i++) umma_commit(bar_bempty + 8 * (s + i));
           ti += g;
           s += g;
-          if (s == p.b_stages) { s = 0; bphase ^= 1u; }
+          if (s == b_stages) { s = 0; bphase ^= 1u; }
         }
         umma_commit(bar_aempty + 8 * ab);
+        if (++ab == a_slots) { ab = 0; aphase ^= 1u; }
       }
       umma_commit(bar_acc);
     }
@@ -415,13 +434,9 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
     p.ks_first[g + 1] = p.ks_first[g] + ks[g];
   }
   p.ks_total = p.ks_first[p.n_tap_groups];
-  const size_t budget = 200 * 1024;
+  p.a_boxes = Cout > 64 ? 2 : 1;
   const size_t kBoxBytes = (size_t)p.slot_rows * 128;
-  int bst = (int)((budget - 1024 - 4 * kBoxBytes) / ((size_t)p.nb * kBoxBytes));
-  if (bst > kMaxBStages) bst = kMaxBStages;
-  RY_CHECK_ARG(bst >= 2, "wgrad: shared memory budget too small");
-  p.b_stages = bst;
-  const size_t smem = 1024 + 4 * kBoxBytes + (size_t)bst * p.nb * kBoxBytes;
+  const size_t smem = 1024 + (size_t)kSmemBoxes * kBoxBytes;
   p.dw = dwk;
   p.dbg = ryolo_knob(RYOLO_KNOB_WG_DBG);
   CUtensorMap tmG, tmX;
@@ -432,7 +447,7 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     configured = true;
   }

@@ -91,14 +91,14 @@ def test_wgrad_stem():
     w = torch.zeros(32, 3, 3, 3, requires_grad=True)
     y = F.conv2d(img.bfloat16().float(), w, None, 1, 1)
     y.backward(dy.float().permute(0, 3, 1, 2))
-    dwk = torch.zeros(32 * 64, device="cuda")
+    dwk = torch.zeros(32 * ops.stem_kpad(3), device="cuda")
     ops.conv2d_wgrad(ops.stem_im2col(img.cuda()), ops.Act(dy.cuda()), 32, 1, 1, dwk)
     assert (ops.wgrad_to_oihw(dwk, 32, 3, 3, stem=True).cpu() - w.grad).abs().max() < 1e-2 * w.grad.abs().max()
     # 6x6 / stride-2 stem of yolov5
     w6 = torch.zeros(64, 3, 6, 6, requires_grad=True)
     dy6 = torch.randn(2, 20, 18, 64, generator=gen).bfloat16()
     F.conv2d(img.bfloat16().float(), w6, None, 2, 2).backward(dy6.float().permute(0, 3, 1, 2))
-    dwk6 = torch.zeros(64 * 128, device="cuda")
+    dwk6 = torch.zeros(64 * ops.stem_kpad(6), device="cuda")
     ops.conv2d_wgrad(ops.stem_im2col(img.cuda(), 6, 2), ops.Act(dy6.cuda()), 64, 1, 1, dwk6)
     assert (ops.wgrad_to_oihw(dwk6, 64, 3, 6, stem=True).cpu() - w6.grad).abs().max() < 1e-2 * w6.grad.abs().max()
 

@@ -48,7 +48,13 @@ def test_gpu_encode_labels_matches_oracle():
     ref = olab.encode_labels(t, csl=True)
     assert got.shape == ref.shape
     assert torch.equal(got[:, :2], ref[:, :2])
-    assert (got[:, 2:7] - ref[:, 2:7]).abs().max() <= 2e-6               # fp32 box values (tolerance: 1e-4 rel >> this)
+    assert (got[:, 2:6] - ref[:, 2:6]).abs().max() <= 2e-6               # fp32 box values (tolerance: 1e-4 rel >> this)
+    # theta: a box lying exactly on the +-pi/2 seam (axis-aligned fixtures) may land on either side of norm_angle's
+    # cut when atan2f differs by one ulp between libm and CUDA: same box, same CSL row (its index is taken mod 180)
+    dth = (got[:, 6] - ref[:, 6]).abs()
+    assert torch.minimum(dth, np.pi - dth).max() <= 2e-6
+    assert ((got[:, 6] >= -np.pi / 2) & (got[:, 6] < np.pi / 2)).all()
+    assert (dth > 1.0).sum() <= 40                                      # only the seam fixtures
     # CSL row: bit-exact against the oracle's gaussian_label evaluated at the kernel's own theta
     for i in range(0, len(t), 7):
         row = olab.gaussian_label(got[i, 6] * 180 / np.pi + 90, 180, 0, 6)
@@ -56,7 +62,7 @@ def test_gpu_encode_labels_matches_oracle():
     same = got[:, 6] == ref[:, 6]
     assert same.float().mean() > 0.95 and torch.equal(got[same][:, 7:], ref[same][:, 7:])
     kf = R.encode_labels(t.cuda(), csl=False).cpu()
-    assert (kf - olab.encode_labels(t, csl=False)).abs().max() <= 2e-6
+    assert torch.equal(kf, got[:, :7])
     assert R.encode_labels(torch.zeros((0, 10), device="cuda"), True).shape == (0, 187)
     boxes = R.xyxyxyxy2xywha(t[:, 2:].cuda()).cpu()
     assert torch.equal(boxes, kf[:, 2:])
@@ -73,7 +79,7 @@ def test_gpu_labels_feed_the_loss():
     t[:, 0] = torch.arange(64) % 2
     lab = R.encode_labels(t.cuda(), csl=True)
     gen = torch.Generator().manual_seed(3)
-    levels = [torch.randn(2, 3, s, s, 187 + 16, generator=gen) for s in (16, 8, 4)]
+    levels = [torch.randn(2, 3, s, s, 185 + 16, generator=gen) for s in (16, 8, 4)]
 
     class M:
         anchors, nc = hp.make_anchors(CFG["anchors"]), 16
