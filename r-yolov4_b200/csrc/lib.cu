@@ -23,12 +23,13 @@ int ryolo_abi_version(void) { return 1; }
 //   wg_split  wgrad: 1 = split-K shares proportional to the tap groups' tap counts, 0 = uniform
 //   wg_dbg    wgrad timing experiments, results are WRONG: 1 no MMAs, 2 no X loads
 //   wg_tapgrp wgrad: 1 = one MMA covers as many taps as fit N = 256, 0 = one tap per MMA
+//   wg_trans  wgrad: 1 = layers with Cin <= 128 transpose their TMA boxes in smem and run K-major MMAs, 0 = MN-major
 //   bn_bwd    BatchNorm backward reduce pass: 1 = low-register variant, 0 = original
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 1};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 1, 1};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

@@ -311,6 +311,233 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
+// ------------------------------------------------------------------------------------ transposing variant (Cin <= 128)
+// MN-major operands cost the tensor core ~2x the smem fetch time of K-major ones, independent of N, which leaves the
+// narrow layers (N = 64 / 128) at a few percent of the MMA rate (measured: ~0.9 us per tap and patch whatever N is).
+// Here the four warps that otherwise idle until the epilogue TRANSPOSE every TMA box in shared memory
+// (ldmatrix.trans -> stmatrix, 128-byte swizzle on both sides) into K-major tiles [channels][pixels], so that the MMAs
+// run on K-major descriptors with K = pixels:
+//   RAW ring   4 boxes [128 px][64 ch]                  TMA destination, freed as soon as it has been transposed
+//   TA  ring   2 slots [2 k-halves][128 co][64 px]      dY^T of a patch (rows 64..127 stay zero when the tile has <= 64 co)
+//   TB  ring   3 stages [2 k-halves][128 rows][64 px]   X^T of two boxes = N <= 128 (two taps for Cin <= 64, one for Cin <= 128)
+// Same work decomposition, TMEM layout and epilogue as conv_wgrad_kernel.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// D fp32, A/B bf16, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t umma_idesc_bf16_k(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void stmatrix_x4(uint32_t addr, const uint32_t (&r)[4]) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+               ::"r"(addr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+
+constexpr int kRawSlots = 4, kTaSlots = 2, kTbStages = 3;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX,
+                    const WgradParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kBox = 16384u;
+  const uint32_t sRaw = smem_base;                          // 4 boxes
+  const uint32_t sTA = sRaw + kRawSlots * kBox;             // 2 slots x 32 KB
+  const uint32_t sTB = sTA + kTaSlots * 2 * kBox;           // 3 stages x 32 KB
+  __shared__ __align__(8) uint64_t bars[2 * kRawSlots + 2 * kTaSlots + 2 * kTbStages + 1];
+  __shared__ uint32_t tmem_slot;
+  const uint32_t bar_rfull = smem_u32(&bars[0]), bar_rempty = smem_u32(&bars[kRawSlots]),
+                 bar_afull = smem_u32(&bars[2 * kRawSlots]), bar_aempty = smem_u32(&bars[2 * kRawSlots + kTaSlots]),
+                 bar_bfull = smem_u32(&bars[2 * kRawSlots + 2 * kTaSlots]),
+                 bar_bempty = smem_u32(&bars[2 * kRawSlots + 2 * kTaSlots + kTbStages]),
+                 bar_acc = smem_u32(&bars[2 * kRawSlots + 2 * kTaSlots + 2 * kTbStages]);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int pr = blockIdx.x % p.ks_total;
+  const int pair = blockIdx.x / p.ks_total;
+  int tgi = 0;
+  while (tgi + 1 < p.n_tap_groups && pr >= p.ks_first[tgi + 1]) tgi++;
+  const int split = pr - p.ks_first[tgi];
+  const int ksplit = p.ks_first[tgi + 1] - p.ks_first[tgi];
+  const int cit = pair % p.n_ci_tiles;
+  const int cot = pair / p.n_ci_tiles;
+  const int tap0 = tgi * p.tg, ntap = min(p.tg, p.ntaps - tap0);
+  const int co0 = cot * 128, ci0 = cit * 64 * p.nb;
+  const int CIT = 64 * p.nb;
+  const int n_patches = p.N * p.tiles_h * p.tiles_w;
+  const int rows = p.TH * p.TW;
+  const uint32_t box_bytes = (uint32_t)rows * 128u;
+  const int na = (co0 + 64 < p.Cout) ? 2 : 1;              // dY boxes per patch
+  const int nxb = ntap * p.nb;                             // X boxes per patch
+  const int nst = (nxb + 1) >> 1;                          // TB stages per patch (two boxes each, the last may hold one)
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmG);
+    prefetch_tmap(&tmX);
+    for (int s = 0; s < kRawSlots; s++) { mbar_init(bar_rfull + 8 * s, 1); mbar_init(bar_rempty + 8 * s, 4); }
+    for (int s = 0; s < kTaSlots; s++) { mbar_init(bar_afull + 8 * s, 4 * na); mbar_init(bar_aempty + 8 * s, 1); }
+    for (int s = 0; s < kTbStages; s++) { mbar_init(bar_bfull + 8 * s, 8); mbar_init(bar_bempty + 8 * s, 1); }
+    mbar_init(bar_acc, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&tmem_slot), p.tmem_cols);
+    tmem_relinquish();
+  }
+  {
+    uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
+    // pixels a TMA box never writes (rows >= TH*TW) become K columns of the transposed tiles: keep them zero
+    const int tail16 = (128 - rows) * 8;
+    for (int i = threadIdx.x; i < kRawSlots * tail16; i += kThreads) {
+      const int b = i / tail16, w = i - b * tail16;
+      *reinterpret_cast<uint4*>(base + (size_t)b * kBox + (size_t)rows * 128 + (size_t)w * 16) = make_uint4(0, 0, 0, 0);
+    }
+    if (na == 1) {      // co rows 64..127 of both k-halves of both TA slots
+      for (int i = threadIdx.x; i < kTaSlots * 2 * 512; i += kThreads) {
+        const int h = i / 512, w = i - h * 512;              // h = slot*2 + k-half, 512 x 16 B = rows 64..127
+        *reinterpret_cast<uint4*>(base + (size_t)(sTA - smem_base) + (size_t)h * kBox + 8192 + (size_t)w * 16) =
+            make_uint4(0, 0, 0, 0);
+      }
+    }
+    fence_proxy_async();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int rs = 0;
+      uint32_t rphase = 0;
+      auto load = [&](const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+        mbar_wait(bar_rempty + 8 * rs, rphase ^ 1u);
+        mbar_expect_tx(bar_rfull + 8 * rs, box_bytes);
+        tma_load_4d(sRaw + (uint32_t)rs * kBox, tm, bar_rfull + 8 * rs, c0, c1, c2, c3);
+        if (++rs == kRawSlots) { rs = 0; rphase ^= 1u; }
+      };
+      for (int patch = split; patch < n_patches; patch += ksplit) {
+        const int pw = patch % p.tiles_w;
+        const int ph = (patch / p.tiles_w) % p.tiles_h;
+        const int img = patch / (p.tiles_w * p.tiles_h);
+        const int h0 = ph * p.TH, w0 = pw * p.TW;
+        for (int j = 0; j < na; j++) load(&tmG, co0 + 64 * j, w0, h0, img);
+        for (int ti = 0; ti < ntap; ti++) {
+          const int tap = tap0 + ti;
+          const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
+          for (int j = 0; j < p.nb; j++)
+            load(&tmX, ci0 + 64 * j, w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aphase = 0, bphase = 0, pit = 0;
+      for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
+        mbar_wait(bar_afull + 8 * as, aphase);
+        tc_fence_after();
+        const uint32_t a0 = sTA + (uint32_t)as * 2 * kBox;
+        for (int st = 0; st < nst; st++) {
+          const int nbox = min(2, nxb - 2 * st);
+          mbar_wait(bar_bfull + 8 * bs, bphase);
+          tc_fence_after();
+          const uint32_t b0 = sTB + (uint32_t)bs * 2 * kBox;
+          const uint32_t idesc = umma_idesc_bf16_k(64 * nbox);
+          const uint32_t d = tmem_base + (uint32_t)(st * 128);           // boxes are consecutive 64-column blocks
+#pragma unroll
+          for (int kk = 0; kk < 8; kk++) {                                // 2 k-halves x 4 K=16 steps
+            const uint32_t off = (uint32_t)(kk >> 2) * kBox + (uint32_t)(kk & 3) * 32u;
+            umma_bf16(d, umma_desc_k_sw128(a0 + off), umma_desc_k_sw128(b0 + off), idesc, (pit | (uint32_t)kk) ? 1u : 0u);
+          }
+          umma_commit(bar_bempty + 8 * bs);
+          if (++bs == kTbStages) { bs = 0; bphase ^= 1u; }
+        }
+        umma_commit(bar_aempty + 8 * as);
+        if (++as == kTaSlots) { as = 0; aphase ^= 1u; }
+      }
+      umma_commit(bar_acc);
+    }
+  } else {
+    // ---------------- transposers (4 warps), then the epilogue
+    const int tw = warp - 2;
+    int rs = 0, as = 0, bs = 0;
+    uint32_t rphase = 0, aphase = 0, bphase = 0;
+    // one box: [128 px][64 ch] (SW128) -> two K-major tiles [64 ch][64 px] (SW128) at dst + khalf*16 KB + row0*128
+    auto transpose_box = [&](uint32_t dst, int row0) {
+      mbar_wait(bar_rfull + 8 * rs, rphase);
+      const uint32_t src = sRaw + (uint32_t)rs * kBox;
+      const int i = lane >> 3, r = lane & 7;
+#pragma unroll
+      for (int q8 = 0; q8 < 8; q8++) {
+        const int q = tw + 4 * q8;                  // 32 (4-tile) jobs per box, 8 per warp
+        const int cb = q & 7, pb0 = (q >> 3) * 4;   // channel block, first of four pixel blocks
+        uint32_t v[4];
+        ldmatrix_x4_trans(src + (uint32_t)(8 * (pb0 + i) + r) * 128u + (uint32_t)((cb ^ r) << 4), v);
+        stmatrix_x4(dst + (uint32_t)(pb0 >> 3) * kBox + (uint32_t)(row0 + 8 * cb + r) * 128u +
+                        (uint32_t)((((pb0 + i) & 7) ^ r) << 4), v);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_rempty + 8 * rs);
+      if (++rs == kRawSlots) { rs = 0; rphase ^= 1u; }
+    };
+    for (int patch = split; patch < n_patches; patch += ksplit) {
+      mbar_wait(bar_aempty + 8 * as, aphase ^ 1u);
+      for (int j = 0; j < na; j++) {
+        transpose_box(sTA + (uint32_t)as * 2 * kBox, 64 * j);
+        if (lane == 0) mbar_arrive(bar_afull + 8 * as);
+      }
+      if (++as == kTaSlots) { as = 0; aphase ^= 1u; }
+      for (int st = 0; st < nst; st++) {
+        const int nbox = min(2, nxb - 2 * st);
+        mbar_wait(bar_bempty + 8 * bs, bphase ^ 1u);
+        for (int j = 0; j < 2; j++) {
+          if (j < nbox) transpose_box(sTB + (uint32_t)bs * 2 * kBox, 64 * j);
+          if (lane == 0) mbar_arrive(bar_bfull + 8 * bs);     // a missing second box still counts (fixed arrival count)
+        }
+        if (++bs == kTbStages) { bs = 0; bphase ^= 1u; }
+      }
+    }
+    const int sub = warp & 3;
+    const int co = co0 + sub * 32 + lane;
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    const int rowlen = p.ntaps * p.Cin;
+    for (int ti = 0; ti < ntap; ti++) {
+      const int tap = tap0 + ti;
+#pragma unroll 1
+      for (int c0 = 0; c0 < CIT; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(sub * 32) << 16) + (uint32_t)(ti * CIT + c0), v);
+        tmem_ld_wait();
+        if (co < p.Cout) {
+          float* row = p.dw + (long long)co * rowlen + (long long)tap * p.Cin + ci0 + c0;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (ci0 + c0 + j < p.Cin)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + j), "f"(__uint_as_float(v[j])),
+                           "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])),
+                           "f"(__uint_as_float(v[j + 3]))
+                           : "memory");
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -448,10 +675,15 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(conv_wgrad_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     configured = true;
   }
-  conv_wgrad_kernel<<<pairs * p.ks_total, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
+  if (ryolo_knob(RYOLO_KNOB_WG_TRANS) && p.nb <= 2)
+    conv_wgrad_t_kernel<<<pairs * p.ks_total, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
+  else
+    conv_wgrad_kernel<<<pairs * p.ks_total, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

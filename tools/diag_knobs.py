@@ -24,12 +24,14 @@ step = R.TrainStep(m, crit)
 img = torch.rand(bs, 3, S, S, device="cuda")
 tg = make_targets(0, bs, 2).cuda()
 flat0 = step.flat.clone()
-KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd"]
+KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans"]
 BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the library's defaults
 VARIANTS = [
     ("base", {}),
     ("wg_uniform", dict(wg_split=0)),
     ("wg_tap1", dict(wg_tapgrp=0)),
+    ("wg_mn", dict(wg_trans=0)),
+    ("wg_mn_uniform", dict(wg_trans=0, wg_split=0)),
     ("wg_nomma", dict(wg_dbg=1)),
     ("wg_noload", dict(wg_dbg=2)),
     ("bn_old", dict(bn_bwd=0)),
