@@ -140,6 +140,12 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
          ((uint64_t)(1024 >> 4) << 32) /* SBO */ | ((uint64_t)1 << 46) /* descriptor version (sm_100) */ |
          ((uint64_t)2 << 61) /* SWIZZLE_128B */;
 }
+// K-major, SWIZZLE_64B: rows of 64 bytes (32 bf16), 8-row groups 512 bytes apart.  Used when Cin == 32: a 64-channel box
+// over a 32-channel tensor overhangs it, and TMA serves overhanging rows on a ~2x slower path (tools/oob_probe.py).
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61) /* SWIZZLE_64B */;
+}
 // Same layout, but the 8-row groups are `sbo_bytes` apart and the start may sit on any 128-byte row of a swizzle atom
 // (shifted view into a halo tile): base_offset carries the row phase of the start address.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128_view(uint32_t saddr, uint32_t sbo_bytes, int use_base_offset) {
@@ -172,6 +178,7 @@ struct ConvKernelParams {
   uint32_t tmem_cols;
   int ksize, stride, pad, kb_per_tap;
   int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
+  int kbk;                         // K elements per stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
   int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads
@@ -211,7 +218,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
   const int BN = p.BN, STAGES = p.stages;
-  const uint32_t kABytes = kBM * kBK * 2, kBBytes = (uint32_t)BN * kBK * 2;
+  const uint32_t kABytes = kBM * (uint32_t)p.kbk * 2, kBBytes = (uint32_t)BN * (uint32_t)p.kbk * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t sA = smem_base;
@@ -259,7 +266,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0) {
     // ================================ TMA producer (one lane) ================================
     if (lane == 0) {
-      const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * kBK * 2;
+      const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
       const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
       int s = 0, as = 0;
       uint32_t phase = 0, aphase = 0;
@@ -299,8 +306,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(bar_empty + 8 * s, phase ^ 1u);
           mbar_expect_tx(bar_full + 8 * s, ((p.dbg & 8) ? 0u : a_bytes) + kBBytes);
           if (!(p.dbg & 8))
-            tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * kBK, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
-          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * kBK, n0);
+            tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * p.kbk, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
+          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
           if (++s == STAGES) { s = 0; phase ^= 1u; }
         }
       }
@@ -348,10 +355,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           tc_fence_after();
           const uint32_t a0 = sA + s * kABytes, b0 = sB + s * kBBytes;
           if (!(p.dbg & 4)) {
+            if (p.kbk == 32) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; k++) {
-              umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
-                        (kb | k) ? 1u : 0u);
+              for (int k = 0; k < 2; k++)
+                umma_bf16(d_tmem, umma_desc_k_sw64(a0 + k * 32), umma_desc_k_sw64(b0 + k * 32), idesc, (kb | k) ? 1u : 0u);
+            } else {
+#pragma unroll
+              for (int k = 0; k < kBK / 16; k++) {
+                umma_bf16(d_tmem, umma_desc_k_sw128(a0 + k * 32), umma_desc_k_sw128(b0 + k * 32), idesc,
+                          (kb | k) ? 1u : 0u);
+              }
             }
           }
           umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
@@ -683,7 +696,7 @@ void pick_patch(int Ho, int Wo, int stride, int* TH, int* TW) {
 void maybe_enable_halo(ConvKernelParams* p) {
   const int mode = ryolo_knob(RYOLO_KNOB_HALO);
   p->halo = 0;
-  if (!mode || p->ntaps != 9 || p->stride != 1 || p->ksize != 3) return;
+  if (!mode || p->ntaps != 9 || p->stride != 1 || p->ksize != 3 || p->kbk != kBK) return;
   const double tiles = (double)((p->Ho + 15) / 16) * ((p->Wo + 7) / 8);
   const double eff = (double)p->Ho * p->Wo / (tiles * 128.0);
   const double cur = (double)p->Ho * p->Wo / ((double)p->tiles_h * p->tiles_w * 128.0);
@@ -703,7 +716,8 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   p->ksize = d->ksize; p->stride = d->stride; p->pad = (d->ksize - 1) / 2;
   p->Ho = (d->H + 2 * p->pad - d->ksize) / d->stride + 1;
   p->Wo = (d->W + 2 * p->pad - d->ksize) / d->stride + 1;
-  p->kb_per_tap = (d->Cin + kBK - 1) / kBK;
+  p->kbk = (d->Cin == 32 && ryolo_knob(RYOLO_KNOB_SW64)) ? 32 : kBK;
+  p->kb_per_tap = (d->Cin + p->kbk - 1) / p->kbk;
   p->ntaps = d->ksize * d->ksize; p->Ktap = d->Cin;
   for (int t = 0; t < p->ntaps; t++) {
     p->tap_dh[t] = (signed char)(t / d->ksize - p->pad);
@@ -766,7 +780,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   // deep-K BN=256 tiles miss; everything else gains, and dgrad's accumulation always does (no read-add-write).
   const bool reducible = knob == 2 && p.residual == (const __nv_bfloat16*)p.out && p.res_cpitch == p.out_cpitch &&
                          !p.scale && !p.shift && p.act == RYOLO_ACT_LINEAR;
-  const bool fits = p.BN <= ryolo_knob(RYOLO_KNOB_EPI_MAXBN) || p.ntaps * p.kb_per_tap * kBK <= 1152 || reducible;
+  const bool fits = p.BN <= ryolo_knob(RYOLO_KNOB_EPI_MAXBN) || p.ntaps * p.kb_per_tap * p.kbk <= 1152 || reducible;
   if (knob && p.mode == RYOLO_OUT_NHWC_BF16 && fits && (p.BN % 64 == 0 || p.n_tiles == 1)) {
     p.epi_tma = 1;
     if (reducible) {
@@ -785,7 +799,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the output operand"); return RYOLO_ERR_CUDA; }
   }
-  size_t stage_bytes = (size_t)kBM * kBK * 2 + (size_t)p.BN * kBK * 2, fixed = 0;
+  size_t stage_bytes = (size_t)kBM * p.kbk * 2 + (size_t)p.BN * p.kbk * 2, fixed = 0;
   if (p.halo) {
     p.a_slots = 3;
     p.a_slot_bytes = (uint32_t)ry_align_up((size_t)(p.TH + 2) * (p.TW + 2) * kBK * 2, 1024);
@@ -852,21 +866,23 @@ int encode_and_launch(const void* x, int N, int H, int W, int C, long long cpitc
   {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * W, (cuuint64_t)cpitch * 2 * W * H};
-    cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(p.halo ? p.TW + 2 : p.TW * estride),
+    cuuint32_t box[4] = {(cuuint32_t)p.kbk, (cuuint32_t)(p.halo ? p.TW + 2 : p.TW * estride),
                          (cuuint32_t)(p.halo ? p.TH + 2 : p.TH * estride), 1};
     cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
     CUresult r = enc(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)x, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, p.kbk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the activation operand"); return RYOLO_ERR_CUDA; }
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)wrows};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {(cuuint32_t)p.kbk, (cuuint32_t)p.BN};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, p.kbk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { ryolo_set_error("cuTensorMapEncodeTiled failed for the weight operand"); return RYOLO_ERR_CUDA; }
   }
@@ -910,7 +926,8 @@ int ryolo_conv2d_dgrad(const void* dy, long long dy_cpitch, int N, int H, int W,
       ConvKernelParams p{};
       p.N = N; p.Ho = Hl; p.Wo = Wl; p.Cout = Cin; p.Cin = Cout; p.Ktap = Cout;
       p.ksize = ksize; p.stride = 1; p.pad = pad;
-      p.kb_per_tap = (Cout + kBK - 1) / kBK;
+      p.kbk = (Cout == 32 && ryolo_knob(RYOLO_KNOB_SW64)) ? 32 : kBK;
+      p.kb_per_tap = (Cout + p.kbk - 1) / p.kbk;
       p.ntaps = 0;
       for (int kh = 0; kh < ksize; kh++) {
         const int vh = ph + pad - kh;

@@ -20,16 +20,18 @@ int ryolo_abi_version(void) { return 1; }
 // (upper case) the first time a knob is read; ryolo_tune overrides them at run time.
 //   halo      conv: 3x3/s1 taps read shifted views of one halo box (0 off | 1 | 2)
 //   dbg       conv timing experiments, results are WRONG: 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads
-//   wg_split  wgrad: 1 = split-K shares proportional to the tap groups' tap counts, 0 = uniform
+//   wg_split  wgrad split-K shares of the tap groups: 1 = by measured cost per patch, 2 = by tap count, 0 = uniform
 //   wg_dbg    wgrad timing experiments, results are WRONG: 1 no MMAs, 2 no X loads
 //   wg_tapgrp wgrad: 1 = one MMA covers as many taps as fit N = 256, 0 = one tap per MMA
-//   wg_trans  wgrad: 1 = layers with Cin <= 128 transpose their TMA boxes in smem and run K-major MMAs, 0 = MN-major
+//   wg_trans  wgrad: 1 = layers with Cin <= 128 transpose their TMA boxes in smem and run K-major MMAs (correct, but
+//             measured slower than the MN-major kernel: its raw ring is only 4 boxes deep), 0 (default) = MN-major
+//   sw64      conv: 1 = Cin == 32 operands use 32-element (64-byte, SWIZZLE_64B) K blocks instead of overhanging 64-element boxes
 //   bn_bwd    BatchNorm backward reduce pass: 1 = low-register variant, 0 = original
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd", "wg_trans"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 1, 1};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 1, 0, 1};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

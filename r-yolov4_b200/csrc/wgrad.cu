@@ -633,21 +633,30 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   const int items = p.n_co_tiles * p.n_ci_tiles * p.n_tap_groups;
   const long long n_patches = (long long)N * p.tiles_h * p.tiles_w;
   RY_CHECK_ARG(n_patches < (1ll << 31), "wgrad: too many patches");
-  // CTAs per (Cout tile, Cin tile) pair, dealt to the tap groups in proportion to their tap counts (greedy: the
-  // group with the most taps per CTA gets the next one).  RYOLO_WG_SPLIT=0 restores the uniform split (A/B switch).
+  // CTAs per (Cout tile, Cin tile) pair are dealt to the tap groups by cost (knob wg_split: 1 cost model, 2 tap counts,
+  // 0 uniform).
   const int prop = ryolo_knob(RYOLO_KNOB_WG_SPLIT);
   const int pairs = p.n_co_tiles * p.n_ci_tiles;
-  int ks[9], gt[9];
+  // Measured cost of one patch for an item of t taps (profiles/r01_wgrad_cost_model.txt): the MMA chain costs ~0.11 us
+  // per MMA whatever its N (8 K steps per group of tap_grp taps), the TMA side ~0.29 us per 16 KB box; an item runs at
+  // the slower of the two.  CTAs go to the item with the highest cost per CTA (greedy), so a one-tap leftover group gets
+  // about a third of an eight-tap group's CTAs, not an eighth.
+  int ks[9];
+  double gw[9];
+  const int a_boxes = Cout > 64 ? 2 : 1;
   for (int g = 0; g < p.n_tap_groups; g++) {
     ks[g] = 1;
-    gt[g] = p.ntaps - g * p.tg < p.tg ? p.ntaps - g * p.tg : p.tg;
+    const int t = p.ntaps - g * p.tg < p.tg ? p.ntaps - g * p.tg : p.tg;
+    const double mma = 8.0 * ((t + p.tap_grp - 1) / p.tap_grp) * 0.11;
+    const double tma = (double)(t * p.nb + a_boxes) * 0.29;
+    gw[g] = prop == 2 ? (double)t : (mma > tma ? mma : tma);
   }
   if (prop) {
     int budget_ctas = sm_count() / pairs;
     for (int used = p.n_tap_groups; used < budget_ctas; used++) {
       int best = 0;
       for (int g = 1; g < p.n_tap_groups; g++)
-        if ((long long)gt[g] * ks[best] > (long long)gt[best] * ks[g]) best = g;
+        if (gw[g] * ks[best] > gw[best] * ks[g]) best = g;
       ks[best]++;
     }
   } else {
