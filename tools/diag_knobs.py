@@ -29,6 +29,7 @@ BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the li
 VARIANTS = [
     ("base", {}),
     ("wg_uniform", dict(wg_split=0)),
+    ("wg_bytaps", dict(wg_split=2)),
     ("wg_tap1", dict(wg_tapgrp=0)),
     ("wg_mn", dict(wg_trans=0)),
     ("wg_mn_uniform", dict(wg_trans=0, wg_split=0)),
