@@ -28,6 +28,7 @@ constexpr int kBM = 128;        // UMMA M (rows of the patch tile, TH*TW <= 128)
 constexpr int kBK = 64;         // bf16 elements per k-block = one 128-byte swizzle row
 constexpr int kThreads = 320;   // 10 warps: TMA, MMA, 2 x 4 epilogue
 constexpr int kMaxStages = 12;
+constexpr int kMaxAcc = 8;
 // fused BatchNorm statistics: fixed-point scales of the cross-CTA accumulators (|sum| < 2^39, sum of squares < 2^43)
 constexpr float kSumScale = 16777216.f;   // 2^24
 constexpr float kSqScale = 1048576.f;     // 2^20
@@ -176,6 +177,7 @@ struct ConvKernelParams {
   int TH, TW, tiles_h, tiles_w, n_tiles;
   int BN, stages;
   uint32_t tmem_cols;
+  int nacc;                        // TMEM accumulators in rotation (2..8, even): hides the MMA <-> epilogue hand-back latency
   int ksize, stride, pad, kb_per_tap;
   int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
   int kbk;                         // K elements per stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
@@ -224,11 +226,12 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + (p.halo ? (uint32_t)p.a_slots * p.a_slot_bytes : (uint32_t)STAGES * kABytes);
   const uint32_t sStage = sB + (uint32_t)STAGES * kBBytes;   // epi_tma: one 128-row x 64-channel bf16 slab per epilogue group
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4 + 8];
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kMaxAcc + 8];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
-                 bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + 2]),
-                 bar_afull = smem_u32(&bars[2 * kMaxStages + 4]), bar_aempty = smem_u32(&bars[2 * kMaxStages + 8]);
+                 bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + kMaxAcc]),
+                 bar_afull = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc]),
+                 bar_aempty = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc + 4]);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.ntaps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
@@ -244,7 +247,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
-    for (int b = 0; b < 2; b++) {
+    for (int b = 0; b < p.nacc; b++) {
       mbar_init(bar_acc_full + 8 * b, 1);
       mbar_init(bar_acc_empty + 8 * b, 4);     // one arrival per epilogue warp
     }
@@ -319,7 +322,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       int s = 0, hslot = 0;
       uint32_t phase = 0, hphase = 0, it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
-        const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+        const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
         mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
@@ -408,7 +411,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
       const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo) && !(p.dbg & 1);
       const long long pix = ((long long)img * p.OutH + ho * p.out_s + p.out_oh) * p.OutW + wo * p.out_s + p.out_ow;
-      const uint32_t buf = it & 1u, aphase = (it >> 1) & 1u;
+      const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;   // nacc is even: tiles of one parity
       mbar_wait(bar_acc_full + 8 * buf, aphase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + buf * (uint32_t)BN + ((uint32_t)(sub * 32) << 16);
@@ -811,8 +814,15 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
   const size_t smem = fixed + (size_t)stages * stage_bytes + slab_bytes + 1024;
+  // Accumulators in rotation: with two, a tile whose main loop is one or two K blocks long (1x1 convs on wide maps) waits
+  // for the commit -> epilogue wake-up -> tcgen05.ld -> arrive -> MMA wake-up round trip (~1 us) every other tile
+  // (ncu: the MMA warp's retries sit on acc_empty, not on the smem ring).  Narrow tiles fit up to 8 in the 512 columns.
+  int nacc = 512 / p.BN;
+  nacc = nacc > kMaxAcc ? kMaxAcc : nacc & ~1;
+  if (nacc < 2 || !ryolo_knob(RYOLO_KNOB_NACC)) nacc = 2;
+  p.nacc = nacc;
   uint32_t cols = 32;
-  while (cols < 2u * (uint32_t)p.BN) cols <<= 1;
+  while (cols < (uint32_t)nacc * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKernelParams);
   KernelFn fn = nullptr;
