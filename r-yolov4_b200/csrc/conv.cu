@@ -93,6 +93,22 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
   asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
   return (uint32_t)v;
 }
+// One lane of a converged warp (the same one every time for the full mask).  Single-thread work (TMA / MMA issue) is
+// written as `warp-uniform loop + if (elect_one())` rather than `if (lane == 0) { loop }`: under a lane test the
+// compiler treats the whole loop as divergent code and wraps every uniform-datapath instruction (UTMALDG, UTCHMMA,
+// UTCBAR) in an elect/branch retry sequence with R2UR copies; ~90 SASS instructions of dependent uniform ALU work per
+// 4 MMAs made the issue thread the bottleneck of every tile narrower than N = 256 (profiles/r01_conv_issue_loop.txt).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -266,8 +282,36 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = tmem_slot;
 
-  if (warp == 0) {
-    // ================================ TMA producer (one lane) ================================
+  if (warp == 0 && !p.halo) {
+    // ================================ TMA producer (warp-uniform loop, one elected lane issues) ===============
+    const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
+    const uint32_t tx_bytes = ((p.dbg & 8) ? 0u : a_bytes) + kBBytes;
+    const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
+    int s = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int nt = t % p.n_tiles;
+      int mt = t / p.n_tiles;
+      const int pw = mt % p.tiles_w; mt /= p.tiles_w;
+      const int ph = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
+      const int hs = ph * p.TH * p.stride, ws = pw * p.TW * p.stride, n0 = nt * BN;
+      int tap = krot / p.kb_per_tap, cb = krot - tap * p.kb_per_tap;       // per-CTA rotation of the K blocks (see below)
+      for (int kb0 = 0; kb0 < KB; kb0++) {
+        mbar_wait(bar_empty + 8 * s, phase ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(bar_full + 8 * s, tx_bytes);
+          if (!(p.dbg & 8))
+            tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * p.kbk, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
+          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1u; }
+        if (++cb == p.kb_per_tap) { cb = 0; if (++tap == p.ntaps) tap = 0; }
+      }
+    }
+  } else if (warp == 0) {
+    // ================================ TMA producer, halo mode (one lane) =====================================
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
       const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
@@ -315,8 +359,44 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
+  } else if (warp == 1 && !p.halo) {
+    // ================================ MMA issuer (warp-uniform loop, one elected lane issues) =================
+    const uint32_t idesc = umma_idesc_bf16(BN);
+    const bool sw64 = p.kbk == 32;
+    // descriptors differ between stages only in their 14-bit start-address field (bytes >> 4, no carry out of it)
+    const uint64_t adesc0 = sw64 ? umma_desc_k_sw64(sA) : umma_desc_k_sw128(sA);
+    const uint64_t bdesc0 = sw64 ? umma_desc_k_sw64(sB) : umma_desc_k_sw128(sB);
+    const uint32_t a_step = kABytes >> 4, b_step = kBBytes >> 4;
+    const int ksteps = p.kbk >> 4;
+    int s = 0;
+    uint32_t phase = 0, it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+      const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
+      mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
+      for (int kb = 0; kb < KB; kb++) {
+        mbar_wait(bar_full + 8 * s, phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * a_step), bd = bdesc0 + (uint64_t)((uint32_t)s * b_step);
+          if (!(p.dbg & 4)) {
+            umma_bf16(d_tmem, ad, bd, idesc, kb ? 1u : 0u);
+            umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+            if (ksteps == 4) {
+              umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+              umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+            }
+          }
+          umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
+          if (kb == KB - 1) umma_commit(bar_acc_full + 8 * buf);  // accumulator complete
+        }
+        __syncwarp();
+        if (++s == STAGES) { s = 0; phase ^= 1u; }
+      }
+    }
   } else if (warp == 1) {
-    // ================================ MMA issuer (one lane) ==================================
+    // ================================ MMA issuer, halo mode (one lane) =======================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(BN);
       int s = 0, hslot = 0;

@@ -58,6 +58,18 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// one lane of a converged warp (see csrc/conv.cu: single-thread issue loops are written warp-uniform + elect)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -217,65 +229,77 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const bool has_work = split < n_patches;
 
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0, ab = 0;
-      uint32_t bphase = 0, aphase = 0;
-      for (int patch = split; patch < n_patches; patch += ksplit) {
-        const int pw = patch % p.tiles_w;
-        const int ph = (patch / p.tiles_w) % p.tiles_h;
-        const int img = patch / (p.tiles_w * p.tiles_h);
-        const int h0 = ph * p.TH, w0 = pw * p.TW;
-        const uint32_t a_dst = sA + (uint32_t)(ab * p.a_boxes) * kBoxBytes;
-        mbar_wait(bar_aempty + 8 * ab, aphase ^ 1u);
+    // TMA producer: warp-uniform loop, one elected lane issues
+    int s = 0, ab = 0;
+    uint32_t bphase = 0, aphase = 0;
+    const uint32_t b_tx = (p.dbg & 2) ? 0u : (uint32_t)p.nb * box_bytes;
+    for (int patch = split; patch < n_patches; patch += ksplit) {
+      const int pw = patch % p.tiles_w;
+      const int ph = (patch / p.tiles_w) % p.tiles_h;
+      const int img = patch / (p.tiles_w * p.tiles_h);
+      const int h0 = ph * p.TH, w0 = pw * p.TW;
+      const uint32_t a_dst = sA + (uint32_t)(ab * p.a_boxes) * kBoxBytes;
+      mbar_wait(bar_aempty + 8 * ab, aphase ^ 1u);
+      if (elect_one()) {
         mbar_expect_tx(bar_afull + 8 * ab, a_two ? 2 * box_bytes : box_bytes);
         tma_load_4d(a_dst, &tmG, bar_afull + 8 * ab, co0, w0, h0, img);
         if (a_two) tma_load_4d(a_dst + kBoxBytes, &tmG, bar_afull + 8 * ab, co0 + 64, w0, h0, img);
-        for (int ti = 0; ti < ntap; ti++) {
-          const int tap = tap0 + ti;
-          const int kh = tap / p.ksize, kw = tap - kh * p.ksize;
-          mbar_wait(bar_bempty + 8 * s, bphase ^ 1u);
-          mbar_expect_tx(bar_bfull + 8 * s, (p.dbg & 2) ? 0u : (uint32_t)p.nb * box_bytes);
-          for (int j = 0; j < ((p.dbg & 2) ? 0 : p.nb); j++)
-            tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + 64 * j,
-                        w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
-          if (++s == b_stages) { s = 0; bphase ^= 1u; }
-        }
-        if (++ab == a_slots) { ab = 0; aphase ^= 1u; }
       }
+      __syncwarp();
+      int kh = tap0 / p.ksize, kw = tap0 - kh * p.ksize;
+      for (int ti = 0; ti < ntap; ti++) {
+        mbar_wait(bar_bempty + 8 * s, bphase ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(bar_bfull + 8 * s, b_tx);
+          if (!(p.dbg & 2)) {
+            for (int j = 0; j < p.nb; j++)
+              tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + 64 * j,
+                          w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
+          }
+        }
+        __syncwarp();
+        if (++s == b_stages) { s = 0; bphase ^= 1u; }
+        if (++kw == p.ksize) { kw = 0; kh++; }
+      }
+      if (++ab == a_slots) { ab = 0; aphase ^= 1u; }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const int ksteps = (rows + 15) / 16;
-      int s = 0, ab = 0;
-      uint32_t bphase = 0, aphase = 0, pit = 0;
-      for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
-        mbar_wait(bar_afull + 8 * ab, aphase);
+    // MMA issuer: warp-uniform loop, one elected lane issues.  Descriptors of the K steps differ only in the 14-bit
+    // start-address field (bytes >> 4): one 64-bit add per MMA instead of rebuilding them.
+    const int ksteps = (p.dbg & 1) ? 0 : (rows + 15) / 16;
+    int s = 0, ab = 0;
+    uint32_t bphase = 0, aphase = 0, pit = 0;
+    for (int patch = split; patch < n_patches; patch += ksplit, pit++) {
+      mbar_wait(bar_afull + 8 * ab, aphase);
+      tc_fence_after();
+      const uint32_t a0 = sA + (uint32_t)(ab * p.a_boxes) * kBoxBytes;
+      const uint32_t a_lbo = p.a_boxes == 2 ? kBoxBytes : sZ - a0;      // upper 64 channels: next box, or the zero box
+      const uint64_t adesc = umma_desc_mn_sw128(a0, a_lbo);
+      // Narrow Cin tiles are issued several taps at a time: consecutive ring slots are consecutive 64-channel N atoms
+      // (LBO = one box) and the taps' accumulators are consecutive TMEM columns, so ONE N = g*CIT MMA covers g taps.
+      for (int ti = 0; ti < ntap;) {
+        int g = min(p.tap_grp, ntap - ti);
+        g = min(g, b_stages - s);                              // a group never wraps around the ring
+        for (int i = 0; i < g; i++) mbar_wait(bar_bfull + 8 * (s + i), bphase);
         tc_fence_after();
-        const uint32_t a0 = sA + (uint32_t)(ab * p.a_boxes) * kBoxBytes;
-        const uint32_t a_lbo = p.a_boxes == 2 ? kBoxBytes : sZ - a0;      // upper 64 channels: next box, or the zero box
-        // An M=128 MMA spends >= 128 cycles fetching its A operand from smem whatever N is, so narrow Cin tiles are
-        // issued several taps at a time: consecutive ring slots are consecutive 64-channel N atoms (LBO = one box)
-        // and the taps' accumulators are consecutive TMEM columns, so ONE N = g*CIT MMA covers g taps.
-        for (int ti = 0; ti < ntap;) {
-          int g = min(p.tap_grp, ntap - ti);
-          g = min(g, b_stages - s);                              // a group never wraps around the ring
-          for (int i = 0; i < g; i++) mbar_wait(bar_bfull + 8 * (s + i), bphase);
-          tc_fence_after();
-          const uint32_t b0 = sB + (uint32_t)(s * p.nb) * kBoxBytes;
+        if (elect_one()) {
+          const uint64_t bdesc = umma_desc_mn_sw128(sB + (uint32_t)(s * p.nb) * kBoxBytes, kBoxBytes);
           const uint32_t idesc_g = umma_idesc_bf16_mn(g * CIT);
-          for (int kk = 0; kk < ((p.dbg & 1) ? 0 : ksteps); kk++) {
-            umma_bf16(tmem_base + (uint32_t)(ti * CIT), umma_desc_mn_sw128(a0 + kk * 2048, a_lbo),
-                      umma_desc_mn_sw128(b0 + kk * 2048, kBoxBytes), idesc_g, (pit | (uint32_t)kk) ? 1u : 0u);
-          }
+          const uint32_t d = tmem_base + (uint32_t)(ti * CIT);
+          for (int kk = 0; kk < ksteps; kk++)                  // one K step = 16 pixel rows = 2048 bytes = 128 units
+            umma_bf16(d, adesc + (uint64_t)(kk * 128), bdesc + (uint64_t)(kk * 128), idesc_g, (pit | (uint32_t)kk) ? 1u : 0u);
           for (int i = 0; i < g; i++) umma_commit(bar_bempty + 8 * (s + i));
-          ti += g;
-          s += g;
-          if (s == b_stages) { s = 0; bphase ^= 1u; }
+          if (ti + g == ntap) {
+            umma_commit(bar_aempty + 8 * ab);
+            if (patch + ksplit >= n_patches) umma_commit(bar_acc);
+          }
         }
-        umma_commit(bar_aempty + 8 * ab);
-        if (++ab == a_slots) { ab = 0; aphase ^= 1u; }
+        __syncwarp();
+        ti += g;
+        s += g;
+        if (s == b_stages) { s = 0; bphase ^= 1u; }
       }
-      umma_commit(bar_acc);
+      if (++ab == a_slots) { ab = 0; aphase ^= 1u; }
     }
   } else if (has_work) {
     // dw is K-major like the packed forward weights: [Cout][tap][Cin] (stem: [Cout][Kpad]).  A lane owns one Cout row
