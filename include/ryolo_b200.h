@@ -22,7 +22,7 @@ const char* ryolo_last_error(void);
 void ryolo_set_error(const char* msg);
 int ryolo_check_device(int device); /* 0 only on a compute-capability 10.x device */
 /* Process-wide tuning / timing-experiment switch (no reference counterpart).  Keys: "halo", "dbg", "wg_split",
- * "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc" (see csrc/lib.cu); defaults come from the environment
+ * "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl" (see csrc/lib.cu); defaults come from the environment
  * variable RYOLO_<KEY>. */
 int ryolo_tune(const char* key, int value);
 int ryolo_knob(int id);

@@ -58,6 +58,7 @@ bn_act_bwd_reduce_kernel(__nv_bfloat16* __restrict__ dout, long long dp, const _
                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
                          float* __restrict__ sums) {
+  ry_pdl_wait();
   extern __shared__ float red[];   // [rows][C] x 2
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
@@ -136,6 +137,7 @@ bn_act_bwd_reduce2_kernel(__nv_bfloat16* __restrict__ dout, long long dp, const 
                           long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
                           float* __restrict__ sums) {
+  ry_pdl_wait();
   extern __shared__ float red[];   // [rows][C] x 2
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
@@ -205,6 +207,7 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, co
                         const float* __restrict__ invstd, const float* __restrict__ sums, long long P, int C,
                         __nv_bfloat16* __restrict__ draw, long long op, float* __restrict__ dgamma,
                         float* __restrict__ dbeta) {
+  ry_pdl_wait();
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -501,10 +504,11 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
   const bool lean = ryolo_knob(RYOLO_KNOB_BN_BWD) != 0 && threads == 256;
 #define RY_BWD(ACT)                                                                                                  \
   if (lean)                                                                                                          \
-    bn_act_bwd_reduce2_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C,    \
-                                                                 sums);                                              \
+    ry_launch(bn_act_bwd_reduce2_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, d, dp, r, rp, scale, shift, mean,   \
+              invstd, P, C, sums);                                                                                   \
   else                                                                                                               \
-    bn_act_bwd_reduce_kernel<ACT><<<blocks, threads, smem, st>>>(d, dp, r, rp, scale, shift, mean, invstd, P, C, sums);
+    ry_launch(bn_act_bwd_reduce_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, d, dp, r, rp, scale, shift, mean,    \
+              invstd, P, C, sums);
   switch (act) {
     case RYOLO_ACT_LEAKY: RY_BWD(RYOLO_ACT_LEAKY) break;
     case RYOLO_ACT_MISH: RY_BWD(RYOLO_ACT_MISH) break;
@@ -512,8 +516,8 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
     default: RY_BWD(RYOLO_ACT_LINEAR) break;
   }
 #undef RY_BWD
-  bn_act_bwd_apply_kernel<<<blocks * 2, threads, 0, st>>>(d, dp, r, rp, scale, mean, invstd, sums, P, C, o, op, dgamma,
-                                                          dbeta);
+  ry_launch(bn_act_bwd_apply_kernel, dim3(blocks * 2), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp, scale,
+            mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -12,7 +12,7 @@ extern "C" void ryolo_set_error(const char* msg);
 
 // process-wide tuning knobs (lib.cu); ids index ryolo_tune's keys
 enum { RYOLO_KNOB_HALO = 0, RYOLO_KNOB_DBG, RYOLO_KNOB_WG_SPLIT, RYOLO_KNOB_WG_DBG, RYOLO_KNOB_EPI_TMA,
-       RYOLO_KNOB_EPI_MAXBN, RYOLO_KNOB_WG_TAPGRP, RYOLO_KNOB_BN_BWD, RYOLO_KNOB_WG_TRANS, RYOLO_KNOB_SW64, RYOLO_KNOB_NACC, RYOLO_KNOB_COUNT };
+       RYOLO_KNOB_EPI_MAXBN, RYOLO_KNOB_WG_TAPGRP, RYOLO_KNOB_BN_BWD, RYOLO_KNOB_WG_TRANS, RYOLO_KNOB_SW64, RYOLO_KNOB_NACC, RYOLO_KNOB_PDL, RYOLO_KNOB_COUNT };
 extern "C" int ryolo_knob(int id);
 
 #define RY_CHECK_ARG(cond, msg)   \
@@ -31,6 +31,31 @@ extern "C" int ryolo_knob(int id);
       return RYOLO_ERR_CUDA;                         \
     }                                                \
   } while (0)
+
+// Programmatic dependent launch: with the attribute set, a kernel may be scheduled while the previous kernel of its
+// stream is still draining (as soon as every CTA of that kernel has executed griddepcontrol.launch_dependents or
+// exited); it runs its prologue (barrier init, TMEM allocation, descriptor prefetch) and must execute
+// griddepcontrol.wait before it reads or writes global memory.  Both instructions are no-ops in a normal launch.
+#ifdef __CUDACC__
+__device__ __forceinline__ void ry_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void ry_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ry_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                    Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ryolo_knob(RYOLO_KNOB_PDL) ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
 
 static inline size_t ry_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -277,9 +277,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     tmem_alloc(smem_u32(&tmem_slot), p.tmem_cols);
     tmem_relinquish();
   }
+  if (threadIdx.x == 0) ry_pdl_trigger();       // every CTA is resident from the start: the next kernel may queue up now
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  ry_pdl_wait();                                // nothing above touches global memory
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0 && !p.halo) {
@@ -930,7 +932,8 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   int grid = sm_count();
   grid -= grid % p.n_tiles;                          // a CTA always sees the same n-tile
   if (tiles < grid) grid = (int)tiles;               // tiles is a multiple of n_tiles, so this keeps the property
-  fn<<<grid, kThreads, smem, st>>>(tmA, tmB, tmO, p);
+  cudaError_t le = ry_launch(fn, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, tmO, p);
+  if (le != cudaSuccess) { ryolo_set_error(cudaGetErrorString(le)); return RYOLO_ERR_CUDA; }
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -110,6 +110,7 @@ scale_shift_act_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const 
                        const float* __restrict__ scale2, const float* __restrict__ shift2,
                        const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
                        long long P, int C) {
+  ry_pdl_wait();
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -430,9 +431,8 @@ int ryolo_scale_shift_act(const void* x, long long xp, const float* scale, const
   const int rows = threads / groups;
   long long want = (P + (long long)rows * 4 - 1) / ((long long)rows * 4);
   const int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
-  fn<<<blocks, threads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, xp, scale, shift, (const __nv_bfloat16*)x2,
-                                                   x2p, scale2, shift2, (const __nv_bfloat16*)residual, rp,
-                                                   (__nv_bfloat16*)y, yp, P, C);
+  ry_launch(fn, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, xp, scale, shift,
+            (const __nv_bfloat16*)x2, x2p, scale2, shift2, (const __nv_bfloat16*)residual, rp, (__nv_bfloat16*)y, yp, P, C);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

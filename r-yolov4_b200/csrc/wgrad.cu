@@ -222,9 +222,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     }
     fence_proxy_async();
   }
+  if (threadIdx.x == 0) ry_pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  ry_pdl_wait();                                // nothing above touches global memory
   const uint32_t tmem_base = tmem_slot;
   const bool has_work = split < n_patches;
 
@@ -433,9 +435,11 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
     }
     fence_proxy_async();
   }
+  if (threadIdx.x == 0) ry_pdl_trigger();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  ry_pdl_wait();                                // nothing above touches global memory
   const uint32_t tmem_base = tmem_slot;
 
   if (warp == 0) {
@@ -714,9 +718,9 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
     configured = true;
   }
   if (ryolo_knob(RYOLO_KNOB_WG_TRANS) && p.nb <= 2)
-    conv_wgrad_t_kernel<<<pairs * p.ks_total, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
+    ry_launch(conv_wgrad_t_kernel, dim3(pairs * p.ks_total), dim3(kThreads), smem, (cudaStream_t)stream, tmG, tmX, p);
   else
-    conv_wgrad_kernel<<<pairs * p.ks_total, kThreads, smem, (cudaStream_t)stream>>>(tmG, tmX, p);
+    ry_launch(conv_wgrad_kernel, dim3(pairs * p.ks_total), dim3(kThreads), smem, (cudaStream_t)stream, tmG, tmX, p);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

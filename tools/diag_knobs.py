@@ -24,7 +24,7 @@ step = R.TrainStep(m, crit)
 img = torch.rand(bs, 3, S, S, device="cuda")
 tg = make_targets(0, bs, 2).cuda()
 flat0 = step.flat.clone()
-KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc"]
+KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl"]
 BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the library's defaults
 VARIANTS = [
     ("base", {}),
@@ -38,6 +38,7 @@ VARIANTS = [
     ("bn_old", dict(bn_bwd=0)),
     ("sw128", dict(sw64=0)),
     ("acc2", dict(nacc=0)),
+    ("nopdl", dict(pdl=0)),
     ("epi_direct", dict(epi_tma=0)),
     ("epi_tma1", dict(epi_tma=1)),
     ("epi_bn64", dict(epi_maxbn=64)),
