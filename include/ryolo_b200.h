@@ -177,7 +177,8 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, int k, int stride, 
 int ryolo_pack_weights(const float* w, int Cout, int Cin, int k, int stem, void* out, void* stream);
 /* all conv weights of a model in one launch.  table (DEVICE array, sorted by `first`): tensor i holds flat
  * elements [first, first + Cout*Cin*k*k) of the launch; dst = layout 0 (or the stem's [Cout][Kpad], padding
- * pre-zeroed by the caller), dst_t = layout 2 or NULL.                                                         */
+ * pre-zeroed by the caller), dst_t = layout 2 or NULL.  Every tensor's element count (hence every `first`) must be
+ * a multiple of 8: a thread packs 8 elements into one 16-byte piece of each layout.                             */
 typedef struct ryolo_pack_entry {
   const float* src; void* dst; void* dst_t;
   long long first;

@@ -326,30 +326,82 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, int Cout, int C
   }
 }
 
-// All conv weights of a model in ONE launch: table[i] describes tensor i; thread t handles flat element t.
+// All conv weights of a model in ONE launch: table[i] describes tensor i.  Thread t owns elements [8t, 8t+8) of the
+// launch's flat element space (every tensor's element count is a multiple of 8) and writes ONE 16-byte piece of each
+// destination layout: 8 consecutive Cin of dst[co][tap][.] and 8 consecutive Cout of dst_t[ci][tap][.].  Lanes step
+// through (tap, ci) fastest, so a warp's strided fp32 reads cover whole sectors between them.
+__device__ __forceinline__ uint4 pack8_bf16(const float (&f)[8]) {
+  uint4 v;
+  __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) b[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return v;
+}
+
 __global__ void __launch_bounds__(256)
 pack_weights_multi_kernel(const ryolo_pack_entry* __restrict__ table, int n, long long total) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const long long chunks = total >> 3;
+  for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < chunks;
+       t += (long long)gridDim.x * blockDim.x) {
+    const long long i = t << 3;
     int lo = 0, hi = n - 1;                       // last entry whose first element <= i
     while (lo < hi) {
       const int mid = (lo + hi + 1) >> 1;
       if (table[mid].first <= i) lo = mid; else hi = mid - 1;
     }
     const ryolo_pack_entry e = table[lo];
-    const long long r = i - e.first;              // OIHW index: ((co*Cin + ci)*k*k + tap)
+    const long long r0 = i - e.first;             // first of this thread's 8 elements (OIHW order for the fallback)
     const int kk = e.k * e.k;
-    const int tap = (int)(r % kk);
-    const int ci = (int)((r / kk) % e.Cin);
-    const int co = (int)(r / ((long long)kk * e.Cin));
-    const __nv_bfloat16 v = __float2bfloat16_rn(e.src[r]);
     __nv_bfloat16* dst = (__nv_bfloat16*)e.dst;
     __nv_bfloat16* dst_t = (__nv_bfloat16*)e.dst_t;
-    if (e.stem) {
-      dst[(long long)co * e.stem + tap * 3 + ci] = v;                   // [Cout][Kpad] im2col order (pad pre-zeroed)
-    } else {
-      dst[((long long)co * kk + tap) * e.Cin + ci] = v;                 // [Cout][kh][kw][Cin]
-      if (dst_t) dst_t[((long long)ci * kk + tap) * e.Cout + co] = v;   // [Cin][kh][kw][Cout]
+    if (e.stem || (e.Cin & 7)) {                  // 3-channel stem: element-wise into the im2col order
+      for (int j = 0; j < 8; j++) {
+        const long long r = r0 + j;               // OIHW index: ((co*Cin + ci)*k*k + tap)
+        const int tap = (int)(r % kk);
+        const int ci = (int)((r / kk) % e.Cin);
+        const int co = (int)(r / ((long long)kk * e.Cin));
+        const __nv_bfloat16 v = __float2bfloat16_rn(e.src[r]);
+        if (e.stem) dst[(long long)co * e.stem + tap * 3 + ci] = v;       // [Cout][Kpad] (pad pre-zeroed)
+        else {
+          dst[((long long)co * kk + tap) * e.Cin + ci] = v;
+          if (dst_t) dst_t[((long long)ci * kk + tap) * e.Cout + co] = v;
+        }
+      }
+      continue;
+    }
+    const long long q0 = r0 >> 3;                 // chunk index inside the tensor
+    float f[8];
+    {   // dst = [Cout][kh][kw][Cin]: chunk -> (co, ci chunk, tap), tap fastest
+      long long q = q0;
+      const int tap = (int)(q % kk); q /= kk;
+      const int cch = e.Cin >> 3;
+      const int cc = (int)(q % cch);
+      const int co = (int)(q / cch);
+      const float* sp = e.src + ((long long)co * e.Cin + 8 * cc) * kk + tap;
+#pragma unroll
+      for (int j = 0; j < 8; j++) f[j] = sp[(long long)j * kk];
+      *reinterpret_cast<uint4*>(dst + ((long long)co * kk + tap) * e.Cin + 8 * cc) = pack8_bf16(f);
+    }
+    if (dst_t) {
+      if ((e.Cout & 7) == 0) {   // dst_t = [Cin][kh][kw][Cout]: chunk -> (co chunk, ci, tap), tap fastest
+        long long q = q0;
+        const int tap = (int)(q % kk); q /= kk;
+        const int ci = (int)(q % e.Cin);
+        const int coc = (int)(q / e.Cin);
+        const float* sp = e.src + ((long long)(8 * coc) * e.Cin + ci) * kk + tap;
+        const long long cs = (long long)e.Cin * kk;
+#pragma unroll
+        for (int j = 0; j < 8; j++) f[j] = sp[j * cs];
+        *reinterpret_cast<uint4*>(dst_t + ((long long)ci * kk + tap) * e.Cout + 8 * coc) = pack8_bf16(f);
+      } else {
+        for (int j = 0; j < 8; j++) {
+          const long long r = r0 + j;
+          const int tap = (int)(r % kk);
+          const int ci = (int)((r / kk) % e.Cin);
+          const int co = (int)(r / ((long long)kk * e.Cin));
+          dst_t[((long long)ci * kk + tap) * e.Cout + co] = __float2bfloat16_rn(e.src[r]);
+        }
+      }
     }
   }
 }
@@ -477,8 +529,8 @@ int ryolo_stem_im2col(const float* img, int N, int H, int W, int k, int stride, 
 }
 
 int ryolo_pack_weights_multi(const ryolo_pack_entry* table_dev, int n, long long total, void* stream) {
-  RY_CHECK_ARG(n > 0 && total > 0, "pack_weights_multi: empty table");
-  pack_weights_multi_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(table_dev, n, total);
+  RY_CHECK_ARG(n > 0 && total > 0 && (total & 7) == 0, "pack_weights_multi: empty table or element count not a multiple of 8");
+  pack_weights_multi_kernel<<<grid_for(total >> 3, 256), 256, 0, (cudaStream_t)stream>>>(table_dev, n, total);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

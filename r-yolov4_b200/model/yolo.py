@@ -134,6 +134,7 @@ class Yolo(nn.Module):
                     pkt.w = torch.empty((Cin, k * k * Cout), dtype=torch.bfloat16, device=dev)
                     pkt.pinned = True
                     dt = pkt.w.data_ptr()
+                assert w.numel() % 8 == 0, "ryolo_pack_weights_multi packs 8 elements per thread"
                 ents.append((w, pk.w.data_ptr(), dt, first, Cout, Cin, k, ops_.stem_kpad(k) if stem else 0))
                 first += w.numel()
         self._pack_params = [e[0] for e in ents]

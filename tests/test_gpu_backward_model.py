@@ -212,3 +212,32 @@ def test_gradient_accumulation_and_schedule():
     sch.accumulate_probe = [sch.batch(0, b)[1:] for b in (998, 999, 1000, 1001)]
     assert [int(a) for a, _ in sch.accumulate_probe] == [2, 2, 2, 2]
     assert [s for _, s in sch.accumulate_probe] == [False, True, False, True]
+
+
+@pytest.mark.parametrize("ver", ["yolov4", "yolov7", "yolov5"])
+def test_fused_weight_pack_matches_per_layer_pack(ver):
+    """ryolo_pack_weights_multi (one launch, 16-byte pieces) == ryolo_pack_weights per tensor and layout."""
+    import ryolo_b200 as R
+    from ryolo_b200 import ops
+    from ryolo_b200.model.blocks import Conv, RepConv
+    torch.manual_seed(1)
+    m = R.Yolo(16 if ver == "yolov7" else 2, CFG, "csl", ver).cuda()
+    for p in m.parameters():
+        torch.nn.init.normal_(p.data, 0.0, 0.5)
+    m.flatten_parameters()
+    m.enable_fused_pack()
+    torch.cuda.synchronize()
+    checked = 0
+    for mod in m.modules():
+        todo = []
+        if isinstance(mod, Conv):
+            todo.append((mod.conv[0].weight, mod._packed, None if (mod.stem or not mod.has_bn) else mod._packed_t, mod.stem))
+        elif isinstance(mod, RepConv):
+            todo.append((mod.rbr_dense[0].weight, mod._pd, mod._pdt, False))
+            todo.append((mod.rbr_1x1[0].weight, mod._p1, mod._p1t, False))
+        for w, pk, pkt, stem in todo:
+            assert torch.equal(pk.w.view(-1), ops.pack_weights(w.data, stem=stem).view(-1)), (tuple(w.shape), "fwd")
+            if pkt is not None:
+                assert torch.equal(pkt.w.view(-1), ops.pack_weights(w.data, transpose=True).view(-1)), (tuple(w.shape), "t")
+            checked += 1
+    assert checked > 80
