@@ -295,6 +295,13 @@ def run_gpu(args):
         tflops = gflop / tc_total                                         # GFLOP / ms == TFLOP/s
         peak = pk["bf16_tflops_sustained"]
         wg_gflop = wl["fwd_gflop"] * BS
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "r01_conv_traffic.json")      # made by tools/conv_traffic.py from an ncu pass
+        if wl["ver"] == "yolov4" and os.path.exists(tp):
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], \
+                f"profiles/r01_conv_traffic.json: mean DRAM bytes over {tj['launches']} launches (one step, cold cache); " \
+                f"algorithmic {tj['algorithmic_bytes_per_launch']:.3g} B/launch"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -314,7 +321,7 @@ def run_gpu(args):
             "clocks": clocks,
             "roofline": {"kernel": "conv_fwd_kernel (tcgen05 implicit GEMM: forward + dgrad launches)",
                          "bound": "tensor", "achieved": tflops, "peak": peak, "unit": "TFLOP/s",
-                         "frac": tflops / peak, "traffic": None,
+                         "frac": tflops / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": f"{pk_src} bf16_tflops_sustained",
                          "ms_per_step": {k: round(v, 3) for k, v in tc_ms.items()},
                          "algorithmic_gflop_per_step": gflop,

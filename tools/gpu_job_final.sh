@@ -20,6 +20,10 @@ echo "== ncu launch list of the bench command"; date
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 2200 -c 760 --csv --log-file $O/launches_bench.csv \
    python bench.py --steps 2 --warmup 3 --no-cpu > $O/ncu_list.log 2>&1
 tail -2 $O/ncu_list.log | cut -c1-300
+echo "== ncu dram bytes of every conv_fwd_kernel launch of one step"; date
+timeout 420 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none -k regex:conv_fwd_kernel -s 480 -c 240 --csv --log-file $O/conv_dram.csv \
+   python tools/train_layers.py 32 > $O/ncu_dram.log 2>&1
+tail -1 $O/ncu_dram.log | cut -c1-200
 echo "== ncu full: conv fwd layers 17-24 (bs=32)"; date
 timeout 420 ncu --set full --clock-control none -k regex:conv_fwd_kernel -s 237 -c 8 -o $O/conv_final python tools/conv_layers.py 32 yolov4 1 > $O/ncu_conv.log 2>&1
 echo "== ncu full: wgrad (bs=32) mid + last"; date
