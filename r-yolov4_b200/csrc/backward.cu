@@ -396,8 +396,9 @@ upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dyp, int N
 }
 
 // glev fp32 [B, na, H, W, ch] -> out bf16 [B, H, W, Cpad] (channel c = a*ch + k, zero for c >= na*ch), multiplied by
-// mul[c] when given (ImplicitM); dbias[c] += sum over pixels of the packed value.  One warp per pixel.
-template <int kMaxPerLane>
+// mul[c] when given (ImplicitM); dbias[c] += sum over pixels of the packed value.  A thread owns 8 consecutive output
+// channels (one 16-byte store per pixel) and walks pixels with a block-wide stride, like the other HBM-bound kernels;
+// its 8 source offsets and bias partials stay in registers.
 __global__ void __launch_bounds__(256)
 head_grad_pack_kernel(const float* __restrict__ glev, int B, int na, int H, int W, int ch, int Cpad,
                       const float* __restrict__ mul, __nv_bfloat16* __restrict__ out, float* __restrict__ dbias) {
@@ -405,41 +406,36 @@ head_grad_pack_kernel(const float* __restrict__ glev, int B, int na, int H, int 
   const int C = na * ch;
   for (int c = threadIdx.x; c < Cpad; c += blockDim.x) sb[c] = 0.f;
   __syncthreads();
-  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const int chunks = Cpad >> 3;
+  const int rows = blockDim.x / chunks;
+  const int g = threadIdx.x % chunks, r = threadIdx.x / chunks;
   const long long npix = (long long)B * H * W;
-  // lane owns channels lane, lane+32, ... (<= 32 of them: Cpad <= 1024): their source offsets are fixed per lane, and the
-  // bias partials live in registers across the warp's pixels (one smem atomic per channel per warp, not per element)
-  int off[kMaxPerLane];
-  float m[kMaxPerLane], acc[kMaxPerLane];
   const long long plane = (long long)H * W * ch;
+  if (r < rows) {
+    long long off[8];
+    float m[8], acc[8];
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; i++) {
-    const int c = lane + 32 * i;
-    const int a = c < C ? c / ch : 0, k = c < C ? c - a * ch : 0;
-    off[i] = (int)((long long)a * plane + k);
-    m[i] = (mul && c < C) ? mul[c] : 1.f;
-    acc[i] = 0.f;
-  }
-  for (long long pix = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); pix < npix; pix += (long long)gridDim.x * wpb) {
-    const int w = (int)(pix % W), h = (int)((pix / W) % H), b = (int)(pix / ((long long)W * H));
-    const float* src = glev + (long long)b * na * plane + ((long long)h * W + w) * ch;
-#pragma unroll
-    for (int i = 0; i < kMaxPerLane; i++) {
-      const int c = lane + 32 * i;
-      if (c < Cpad) {
-        float v = 0.f;
-        if (c < C) {
-          v = src[off[i]] * m[i];
-          acc[i] += v;
-        }
-        out[pix * Cpad + c] = __float2bfloat16_rn(v);
-      }
+    for (int j = 0; j < 8; j++) {
+      const int c = 8 * g + j;
+      const int a = c < C ? c / ch : 0, k = c < C ? c - a * ch : 0;
+      off[j] = c < C ? (long long)a * plane + k : -1;
+      m[j] = (mul && c < C) ? mul[c] : 1.f;
+      acc[j] = 0.f;
     }
-  }
+    const long long hw = (long long)H * W;
+    for (long long pix = (long long)blockIdx.x * rows + r; pix < npix; pix += (long long)gridDim.x * rows) {
+      const long long b = pix / hw, p = pix - b * hw;
+      const float* src = glev + b * na * plane + p * ch;
+      float v[8];
 #pragma unroll
-  for (int i = 0; i < kMaxPerLane; i++) {
-    const int c = lane + 32 * i;
-    if (c < C) atomicAdd(&sb[c], acc[i]);
+      for (int j = 0; j < 8; j++) v[j] = off[j] >= 0 ? __ldg(src + off[j]) * m[j] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] += v[j];
+      *reinterpret_cast<uint4*>(out + pix * Cpad + 8 * g) = pack8(v);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      if (off[j] >= 0) atomicAdd(&sb[8 * g + j], acc[j]);
   }
   __syncthreads();
   if (dbias)
@@ -605,20 +601,15 @@ int ryolo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 
 int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch, int Cpad, const float* mul, void* out,
                          float* dbias, void* stream) {
-  RY_CHECK_ARG(Cpad % 8 == 0 && Cpad >= na * ch && Cpad <= 1024, "head_grad_pack: bad padded channel count");
-  RY_CHECK_ARG((long long)na * H * W * ch < (1ll << 31), "head_grad_pack: level too large for 32-bit offsets");
+  RY_CHECK_ARG(Cpad % 8 == 0 && Cpad >= na * ch && Cpad <= 2048, "head_grad_pack: bad padded channel count");
+  RY_CHECK_ARG((((uintptr_t)out) & 15) == 0, "head_grad_pack: output must be 16-byte aligned");
   const long long npix = (long long)B * H * W;
   if (npix == 0) return RYOLO_OK;
-  const int blocks = (int)(npix / 8 + 1 > 148 * 4 ? 148 * 4 : npix / 8 + 1);
-  if (Cpad <= 384)
-    head_grad_pack_kernel<12><<<blocks, 256, (size_t)Cpad * sizeof(float), (cudaStream_t)stream>>>(
-        glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias);
-  else if (Cpad <= 640)
-    head_grad_pack_kernel<20><<<blocks, 256, (size_t)Cpad * sizeof(float), (cudaStream_t)stream>>>(
-        glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias);
-  else
-    head_grad_pack_kernel<32><<<blocks, 256, (size_t)Cpad * sizeof(float), (cudaStream_t)stream>>>(
-        glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias);
+  const int rows = 256 / (Cpad / 8);
+  long long want = (npix + 4ll * rows - 1) / (4ll * rows);
+  const int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
+  head_grad_pack_kernel<<<blocks, 256, (size_t)Cpad * sizeof(float), (cudaStream_t)stream>>>(
+      glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }
