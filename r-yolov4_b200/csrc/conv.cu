@@ -7,13 +7,15 @@
 //                  is a single 4-D TMA box of the NHWC input at coordinates shifted by (kh-pad, kw-pad):
 //                  zero padding falls out of TMA's out-of-bounds fill, stride-2 convs use the tensor map's
 //                  element strides.  No im2col buffer ever exists.
-//   operands       bf16, K-major, 128-byte swizzle (TMA writes it, the UMMA descriptor reads it)
-//   pipeline       persistent CTAs (one per SM); warp 0: TMA producer | warp 1: TMEM alloc + single-thread MMA
-//                  issue into two alternating TMEM accumulators | warps 2-5 / 6-9: two epilogue groups, one per
-//                  accumulator (tcgen05.ld -> scale/shift/activation/residual/BN statistics -> global) overlapping
-//                  the following tiles' main loops; mbarrier smem ring
-//   epilogue       mode 0: bf16 NHWC into a channel slice of a (concat) buffer; per-channel scale/shift =
-//                  folded BatchNorm (eval) or identity (train: raw conv output, BN statistics follow);
+//   operands       bf16, K-major, 128-byte swizzle (TMA writes it, the UMMA descriptor reads it); 64-byte swizzle and
+//                  32-element K blocks when Cin == 32 (no overhanging TMA boxes)
+//   pipeline       persistent CTAs (one per SM); warp 0: TMA producer | warp 1: TMEM alloc + MMA issue (warp-uniform
+//                  loop, one elected lane) into 2-8 rotating TMEM accumulators | warps 2-5 / 6-9: two epilogue groups
+//                  taking alternate tiles (tcgen05.ld -> scale/shift/activation/residual/BN statistics -> global)
+//                  overlapping the following tiles' main loops; mbarrier smem ring; programmatic dependent launch
+//   epilogue       mode 0: bf16 NHWC into a channel slice of a (concat) buffer, staged in smem and stored (or, for
+//                  dgrad's accumulation, reduce-added) by TMA; per-channel scale/shift = folded BatchNorm (eval) or
+//                  identity (train: raw conv output + fused BatchNorm statistics and finalize);
 //                  mode 1: fp32 head written directly in the reference's [B, na, gs, gs, ch] layout
 //                  (the permute+contiguous of model/yololayer.py:25,76 is fused away).
 #include "common.cuh"

@@ -11,9 +11,10 @@
 // of every tap reuses the same tensor map as the forward pass (element strides = conv stride, OOB = padding).
 //
 //   work item   (128-channel Cout tile) x (64*nb-channel Cin tile) x (group of taps that fits TMEM: tg*64*nb <= 512)
-//   split-K     the patches of an item are dealt round-robin to its CTAs (the SMs are shared out between the items in
-//               proportion to their tap counts); every CTA keeps its partial dW in TMEM
-//               for its whole life and adds it to the fp32 OIHW gradient with atomics once at the end
+//   split-K     the patches of an item are dealt round-robin to its CTAs (the SMs are shared out between the items by
+//               their measured cost per patch); every CTA keeps its partial dW in TMEM for its whole life and adds it
+//               to the K-major fp32 scratch with vector atomics once at the end
+//   MMAs        narrow Cin tiles issue several taps per MMA (consecutive ring slots = consecutive N atoms)
 //   pipeline    warp 0 TMA producer (dY ring of 2-6 slots, X ring of 2-12 stages: 14 boxes of smem shared out per CTA
 //               by the length of its tap group) | warp 1 MMA issuer | warps 2-5 epilogue
 #include "common.cuh"
