@@ -124,7 +124,7 @@ template <int ACT>
 __device__ __forceinline__ float act_grad2(float y) {
   if (ACT == RYOLO_ACT_MISH) {
     const float e = __expf(fminf(y, 20.f));
-    const float r = __fdividef(1.f, fmaf(e, e + 2.f, 2.f));
+    const float r = ry_rcp_fma(fmaf(e, e + 2.f, 2.f));       // denominator in [2, 2.4e17]
     const float t = fmaf(-2.f, r, 1.f);
     return fmaf(4.f * y, e * (e + 1.f) * (r * r), t);
   }

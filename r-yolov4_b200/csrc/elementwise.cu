@@ -14,12 +14,11 @@ namespace {
 __device__ __forceinline__ float act_apply(float x, int act) {
   if (act == RYOLO_ACT_LEAKY) return x > 0.f ? x : 0.1f * x;
   if (act == RYOLO_ACT_MISH) {
-    if (x > 20.f) return x;
-    const float e = __expf(x);
+    const float e = __expf(fminf(x, 20.f));          // x > 20: n/(n+2) rounds to 1
     const float n = e * (e + 2.f);
-    return x * __fdividef(n, n + 2.f);
+    return x * (n * ry_rcp_fma(n + 2.f));            // n + 2 in [2, 2.4e17]
   }
-  if (act == RYOLO_ACT_SWISH) return x * __fdividef(1.f, 1.f + __expf(-x));
+  if (act == RYOLO_ACT_SWISH) return x * ry_rcp_fma(1.f + __expf(fminf(-x, 60.f)));   // denominator in [1, 1.1e26]
   return x;
 }
 
