@@ -341,6 +341,68 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv
   }
 }
 
+// Same routing for a stride-1 "same" pool on a small map (SPP), one block per (image, 8 channels): the map, its row
+// maxima and an fp32 gradient tile live in shared memory.  The window maximum m is separable; the first maximum in
+// row-major scan order is the first row whose row-window maximum equals m, then the first column of that row equal to m
+// (2k comparisons per output and channel instead of k*k), and no global scratch / second pass is needed.
+__global__ void __launch_bounds__(256)
+maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv_bfloat16* __restrict__ dy,
+                              long long dyp, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, long long dxp,
+                              int accumulate) {
+  extern __shared__ float sm_pb[];             // [H*W][8] map | [H*W][8] row maxima | [H*W][8] gradient
+  const int HW = H * W, p = k >> 1;
+  float* sx = sm_pb;
+  float* sr = sm_pb + 8 * HW;
+  float* sg = sm_pb + 16 * HW;
+  const int groups = C >> 3;
+  const int n = blockIdx.x / groups, c = (blockIdx.x % groups) * 8;
+  const __nv_bfloat16* xb = x + (long long)n * HW * xp + c;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(xb + (long long)i * xp), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sx[i * 8 + j] = f[j]; sg[i * 8 + j] = 0.f; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+    const int j = i & 7, pix = i >> 3;
+    const int h = pix / W, w = pix - h * W;
+    const int w0 = max(w - p, 0), w1 = min(w + p, W - 1);
+    float m = sx[(h * W + w0) * 8 + j];
+    for (int ww = w0 + 1; ww <= w1; ww++) m = fmaxf(m, sx[(h * W + ww) * 8 + j]);
+    sr[i] = m;
+  }
+  __syncthreads();
+  const __nv_bfloat16* gb = dy + (long long)n * HW * dyp + c;
+  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
+    const int j = i & 7, pix = i >> 3;
+    const int h = pix / W, w = pix - h * W;
+    const int h0 = max(h - p, 0), h1 = min(h + p, H - 1);
+    const int w0 = max(w - p, 0), w1 = min(w + p, W - 1);
+    float m = sr[(h0 * W + w) * 8 + j];
+    for (int hh = h0 + 1; hh <= h1; hh++) m = fmaxf(m, sr[(hh * W + w) * 8 + j]);
+    int hs = h0;
+    while (hs < h1 && sr[(hs * W + w) * 8 + j] != m) hs++;          // first row holding the maximum
+    int ws = w0;
+    while (ws < w1 && sx[(hs * W + ws) * 8 + j] != m) ws++;         // first column of that row
+    atomicAdd(&sg[(hs * W + ws) * 8 + j], __bfloat162float(gb[(long long)pix * dyp + j]));
+  }
+  __syncthreads();
+  __nv_bfloat16* db = dx + (long long)n * HW * dxp + c;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) a[j] = sg[i * 8 + j];
+    if (accumulate) {
+      float b[8];
+      unpack8(*reinterpret_cast<const uint4*>(db + (long long)i * dxp), b);
+#pragma unroll
+      for (int j = 0; j < 8; j++) a[j] += b[j];
+    }
+    *reinterpret_cast<uint4*>(db + (long long)i * dxp) = pack8(a);
+  }
+}
+
 // dst (bf16 view) (+)= acc (dense fp32 [P, C])
 __global__ void __launch_bounds__(256)
 add_f32_into_kernel(__nv_bfloat16* __restrict__ dst, long long dpitch, const float* __restrict__ acc, long long P, int C,
@@ -559,6 +621,20 @@ int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp
   const long long P = (long long)N * H * W;
   if (P == 0) return RYOLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (stride == 1 && (k & 1) && pad == k / 2 && H * W <= 1024 && (long long)N * (C / 8) < (1ll << 31)) {
+    const size_t smem = (size_t)24 * H * W * sizeof(float);          // <= 96 KB
+    static bool configured = false;
+    if (!configured) {
+      cudaError_t e = cudaFuncSetAttribute(maxpool_same_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           96 * 1024);
+      if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
+      configured = true;
+    }
+    maxpool_same_small_bwd_kernel<<<(unsigned)(N * (C / 8)), 256, smem, st>>>(
+        (const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, H, W, C, k, (__nv_bfloat16*)dx, dxp, accumulate);
+    RY_CHECK_LAUNCH();
+    return RYOLO_OK;
+  }
   cudaMemsetAsync(scratch, 0, (size_t)P * C * sizeof(float), st);
   if (total > 0)
     maxpool_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, N,

@@ -203,6 +203,49 @@ maxpool_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, 
   }
 }
 
+// Stride-1 "same" max pool on a small map (SPP: k = 5 / 9 / 13 on 25x25): one block per (image, 8 channels), the map
+// lives in shared memory and the window maximum is separable (row maxima, then a column of row maxima): 2k instead
+// of k*k comparisons per output.
+__device__ __forceinline__ uint4 max8_bf16(const uint4& a, const uint4& b) {
+  uint4 r;
+  const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* pb = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* pr = reinterpret_cast<__nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; j++) pr[j] = __hmax2(pa[j], pb[j]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+maxpool_same_small_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int H, int W, int C, int k,
+                          __nv_bfloat16* __restrict__ y, long long yp) {
+  extern __shared__ uint4 sm_pool[];           // [H*W] map | [H*W] row maxima
+  uint4* sx = sm_pool;
+  uint4* sr = sm_pool + H * W;
+  const int groups = C >> 3;
+  const int n = blockIdx.x / groups, c = (blockIdx.x % groups) * 8;
+  const int HW = H * W, p = k >> 1;
+  const __nv_bfloat16* xb = x + (long long)n * HW * xp + c;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) sx[i] = *reinterpret_cast<const uint4*>(xb + (long long)i * xp);
+  __syncthreads();
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int h = i / W, w = i - h * W;
+    const int w0 = max(w - p, 0), w1 = min(w + p, W - 1);
+    uint4 m = sx[h * W + w0];
+    for (int ww = w0 + 1; ww <= w1; ww++) m = max8_bf16(m, sx[h * W + ww]);
+    sr[i] = m;
+  }
+  __syncthreads();
+  __nv_bfloat16* yb = y + (long long)n * HW * yp + c;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+    const int h = i / W, w = i - h * W;
+    const int h0 = max(h - p, 0), h1 = min(h + p, H - 1);
+    uint4 m = sr[h0 * W + w];
+    for (int hh = h0 + 1; hh <= h1; hh++) m = max8_bf16(m, sr[hh * W + w]);
+    *reinterpret_cast<uint4*>(yb + (long long)i * yp) = m;
+  }
+}
+
 // nearest-neighbour x`f` upsample (f = 1 is a plain strided copy between views)
 __global__ void __launch_bounds__(256)
 resize_copy_kernel(const __nv_bfloat16* __restrict__ x, long long xp, int N, int H, int W, int C, int f,
@@ -494,6 +537,12 @@ int ryolo_maxpool(const void* x, long long xp, int N, int H, int W, int C, int k
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const long long total = (long long)N * Ho * Wo * (C / 8);
   if (total == 0) return RYOLO_OK;
+  if (stride == 1 && (k & 1) && pad == k / 2 && H * W <= 1024 && (long long)N * (C / 8) < (1ll << 31)) {
+    maxpool_same_small_kernel<<<(unsigned)(N * (C / 8)), 256, (size_t)2 * H * W * sizeof(uint4), (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, xp, H, W, C, k, (__nv_bfloat16*)y, yp);
+    RY_CHECK_LAUNCH();
+    return RYOLO_OK;
+  }
   maxpool_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, xp, N, H, W, C, k,
                                                                          stride, pad, (__nv_bfloat16*)y, yp, Ho, Wo);
   RY_CHECK_LAUNCH();
