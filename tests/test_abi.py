@@ -53,3 +53,29 @@ def test_product_never_imports_oracle():
                 s = open(os.path.join(dp, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", s, flags=re.M), os.path.join(dp, f)
                 assert "oracle/" not in s or f.endswith((".cuh", ".cu")), os.path.join(dp, f)
+
+
+def test_tuning_knobs_host_api():
+    """ryolo_tune / ryolo_knob are host-only: defaults, overrides, unknown keys (include/ryolo_b200.h)."""
+    from ryolo_b200 import _lib as L
+    lib = L.lib()
+    names = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64",
+             "nacc", "pdl"]
+    before = [lib.ryolo_knob(i) for i in range(len(names))]
+    assert before[names.index("dbg")] == 0 and before[names.index("wg_dbg")] == 0, "timing experiments must be off"
+    assert before[names.index("epi_tma")] == 2 and before[names.index("wg_trans")] == 0
+    try:
+        L.tune(epi_tma=0, wg_split=2)
+        assert lib.ryolo_knob(names.index("epi_tma")) == 0 and lib.ryolo_knob(names.index("wg_split")) == 2
+        with pytest.raises(L.RyoloError):
+            L.tune(no_such_knob=1)
+        assert lib.ryolo_knob(-1) == 0 and lib.ryolo_knob(999) == 0
+    finally:
+        L.tune(**dict(zip(names, before)))
+    assert [lib.ryolo_knob(i) for i in range(len(names))] == before
+
+
+def test_label_encoder_rejects_cpu_tensors():
+    import ryolo_b200
+    with pytest.raises(ryolo_b200.RyoloError):
+        ryolo_b200.encode_labels(torch.zeros(3, 10))
