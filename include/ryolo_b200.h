@@ -197,8 +197,8 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
                        long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, float* dwk, void* stream);
 /* d raw = backward of act(BatchNorm2d_train(raw)) given d out; d gamma, d beta (fp32[C], nullable) are ACCUMULATED
  * into (autograd .grad semantics: gradient accumulation over micro-batches, reference train.py:198-202).
- * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.  dout is overwritten
- * with dout*act'(.) (dead afterwards).                                                                        */
+ * scale/shift/mean/invstd are what the forward pass saved; sums = fp32[2C] zeroed scratch.  dout may be overwritten
+ * with dout*act'(.) (knob bn_bwd < 2): treat it as dead afterwards.                                                                        */
 int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
                      float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream);

@@ -255,6 +255,130 @@ bn_act_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, co
   }
 }
 
+// Variant 2 of the two passes (knob bn_bwd = 2): the reduce pass does not store dY (4 B/element of traffic instead of 6);
+// the apply pass recomputes dY = dOut * act'(.) from dOut and raw (6 B/element as before, plus ~15 flops: the
+// activation derivative costs one exp and an FMA-pipe reciprocal).  dY never rounds to bf16 and dOut stays intact.
+template <int ACT>
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_reduce3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
+                          float* __restrict__ sums) {
+  ry_pdl_wait();
+  extern __shared__ float red[];   // [rows][C] x 2
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int c = 8 * g;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < rows) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sc[j] = scale[c + j]; sh[j] = shift[c + j]; }
+    const long long stride = (long long)gridDim.x * rows;
+    for (long long pix0 = (long long)blockIdx.x * rows + r; pix0 < P; pix0 += 2 * stride) {
+      uint4 vd[2], vr[2];
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const long long pix = pix0 + u * stride;
+        if (pix < P) {
+          vd[u] = *reinterpret_cast<const uint4*>(dout + pix * dp + c);
+          vr[u] = *reinterpret_cast<const uint4*>(raw + pix * rp + c);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 2; u++) {
+        const long long pix = pix0 + u * stride;
+        if (pix < P) {
+          float d[8], x[8];
+          unpack8(vd[u], d);
+          unpack8(vr[u], x);
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            if (ACT != RYOLO_ACT_LINEAR) d[j] *= act_grad2<ACT>(fmaf(x[j], sc[j], sh[j]));
+            s1[j] += d[j];
+            s2[j] = fmaf(d[j], x[j], s2[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) s2[j] = invstd[c + j] * (s2[j] - mean[c + j] * s1[j]);
+  }
+  float* r1 = red;
+  float* r2 = red + (size_t)rows * C;
+  if (r < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { r1[r * C + c + j] = s1[j]; r2[r * C + c + j] = s2[j]; }
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; rr++) { a += r1[rr * C + cc]; b += r2[rr * C + cc]; }
+    atomicAdd(sums + cc, a);
+    atomicAdd(sums + C + cc, b);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256, 3)
+bn_act_bwd_apply2_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                         long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
+                         long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  ry_pdl_wait();
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (blockIdx.x == 0) {
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      if (dbeta) dbeta[cc] += sums[cc];
+      if (dgamma) dgamma[cc] += sums[C + cc];
+    }
+  }
+  if (r >= rows) return;
+  const int c = 8 * g;
+  const float invP = 1.f / (float)P;
+  // o = sc*(d - m1 - (x - mu)*is*m2) = sc*d - x*k2 - k1   with k2 = sc*is*m2, k1 = sc*(m1 - mu*is*m2)
+  float sc[8], sh[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c + j]; sh[j] = shift[c + j];
+    const float is = invstd[c + j], mu = mean[c + j];
+    const float m1 = sums[c + j] * invP, m2 = sums[C + c + j] * invP;
+    k2[j] = sc[j] * is * m2;
+    k1[j] = sc[j] * (m1 - mu * is * m2);
+  }
+  const long long stride = (long long)gridDim.x * rows;
+  for (long long pix0 = (long long)blockIdx.x * rows + r; pix0 < P; pix0 += 2 * stride) {
+    uint4 vd[2], vr[2];
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long pix = pix0 + u * stride;
+      if (pix < P) {
+        vd[u] = *reinterpret_cast<const uint4*>(dout + pix * dp + c);
+        vr[u] = *reinterpret_cast<const uint4*>(raw + pix * rp + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; u++) {
+      const long long pix = pix0 + u * stride;
+      if (pix < P) {
+        float d[8], x[8], o[8];
+        unpack8(vd[u], d);
+        unpack8(vr[u], x);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          if (ACT != RYOLO_ACT_LINEAR) d[j] *= act_grad2<ACT>(fmaf(x[j], sc[j], sh[j]));
+          o[j] = fmaf(sc[j], d[j], -fmaf(x[j], k2[j], k1[j]));
+        }
+        *reinterpret_cast<uint4*>(draw + pix * op + c) = pack8(o);
+      }
+    }
+  }
+}
+
 // ds = dout * act'(x1*s1+b1 + x2*s2+b2)   (two-branch pre-activation, RepConv)
 template <int ACT>
 __global__ void __launch_bounds__(256)
@@ -559,14 +683,23 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
   __nv_bfloat16* d = (__nv_bfloat16*)dout;
   const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
   __nv_bfloat16* o = (__nv_bfloat16*)draw;
-  const bool lean = ryolo_knob(RYOLO_KNOB_BN_BWD) != 0 && threads == 256;
+  const int variant = threads == 256 ? ryolo_knob(RYOLO_KNOB_BN_BWD) : 0;
 #define RY_BWD(ACT)                                                                                                  \
-  if (lean)                                                                                                          \
-    ry_launch(bn_act_bwd_reduce2_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, d, dp, r, rp, scale, shift, mean,   \
-              invstd, P, C, sums);                                                                                   \
-  else                                                                                                               \
-    ry_launch(bn_act_bwd_reduce_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, d, dp, r, rp, scale, shift, mean,    \
-              invstd, P, C, sums);
+  if (variant == 2) {                                                                                                \
+    ry_launch(bn_act_bwd_reduce3_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, (const __nv_bfloat16*)d, dp, r, rp, \
+              scale, shift, mean, invstd, P, C, sums);                                                               \
+    ry_launch(bn_act_bwd_apply2_kernel<ACT>, dim3(blocks * 2), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp, \
+              scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                           \
+  } else {                                                                                                           \
+    if (variant == 1)                                                                                                \
+      ry_launch(bn_act_bwd_reduce2_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, d, dp, r, rp, scale, shift,   \
+                mean, invstd, P, C, sums);                                                                           \
+    else                                                                                                             \
+      ry_launch(bn_act_bwd_reduce_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, d, dp, r, rp, scale, shift,    \
+                mean, invstd, P, C, sums);                                                                           \
+    ry_launch(bn_act_bwd_apply_kernel, dim3(blocks * 2), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp,   \
+              scale, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                                  \
+  }
   switch (act) {
     case RYOLO_ACT_LEAKY: RY_BWD(RYOLO_ACT_LEAKY) break;
     case RYOLO_ACT_MISH: RY_BWD(RYOLO_ACT_MISH) break;
@@ -574,8 +707,6 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
     default: RY_BWD(RYOLO_ACT_LINEAR) break;
   }
 #undef RY_BWD
-  ry_launch(bn_act_bwd_apply_kernel, dim3(blocks * 2), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp, scale,
-            mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -28,12 +28,13 @@ int ryolo_abi_version(void) { return 1; }
 //   sw64      conv: 1 = Cin == 32 operands use 32-element (64-byte, SWIZZLE_64B) K blocks instead of overhanging 64-element boxes
 //   nacc      conv: 1 = as many TMEM accumulators in rotation as fit (up to 8), 0 = two
 //   pdl       1 = the conv / wgrad / BatchNorm-backward / scale-shift-act kernels use programmatic dependent launch
-//   bn_bwd    BatchNorm backward reduce pass: 1 = low-register variant, 0 = original
+//   bn_bwd    BatchNorm backward: 0 = original passes, 1 = low-register reduce (stores dY), 2 = reduce without the dY
+//             store + an apply pass that recomputes the activation derivative
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
                                                           "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 1, 0, 1, 1, 1};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 2, 0, 1, 1, 1};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

@@ -36,6 +36,7 @@ VARIANTS = [
     ("wg_nomma", dict(wg_dbg=1)),
     ("wg_noload", dict(wg_dbg=2)),
     ("bn_old", dict(bn_bwd=0)),
+    ("bn_store", dict(bn_bwd=1)),
     ("sw128", dict(sw64=0)),
     ("acc2", dict(nacc=0)),
     ("nopdl", dict(pdl=0)),
