@@ -465,6 +465,52 @@ maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv
   }
 }
 
+// Non-overlapping pool (k == stride, no padding, H and W multiples of k: yolov7's MaxConv 2x2/s2): every input element
+// belongs to exactly one window, so its gradient is written directly (the window's first maximum gets dy, the others 0):
+// no scratch, no atomics, no second pass.
+__global__ void __launch_bounds__(256)
+maxpool_tiled_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv_bfloat16* __restrict__ dy,
+                         long long dyp, int N, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, long long dxp,
+                         int accumulate) {
+  const int groups = C >> 3, Ho = H / k, Wo = W / k;
+  const long long total = (long long)N * Ho * Wo * groups;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % groups) * 8;
+    const long long pix = i / groups;
+    const int wo = (int)(pix % Wo), ho = (int)((pix / Wo) % Ho), n = (int)(pix / ((long long)Wo * Ho));
+    float m[8], g[8];
+    int am[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { m[j] = -INFINITY; am[j] = -1; }
+    for (int dh = 0; dh < k; dh++) {
+      for (int dw = 0; dw < k; dw++) {
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4*>(x + (((long long)n * H + ho * k + dh) * W + wo * k + dw) * xp + c), f);
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+          if (f[j] > m[j] || am[j] < 0) { m[j] = f[j]; am[j] = dh * k + dw; }
+      }
+    }
+    unpack8(*reinterpret_cast<const uint4*>(dy + pix * dyp + c), g);
+    for (int dh = 0; dh < k; dh++) {
+      for (int dw = 0; dw < k; dw++) {
+        __nv_bfloat16* o = dx + (((long long)n * H + ho * k + dh) * W + wo * k + dw) * dxp + c;
+        float a[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) a[j] = am[j] == dh * k + dw ? g[j] : 0.f;
+        if (accumulate) {
+          float b[8];
+          unpack8(*reinterpret_cast<const uint4*>(o), b);
+#pragma unroll
+          for (int j = 0; j < 8; j++) a[j] += b[j];
+        }
+        *reinterpret_cast<uint4*>(o) = pack8(a);
+      }
+    }
+  }
+}
+
 // Same routing for a stride-1 "same" pool on a small map (SPP), one block per (image, 8 channels): the map, its row
 // maxima and an fp32 gradient tile live in shared memory.  The window maximum m is separable; the first maximum in
 // row-major scan order is the first row whose row-window maximum equals m, then the first column of that row equal to m
@@ -763,6 +809,12 @@ int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp
     }
     maxpool_same_small_bwd_kernel<<<(unsigned)(N * (C / 8)), 256, smem, st>>>(
         (const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, H, W, C, k, (__nv_bfloat16*)dx, dxp, accumulate);
+    RY_CHECK_LAUNCH();
+    return RYOLO_OK;
+  }
+  if (stride == k && pad == 0 && H % k == 0 && W % k == 0) {
+    maxpool_tiled_bwd_kernel<<<grid_for(total, 256), 256, 0, st>>>((const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy,
+                                                                  dyp, N, H, W, C, k, (__nv_bfloat16*)dx, dxp, accumulate);
     RY_CHECK_LAUNCH();
     return RYOLO_OK;
   }

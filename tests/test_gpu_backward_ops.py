@@ -156,6 +156,8 @@ def test_pool_upsample_add_headpack_backward():
     dx = ops.Act(torch.zeros(2, 24, 24, 64).bfloat16().cuda())
     ops.maxpool_bwd(ops.Act(x2.cuda()), ops.Act(dy2.cuda()), 2, 2, 0, dx, False)
     assert torch.equal(dx.torch().float().cpu(), xn.grad.permute(0, 2, 3, 1))
+    ops.maxpool_bwd(ops.Act(x2.cuda()), ops.Act(dy2.cuda()), 2, 2, 0, dx, True)          # accumulates
+    assert (dx.torch().float().cpu() - 2 * xn.grad.permute(0, 2, 3, 1)).abs().max() <= 2e-2 * xn.grad.abs().max()
     # upsample x2
     g = torch.randn(2, 20, 20, 32, generator=gen).bfloat16()
     ref = g.float().view(2, 10, 2, 10, 2, 32).sum((2, 4))
