@@ -84,6 +84,9 @@ def _implicit_head_grads(model, conv, gl, y, mul, param_grads):
     dpre_sum = (gl.sum((0, 2, 3)).reshape(-1) * mul)                      # sum over pixels of d pre
     w = conv.conv[0].weight.data.float().flatten(1)                       # [Cout, Cin]
     param_grads[id(ia.implicit)].add_((w.t() @ dpre_sum).view_as(ia.implicit))
+    # the conv's input is x + ia: the wgrad GEMM sees x only, the constant part contributes (sum d pre) (x) ia
+    param_grads[id(conv.conv[0].weight)].add_(
+        torch.outer(dpre_sum, ia.implicit.data.float().flatten()).view_as(conv.conv[0].weight))
 
 def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
     """out = silu(bn_d(conv3x3(x)) + bn_1(conv1x1(x)))   (model/utils.py:209-215)."""

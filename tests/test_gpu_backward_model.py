@@ -245,3 +245,64 @@ def test_fused_weight_pack_matches_per_layer_pack(ver):
                 assert torch.equal(pkt.w.view(-1), ops.pack_weights(w.data, transpose=True).view(-1)), (tuple(w.shape), "t")
             checked += 1
     assert checked > 80
+
+
+def test_v7_implicit_head_forward_backward():
+    """yolov7 head  y = ImplicitM * (conv1x1(RepConv(x) + ImplicitA) + b)  (model/neck.py:201,208,215; model/utils.py:163-186):
+    forward and every gradient (ImplicitA, ImplicitM, head weight / bias, RepConv parameters, dx) against torch autograd
+    on the oracle's bf16-emulating restatement of the RepConv."""
+    import torch.nn.functional as F
+    from oracle import model_cpu
+    from ryolo_b200 import ops
+    from ryolo_b200.model import blocks as B
+    from ryolo_b200.model.backward import run_backward
+    from ryolo_b200.model.neck import Neckv7
+    na, ch, c1, c2, N, hw = 3, 24, 64, 128, 4, 12
+    gen = torch.Generator().manual_seed(17)
+
+    class MiniNeck(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.repVgg1 = B.RepConv(c1, c2)
+            self.ia1 = B.ImplicitA(c2)
+            self.conv5 = B.Conv(c2, na * ch, 1, 1, 'linear', bn=False, bias=True)
+            self.im1 = B.ImplicitM(na * ch)
+            self.conv6 = self.conv7 = None          # the two other pyramid levels do not exist here
+
+    neck = det_init(MiniNeck())
+    with torch.no_grad():
+        neck.ia1.implicit.normal_(0.0, 0.3, generator=gen)
+        neck.im1.implicit.normal_(1.0, 0.1, generator=gen)
+        neck.conv5.conv[0].bias.normal_(0.0, 0.5, generator=gen)
+    x = torch.randn(N, hw, hw, c1, generator=gen).bfloat16()
+    gl = torch.randn(N, na, hw, hw, ch, generator=gen)
+    # ---- reference: autograd
+    pn = {k for k, _ in neck.named_parameters()}
+    sd = {k: v.clone().requires_grad_(k in pn) for k, v in neck.state_dict().items()}
+    rep_sd = {"blk." + k[len("repVgg1."):]: v for k, v in sd.items() if k.startswith("repVgg1.")}
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yrep = model_cpu.Net(rep_sd, True, emulate_bf16=True).repconv(xr, "blk")
+    pre = F.conv2d(yrep + sd["ia1.implicit"], sd["conv5.conv.0.weight"], sd["conv5.conv.0.bias"])
+    ref = (pre * sd["im1.implicit"]).view(N, na, ch, hw, hw).permute(0, 1, 3, 4, 2)
+    ref.backward(gl)
+    # ---- product
+    neck = neck.cuda().train()
+
+    class Model:
+        pass
+    model = Model()
+    model.neck, model.na, model.ch = neck, na, ch
+    bns = [m for m in neck.modules() if isinstance(m, torch.nn.BatchNorm2d)]
+    model._bn_channels, model._bn_layers = sum(m.num_features for m in bns), len(bns)
+    ctx = B.Ctx(model, True, torch.device("cuda"))
+    xa = ops.Act(x.cuda())
+    out = Neckv7._head(neck, ctx, 1, xa, na, ch)
+    assert out.shape == ref.shape
+    assert _rel(out.float().cpu(), ref.detach()) < 4e-2
+    grads = {id(p): torch.zeros_like(p) for p in neck.parameters()}
+    G = run_backward(model, ctx, [None, None, gl.cuda()], grads)
+    dx = G.view(xa).torch().float().cpu()
+    assert _l2(dx, xr.grad.permute(0, 2, 3, 1)) < 6e-2, _l2(dx, xr.grad.permute(0, 2, 3, 1))
+    for k, p in neck.named_parameters():
+        e = _l2(grads[id(p)].cpu(), sd[k].grad)
+        assert e < 6e-2, (k, e)
