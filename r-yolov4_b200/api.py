@@ -3,6 +3,7 @@ test.py / detect.py use, under their real names plus the aliases BASELINE.json's
 from ._lib import RyoloError, SO_PATH, lib
 from .lib.general import (encode_labels, xyxyxyxy2xywha, nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
                           post_process_device)
+from .lib import labels_io
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
 from .lib.metrics import ap_per_class, compute_ap, get_batch_statistics
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
@@ -23,4 +24,4 @@ def compute_loss(model, hyp, mode="csl"):
 
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
-           "encode_labels", "xyxyxyxy2xywha", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle", "get_batch_statistics", "ap_per_class", "compute_ap", "RyoloError", "SO_PATH", "lib"]
+           "encode_labels", "xyxyxyxy2xywha", "labels_io", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle", "get_batch_statistics", "ap_per_class", "compute_ap", "RyoloError", "SO_PATH", "lib"]
