@@ -116,3 +116,15 @@ def test_label_files_match_reference_golden(tmp_path):
     assert torch.equal(lio.collate_targets([finals[0].clone(), finals[1].clone()]), g["collated"])
     with pytest.raises(NotImplementedError):
         lio.load_label_file(path, cat, "voc")
+
+
+def test_geometry_helpers_match_reference_golden():
+    """xywh2xyxy / xywha2xyxyxyxy / rescale_boxes against the reference's own functions (tests/golden/geometry.pt)."""
+    import ryolo_b200 as R
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "geometry.pt"))
+    assert torch.equal(R.xywh2xyxy(g["boxes"][:, :4].clone()), g["xyxy"])
+    got = R.xywha2xyxyxyxy(g["boxes"].clone())
+    assert got.shape == g["corners"].shape
+    assert (got - g["corners"]).abs().max() <= 1e-4 * g["corners"].abs().max()      # fp32 box values, 1e-4 rel
+    for case in g["rescale"]:
+        assert torch.equal(R.rescale_boxes(case["inp"].clone(), case["dim"], case["shape"]), case["out"])
