@@ -5,7 +5,7 @@ from .lib.general import (encode_labels, rescale_boxes, xywh2xyxy, xywha2xyxyxyx
                           post_process_device)
 from .lib import labels_io
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
-from .lib.metrics import ap_per_class, compute_ap, get_batch_statistics
+from .lib.metrics import ap_per_class, calculate_eval_stats, compute_ap, fitness, get_batch_statistics
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
 from .schedule import Schedule, one_cycle
 from .train_step import TrainStep
@@ -24,4 +24,4 @@ def compute_loss(model, hyp, mode="csl"):
 
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
-           "encode_labels", "xyxyxyxy2xywha", "xywha2xyxyxyxy", "xywh2xyxy", "rescale_boxes", "labels_io", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle", "get_batch_statistics", "ap_per_class", "compute_ap", "RyoloError", "SO_PATH", "lib"]
+           "encode_labels", "xyxyxyxy2xywha", "xywha2xyxyxyxy", "xywh2xyxy", "rescale_boxes", "labels_io", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle", "get_batch_statistics", "ap_per_class", "compute_ap", "calculate_eval_stats", "fitness", "RyoloError", "SO_PATH", "lib"]

@@ -100,3 +100,23 @@ def ap_per_class(tp, conf, pred_cls, target_cls):
     f1 = 2 * p * r / (p + r + 1e-16)
     i = f1.mean(0).argmax()
     return p[:, i], r[:, i], ap, f1[:, i], unique_classes.astype('int32')
+
+
+def calculate_eval_stats(stats, num_classes):
+    """Per-class and mean P / R / AP@0.5 / AP@0.5:0.95 from the concatenated batch statistics (test.py:152-165)."""
+    p, r, f1, mp, mr, map50, map_ = 0., 0., 0., 0., 0., 0., 0.
+    ap50, ap, ap_class = [], [], []
+    if len(stats) and stats[0].any():
+        p, r, ap, f1, ap_class = ap_per_class(*stats)
+        ap50, ap = ap[:, 0], ap.mean(1)
+        mp, mr, map50, map_ = p.mean(), r.mean(), ap50.mean(), ap.mean()
+        nt = np.bincount(stats[3].astype(np.int64), minlength=num_classes)
+    else:
+        nt = torch.zeros(1)
+    return nt, p, r, ap50, ap, f1, ap_class, mp, mr, map50, map_
+
+
+def fitness(x):
+    """Model fitness = 0.1 mAP@0.5 + 0.9 mAP@0.5:0.95 over rows (P, R, mAP@0.5, mAP@0.5:0.95) (train.py:41-44)."""
+    w = [0.0, 0.0, 0.1, 0.9]
+    return (x * w).sum(0)
