@@ -108,10 +108,9 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
   const int nq = qn;
   for (int q = tid; q < nq; q += 256) {
     int p = queue[q], i = p >> 6, j = p & 63;
-    // cheap fp32 estimate first; the bit-exact Appendix-B computation only where the estimate is near the threshold
-    float v = rbox_iou_fast(srow[i], scol[j]);
-    if (fabsf(v - thr) <= 2e-3f) v = rbox_iou_full(srow[i], scol[j]);
-    if (v > thr) atomicOr(&tmask[i], 1ull << j);
+    // cheap fp32 estimate where its error is provably small (rbox_fast_ok) and far from the threshold; the bit-exact
+    // Appendix-B computation everywhere else
+    if (rbox_iou_exceeds(srow[i], scol[j], thr)) atomicOr(&tmask[i], 1ull << j);
   }
   __syncthreads();
   if (tid < kTile) {

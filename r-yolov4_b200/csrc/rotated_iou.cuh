@@ -8,8 +8,21 @@
 // All fp32 arithmetic goes through __f{add,sub,mul}_rn / __fdiv_rn so that nvcc can never contract
 // a multiply-add into an FMA: keep/suppress decisions are compared bit-for-bit with a CPU build.
 #pragma once
-#include <cuda_runtime.h>
 #include <math.h>
+#if defined(__CUDACC__)
+#include <cuda_runtime.h>
+#define RY_RDEV __device__ __forceinline__
+#define RY_RDEV_NOINLINE __device__ __noinline__
+#else
+// Host build (tests/host/rotated_iou_host.cpp, g++ -ffp-contract=off): the same source decides the same pairs on the
+// CPU, so the fast-path gate below can be checked against the oracle over millions of adversarial pairs without a GPU.
+#define RY_RDEV static inline
+#define RY_RDEV_NOINLINE static
+static inline float __fmul_rn(float a, float b) { return a * b; }
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline float __fdiv_rn(float a, float b) { return a / b; }
+#endif
 
 namespace ryolo {
 
@@ -24,14 +37,14 @@ struct V2 {
   float x, y;
 };
 
-__device__ __forceinline__ float fm(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float fa(float a, float b) { return __fadd_rn(a, b); }
-__device__ __forceinline__ float fs(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ V2 vsub(V2 a, V2 b) { return {fs(a.x, b.x), fs(a.y, b.y)}; }
-__device__ __forceinline__ float vdot(V2 a, V2 b) { return fa(fm(a.x, b.x), fm(a.y, b.y)); }
-__device__ __forceinline__ float vcross(V2 a, V2 b) { return fs(fm(a.x, b.y), fm(b.x, a.y)); }
+RY_RDEV float fm(float a, float b) { return __fmul_rn(a, b); }
+RY_RDEV float fa(float a, float b) { return __fadd_rn(a, b); }
+RY_RDEV float fs(float a, float b) { return __fsub_rn(a, b); }
+RY_RDEV V2 vsub(V2 a, V2 b) { return {fs(a.x, b.x), fs(a.y, b.y)}; }
+RY_RDEV float vdot(V2 a, V2 b) { return fa(fm(a.x, b.x), fm(a.y, b.y)); }
+RY_RDEV float vcross(V2 a, V2 b) { return fs(fm(a.x, b.y), fm(b.x, a.y)); }
 
-__device__ __forceinline__ RPrep rprep(float cx, float cy, float w, float h, float deg) {
+RY_RDEV RPrep rprep(float cx, float cy, float w, float h, float deg) {
   RPrep r;
   r.cx = cx; r.cy = cy; r.w = w; r.h = h;
   double theta = (double)deg * 0.01745329251;
@@ -46,7 +59,7 @@ __device__ __forceinline__ RPrep rprep(float cx, float cy, float w, float h, flo
 }
 
 // true => the two boxes are certainly disjoint (IoU == 0 exactly under Appendix B)
-__device__ __forceinline__ bool rbox_far(const RPrep& a, const RPrep& b) {
+RY_RDEV bool rbox_far(const RPrep& a, const RPrep& b) {
   float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.reach + b.reach;
   return dx * dx + dy * dy > rr * rr;
 }
@@ -56,11 +69,19 @@ __device__ __forceinline__ bool rbox_far(const RPrep& a, const RPrep& b) {
 //   (1) area bound: IoU <= min(area)/max(area); 0.1 % margin covers fp32 rounding of the clipped area
 //   (2) separating-axis test on the four box axes with a margin far above the +-EPS slack of Appendix B step 3
 //       (a disjoint pair can only produce a sliver of IoU << 1e-6)
-__device__ __forceinline__ bool rbox_cannot_exceed(float acx, float acy, float aw, float ah, float ac2, float as2,
+RY_RDEV bool rbox_cannot_exceed(float acx, float acy, float aw, float ah, float ac2, float as2,
                                                    float aarea, float bcx, float bcy, float bw, float bh, float bc2,
                                                    float bs2, float barea, float thr) {
+  // Appendix B's absolute EPS = 1e-5 slack (on squared-length quantities) dominates sub-unit boxes: disjoint slivers
+  // can "overlap" there, so no geometric bound is sound for them.
+  const float smin = fminf(fminf(fabsf(aw), fabsf(ah)), fminf(fabsf(bw), fabsf(bh)));
+  if (!(smin >= 1.f)) return false;
+  // The area bound assumes intersection <= min(area).  With (nearly) parallel edges Appendix B can mis-order its
+  // near-duplicate points and report up to a few times the smaller area (see rbox_fast_ok), so it only applies to
+  // skewed pairs.
+  const float sd = 4.f * (as2 * bc2 - ac2 * bs2), cd = 4.f * (ac2 * bc2 + as2 * bs2);
   const float amin = fminf(aarea, barea), amax = fmaxf(aarea, barea);
-  if (amin < thr * 0.999f * amax) return true;
+  if (fminf(fabsf(sd), fabsf(cd)) >= 0.02f && amin < thr * 0.999f * amax) return true;
   const float dx = bcx - acx, dy = bcy - acy;
   // half-extent vectors: w-axis (c2*w, -s2*w), h-axis (s2*h, c2*h)   [c2 = cos/2, s2 = sin/2]
   const float awx = ac2 * aw, awy = -as2 * aw, ahx = as2 * ah, ahy = ac2 * ah;
@@ -90,7 +111,7 @@ __device__ __forceinline__ bool rbox_cannot_exceed(float acx, float acy, float a
   return false;
 }
 
-__device__ __forceinline__ void rcorners(float cx, float cy, const RPrep& b, V2 (&p)[4]) {
+RY_RDEV void rcorners(float cx, float cy, const RPrep& b, V2 (&p)[4]) {
   p[0].x = fa(fa(cx, fm(b.s2, b.h)), fm(b.c2, b.w));
   p[0].y = fs(fa(cy, fm(b.c2, b.h)), fm(b.s2, b.w));
   p[1].x = fa(fs(cx, fm(b.s2, b.h)), fm(b.c2, b.w));
@@ -101,7 +122,7 @@ __device__ __forceinline__ void rcorners(float cx, float cy, const RPrep& b, V2 
   p[3].y = fs(fm(2.f, cy), p[1].y);
 }
 
-__device__ __noinline__ float rbox_iou_full(const RPrep& A, const RPrep& B) {
+RY_RDEV_NOINLINE float rbox_iou_full(const RPrep& A, const RPrep& B) {
   const double EPS = 1e-5;
   // step 1: shift both centres by the pair midpoint
   double sx = (double)fa(A.cx, B.cx) / 2.0, sy = (double)fa(A.cy, B.cy) / 2.0;
@@ -207,9 +228,9 @@ __device__ __noinline__ float rbox_iou_full(const RPrep& A, const RPrep& B) {
 }
 
 // Fast fp32 estimate of the same skew IoU by Sutherland-Hodgman clipping of A's rectangle against B's four edges
-// (<= 8 vertices, no sort, no fp64).  It is NOT bit-identical with Appendix B; the NMS kernel only trusts it when the
-// estimate is far (> 2e-3) from the threshold and re-runs rbox_iou_full otherwise, so decisions stay exact.
-__device__ __forceinline__ float rbox_iou_fast(const RPrep& A, const RPrep& B) {
+// (<= 8 vertices, no sort, no fp64).  It is NOT bit-identical with Appendix B; the NMS kernel only trusts it under
+// rbox_fast_ok() and when the estimate is farther than kFastBand from the threshold (see rbox_iou_exceeds).
+RY_RDEV float rbox_iou_fast(const RPrep& A, const RPrep& B) {
   if (A.area < 1e-12f || B.area < 1e-12f) return 0.f;
   // work in A-centred coordinates
   V2 pa[4], pb[4];
@@ -253,8 +274,79 @@ __device__ __forceinline__ float rbox_iou_fast(const RPrep& A, const RPrep& B) {
   return inter / (A.area + B.area - inter);
 }
 
+// When may the NMS decision trust the fast estimate?  Two error sources separate it from Appendix B:
+//   (1) Appendix B itself departs from the true polygon overlap through its absolute EPS = 1e-5 slack on SQUARED-length
+//       quantities (a corner up to 1e-5/|edge| outside still counts as inside) and the 1e-6 / 1e-8 hull cut-offs:
+//       negligible once every side is >= 1 unit (<= 4e-5 units of slack), unbounded for sub-unit boxes;
+//   (2) the estimate's own fp32 rounding, ~C * 2^-24 * L^2 of absolute area error with L the coordinate range in the
+//       A-centred frame (<= 2 (reach_A + reach_B)), to be compared with the union >= max(area).
+// The gate keeps both below ~3e-4 of IoU (tests/test_rotated_iou_host.py measures the worst case over adversarial
+// pairs: thin slivers, sub-unit boxes, near-coincident edges, near-duplicates, 4096*cls offsets); everything else,
+// and every estimate within kFastBand of the threshold, takes the bit-exact path.
+constexpr float kFastBand = 2e-3f;
+constexpr float kFastMinSkew = 0.02f;     // |sin| / |cos| of the angle between the boxes (~1.15 degrees)
+RY_RDEV bool rbox_fast_ok(const RPrep& A, const RPrep& B) {
+  const float sa = fminf(fabsf(A.w), fabsf(A.h)), sb = fminf(fabsf(B.w), fabsf(B.h));
+  if (!(sa >= 1.f && sb >= 1.f)) return false;
+  const float L = 2.f * (A.reach + B.reach);
+  if (!(L * L <= 256.f * fmaxf(A.area, B.area))) return false;
+  // (3) near-parallel edges: Appendix B intersects (almost) coincident edge lines with a tiny determinant and then
+  //     de-duplicates / orders the resulting points with absolute cut-offs, which for near-duplicate boxes yields
+  //     "IoU" values such as 1/3, 3 or 55 where the geometric overlap is ~1 (tests/test_rotated_iou_host.py shows
+  //     them).  Those values ARE the frozen spec, so such pairs must take the bit-exact path.  Edges of the two
+  //     rectangles are parallel when sin or cos of the angle difference vanishes.
+  const float sd = 4.f * (A.s2 * B.c2 - A.c2 * B.s2), cd = 4.f * (A.c2 * B.c2 + A.s2 * B.s2);
+  if (!(fminf(fabsf(sd), fabsf(cd)) >= kFastMinSkew)) return false;
+  // (4) a corner of one box (almost) on an edge line of the other: two or three of Appendix B's candidate points then
+  //     (almost) coincide, its Graham scan orders the near-duplicate of the start point by a meaningless angle and
+  //     drops real vertices (observed: 0.318 where the overlap is 0.877, corner 3e-5 px from the edge).  The damage
+  //     stops ~2.5e-5 of the box size away from the singular position; the gate keeps 40x that distance.
+  const float delta = 1e-3f * (A.reach + B.reach);
+  const float dx = A.cx - B.cx, dy = A.cy - B.cy;
+  // half-extent vectors (see rcorners): w-axis (c2 w, -s2 w), h-axis (s2 h, c2 h); unit axes are 2*(c2, -s2), 2*(s2, c2)
+  const float apx = A.c2 * A.w, apy = -A.s2 * A.w, aqx = A.s2 * A.h, aqy = A.c2 * A.h;
+  const float bpx = B.c2 * B.w, bpy = -B.s2 * B.w, bqx = B.s2 * B.h, bqy = B.c2 * B.h;
+  {  // corners of A in B's frame
+    const float ux = 2.f * B.c2, uy = -2.f * B.s2, vx = 2.f * B.s2, vy = 2.f * B.c2;
+    const float uD = ux * dx + uy * dy, uP = ux * apx + uy * apy, uQ = ux * aqx + uy * aqy;
+    const float vD = vx * dx + vy * dy, vP = vx * apx + vy * apy, vQ = vx * aqx + vy * aqy;
+    const float hw = 0.5f * fabsf(B.w), hh = 0.5f * fabsf(B.h);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float sp = (k & 1) ? -1.f : 1.f, sq = (k & 2) ? -1.f : 1.f;
+      if (fabsf(fabsf(uD + sp * uP + sq * uQ) - hw) < delta) return false;
+      if (fabsf(fabsf(vD + sp * vP + sq * vQ) - hh) < delta) return false;
+    }
+  }
+  {  // corners of B in A's frame
+    const float ux = 2.f * A.c2, uy = -2.f * A.s2, vx = 2.f * A.s2, vy = 2.f * A.c2;
+    const float uD = -(ux * dx + uy * dy), uP = ux * bpx + uy * bpy, uQ = ux * bqx + uy * bqy;
+    const float vD = -(vx * dx + vy * dy), vP = vx * bpx + vy * bpy, vQ = vx * bqx + vy * bqy;
+    const float hw = 0.5f * fabsf(A.w), hh = 0.5f * fabsf(A.h);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float sp = (k & 1) ? -1.f : 1.f, sq = (k & 2) ? -1.f : 1.f;
+      if (fabsf(fabsf(uD + sp * uP + sq * uQ) - hw) < delta) return false;
+      if (fabsf(fabsf(vD + sp * vP + sq * vQ) - hh) < delta) return false;
+    }
+  }
+  return true;
+}
+
+// NMS decision "IoU(A, B) > thr" for a pair that survived the early-outs: bit-identical with Appendix B.
+RY_RDEV bool rbox_iou_exceeds(const RPrep& A, const RPrep& B, float thr) {
+  float v;
+  if (rbox_fast_ok(A, B)) {
+    v = rbox_iou_fast(A, B);
+    if (fabsf(v - thr) <= kFastBand) v = rbox_iou_full(A, B);
+  } else {
+    v = rbox_iou_full(A, B);
+  }
+  return v > thr;
+}
+
 // IoU(A, B) with A = the higher-scored ("row") box, B = the candidate ("column") box.
-__device__ __forceinline__ float rbox_iou(const RPrep& A, const RPrep& B) {
+RY_RDEV float rbox_iou(const RPrep& A, const RPrep& B) {
   if (rbox_far(A, B)) return 0.f;
   return rbox_iou_full(A, B);
 }

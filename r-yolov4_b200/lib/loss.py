@@ -25,9 +25,16 @@ def _run_loss(cfg, targets, levels, need_grad):
     mode, na, nc, anchors, hyp = cfg
     lib = L.lib()
     dev = levels[0].device
+    for p in levels:
+        L.require_cuda(p, "outputs")
+        if p.dtype != torch.float32:
+            raise L.RyoloError(f"outputs must be float32 head levels (got {p.dtype}): the loss kernels read fp32")
+    T = targets.shape[0]
+    if T and targets.device != dev:
+        raise L.RyoloError(f"targets are on {targets.device} but the head levels are on {dev} (train.py:187 moves "
+                           "them to the model's device)")
     lv = [p.detach().contiguous() for p in levels]
     B = lv[0].shape[0]
-    T = targets.shape[0]
     tg = targets.detach().contiguous().float() if T else torch.zeros((0, 187 if mode == 0 else 7), device=dev)
     ghw = _grid_hw(lv)
     nb = lib.ryolo_loss_workspace(B, na, ghw, T)
@@ -141,6 +148,7 @@ class _ComputeLoss:
     def build_targets(self, p, targets):
         """Reference-format assignment tuples (bit-exact indices, reference emission order)."""
         lib = L.lib()
+        L.require_cuda(targets, "targets")
         dev = targets.device
         T = targets.shape[0]
         B = p[0].shape[0]

@@ -30,6 +30,8 @@ class Ctx:
         self._partial = torch.zeros(4 * 2048, dtype=torch.float32, device=device) if training else None
         self._counters = torch.zeros(model._bn_layers, dtype=torch.int32, device=device) if training else None
         self._ctr_off = 0
+        if training:
+            BN_EPOCH[0] += 1      # the fused conv epilogue rewrites running statistics through raw pointers
 
     def new(self, N, H, W, C):
         return Act.empty(N, H, W, C, self.device)
@@ -41,6 +43,7 @@ class Ctx:
 
 
 WEIGHT_EPOCH = [0]     # bumped by whoever rewrites parameters through raw pointers (TrainStep's SGD kernel)
+BN_EPOCH = [0]         # bumped by every training-mode forward: running statistics change without a torch version bump
 
 
 class _Packed:
@@ -61,7 +64,7 @@ class _Packed:
 
 def _bn_eval_affine(bn, cache):
     key = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version,
-           bn.weight.data_ptr(), WEIGHT_EPOCH[0], bn.num_batches_tracked.data_ptr())
+           bn.weight.data_ptr(), WEIGHT_EPOCH[0], BN_EPOCH[0], bn.num_batches_tracked.data_ptr())
     if cache.get("key") != key:
         scale = bn.weight.data.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
         cache["scale"], cache["shift"] = scale.contiguous(), (bn.bias.data.float() - bn.running_mean.float() * scale)

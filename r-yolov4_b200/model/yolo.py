@@ -56,7 +56,7 @@ class Yolo(nn.Module):
         self.yolo = layer
         self.autograd = True          # False: the caller drives Yolo.backward() itself (TrainStep)
         self._flat = self._flat_grad = self._grad_views = None
-        self._pack_table = None
+        self._pack_table = self._pack_params = self._pack_sig = None
         self._bn_channels = sum(m.num_features for m in self.modules() if isinstance(m, nn.BatchNorm2d))
         self._bn_layers = sum(1 for m in self.modules() if isinstance(m, nn.BatchNorm2d))
         self.last_ctx = None
@@ -70,7 +70,17 @@ class Yolo(nn.Module):
             heads = self._run(i, train)
         return self.yolo(list(heads), training)
 
+    def _pack_signature(self):
+        """Cheap staleness key of the pinned bf16 operand copies: any torch-visible write to a conv weight
+        (load_state_dict, .apply(weights_init_normal), an EMA swap-in, a re-homed .data) changes it.  Writers that go
+        through raw pointers (TrainStep's optimizer kernels) repack themselves and bump WEIGHT_EPOCH."""
+        from .blocks import WEIGHT_EPOCH
+        return (sum(p._version for p in self._pack_params), WEIGHT_EPOCH[0],
+                tuple(p.data_ptr() for p in self._pack_params[:4]))
+
     def _run(self, i, train):
+        if getattr(self, "_pack_params", None) is not None and self._pack_signature() != self._pack_sig:
+            self.repack_weights()
         ctx = Ctx(self, train, i.device)
         with torch.no_grad():
             d3, d4, d5 = self.backbone(ctx, i)
@@ -185,6 +195,7 @@ class Yolo(nn.Module):
         L_.check(L_.lib().ryolo_pack_weights_multi(L_.ptr(self._pack_table), len(self._pack_meta), self._pack_total,
                                                    L_.stream()))
         L_.count(1)
+        self._pack_sig = self._pack_signature()
 
     @staticmethod
     def _make_anchors(strides, anchors):

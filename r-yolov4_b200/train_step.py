@@ -55,7 +55,7 @@ class TrainStep:
             ops.sgd_step(self.flat, self.grad, self.buf, self.lr, self.momentum, self.wd, self.nesterov, self.first)
         self.first = False
         blocks.WEIGHT_EPOCH[0] += 1          # BN-eval affine caches are stale now
-        self.model.repack_weights()          # refresh every bf16 operand copy in one launch
+        self.model.repack_weights()          # refresh every bf16 operand copy in one launch (re-keys the staleness check)
 
     def __call__(self, imgs, targets):
         self.zero_grad()

@@ -306,3 +306,139 @@ def test_v7_implicit_head_forward_backward():
     for k, p in neck.named_parameters():
         e = _l2(grads[id(p)].cpu(), sd[k].grad)
         assert e < 6e-2, (k, e)
+
+
+def _oracle_levels(sd, img, ver, mode, nc, emulate_bf16):
+    from oracle import hotpath as hp
+    from oracle import model_cpu
+    net = model_cpu.Net(sd, True, emulate_bf16=emulate_bf16)
+    d3, d4, d5 = getattr(net, "backbone_" + ver[-2:])(img)
+    heads = getattr(net, "neck_" + ver[-2:])(d5, d4, d3)
+    na, ch = (3, nc + 185) if mode == "csl" else (18, nc + 6)
+    return [hp.head_to_grid(h, na, ch) for h in heads], net.new_stats
+
+
+def _plog(rec):
+    import json
+    import os
+    from tests.util import ROOT
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", "model_backward_parity.jsonl"), "a") as f:
+        f.write(json.dumps(rec) + "\n")
+
+
+@pytest.mark.parametrize("ver,mode,nc", [("yolov4", "csl", 2), ("yolov7", "csl", 16), ("yolov5", "csl", 2),
+                                         ("yolov4", "kfiou", 2)])
+def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc):
+    """Yolo.backward (tape walk: concat slices across blocks, up-sampling paths, GradStore accumulation, side-stream
+    wgrad, flat-gradient unpack) against torch autograd on the oracle's bf16-emulating restatement of the WHOLE network
+    (oracle/model_cpu.py, pinned to the reference's forward and backward by tests/test_config1.py), per parameter
+    tensor.  Fixture: 256x256, bs=4 so that every BatchNorm sees >= 256 samples per channel; the SAME upstream gradient
+    (the product's fused CSL/KFIoU loss gradient on its own head tensors) is pushed through both."""
+    import os
+    R, m, img, tg, crit = _model_and_batch(ver, mode, nc, S=256, bs=4)
+    tg = make_targets(5, 4, 12, nc, mode == "csl").cuda()
+    img = img.bfloat16().float()                        # both sides see bf16-exact pixels (the stem stores bf16)
+    pn = {k for k, _ in m.named_parameters()}
+    sd = {k: v.detach().cpu().clone().requires_grad_(k in pn) for k, v in m.state_dict().items()}
+    m.autograd = False
+    flat, grad = m.flatten_parameters()
+    grad.zero_()
+    levels = m(img, training=True)
+    items, dl = crit.value_and_grad(levels, tg)
+    m.backward(dl)
+    torch.cuda.synchronize()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    ref_levels, _ = _oracle_levels(sd, img.cpu(), ver, mode, nc, True)
+    fwd = [_l2(a.cpu(), b.detach()) for a, b in zip(levels, ref_levels)]
+    torch.autograd.backward(ref_levels, [d.cpu() for d in dl])
+    errs = {k: _l2(p.grad.cpu(), sd[k].grad) for k, p in m.named_parameters()}
+    e = torch.tensor(list(errs.values()))
+    worst = sorted(errs, key=errs.get)[-5:]
+    rec = dict(case=f"{ver}_{mode}", fwd_rel_l2=fwd, n=len(errs), median=float(e.median()), p95=float(e.quantile(0.95)),
+               max=float(e.max()), worst={k: errs[k] for k in worst})
+    _plog(rec)
+    assert max(fwd) < 5e-2, rec
+    # tolerance: bf16 storage of activations and activation gradients (2^-9 per rounding, ~60 roundings deep) on both
+    # sides, decided independently at every LeakyReLU kink / max-pool tie; a dropped or mis-routed branch gradient
+    # shows as an O(1) error on every tensor upstream of it
+    assert float(e.median()) < 4e-2 and float(e.quantile(0.95)) < 8e-2 and float(e.max()) < 0.2, rec
+
+
+def test_loss_curve_bf16_gpu_vs_fp32_oracle_20_steps():
+    """20 SGD steps (lr .01, momentum .937, nesterov; train.py:156) of yolov4/csl on a fixed batch: the B200 path
+    (bf16 storage / fp32 accumulate) against the fp32 oracle port of the reference step (torch CPU autograd +
+    torch.optim.SGD), same initial weights.  The curves must stay together (convergence equivalence is the
+    end-to-end criterion for the conv stack, the 1e-4 bar applies per kernel)."""
+    import os
+    from oracle import hotpath as hp
+    R, m, img, tg, crit = _model_and_batch("yolov4", "csl", 2, S=128, bs=4)
+    tg = make_targets(9, 4, 10, 2, True).cuda()
+    pn = {k for k, _ in m.named_parameters()}
+    sd = {k: v.detach().cpu().clone().requires_grad_(k in pn) for k, v in m.state_dict().items()}
+    step = R.TrainStep(m, crit, lr=0.01, momentum=0.937, nesterov=True)
+    gpu = [float(step(img, tg)[4]) for _ in range(20)]
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    params = [sd[k] for k in sd if k in pn]
+    opt = torch.optim.SGD(params, lr=0.01, momentum=0.937, nesterov=True)
+    an = hp.make_anchors(CFG["anchors"])
+    cpu = []
+    for _ in range(20):
+        opt.zero_grad()
+        lv, stats = _oracle_levels(sd, img.cpu(), "yolov4", "csl", 2, False)
+        loss, it = hp.csl_loss(lv, tg.cpu(), an, 2, HYP)
+        loss.backward()
+        opt.step()
+        with torch.no_grad():
+            for k, v in stats.items():
+                sd[k].copy_(v)
+        cpu.append(it["total_loss"])
+    rel = [abs(a - b) / b for a, b in zip(gpu, cpu)]
+    _plog(dict(case="loss_curve_v4_csl_128_bs4", gpu=gpu, cpu=cpu, max_rel=max(rel)))
+    assert cpu[-1] < 0.9 * cpu[0] and gpu[-1] < 0.9 * gpu[0], (gpu, cpu)
+    assert rel[0] < 1e-2, rel                  # same weights, one forward: bf16 storage only
+    assert max(rel) < 5e-2, (gpu, cpu)         # 20 steps later the two trajectories are still the same curve
+
+
+def test_parameter_writes_after_trainstep_refresh_the_packed_operands():
+    """After TrainStep pinned the bf16 operand copies, any torch-visible parameter write (load_state_dict to resume a
+    checkpoint, .apply(weights_init_normal), an EMA swap-in) must reach the kernels: eval output == a freshly built
+    model with the same state dict, bit for bit.  Likewise the eval-mode BN affine cache must see running statistics
+    that a training-mode forward rewrote through raw pointers (no optimizer step in between)."""
+    import ryolo_b200 as R
+    from tests.util import winit
+    R_, m, img, tg, crit = _model_and_batch("yolov4", "csl", 2, S=96, bs=2)
+    step = R.TrainStep(m, crit, lr=0.01)
+    step(img, tg)
+    torch.manual_seed(3)
+    other = R.Yolo(2, CFG, "csl", "yolov4")
+    other.apply(winit)
+    sd = {k: v.clone() for k, v in other.state_dict().items()}
+    m.load_state_dict(sd)                                   # resume-style load AFTER TrainStep was built
+    m.eval()
+    fresh = other.cuda().eval()
+    with torch.no_grad():
+        a, ia = m(img, training=False)
+        b, ib = fresh(img, training=False)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert torch.equal(ia, ib)
+    # the first resumed step computes forward / dgrad / wgrad from the loaded weights too
+    m.train()
+    fresh.train()
+    l1 = m(img, training=True)
+    fresh.autograd = False
+    l2 = fresh(img, training=True)
+    for x, y in zip(l1, l2):
+        assert torch.equal(x.detach(), y)
+    # eval -> train forward (running statistics move, no optimizer step) -> eval
+    m.eval()
+    with torch.no_grad():
+        c, _ = m(img, training=False)
+    fresh.load_state_dict(m.state_dict())
+    fresh.eval()
+    with torch.no_grad():
+        d, _ = fresh(img, training=False)
+    for x, y, z in zip(c, d, a):
+        assert torch.equal(x, y)
+        assert not torch.equal(x, z)

@@ -124,3 +124,60 @@ def test_post_process_idempotent_shapes_at_scale():
         rb[:, 4] = rb[:, 4] / np.pi * 180
         again = R.nms_rotated(rb.cuda(), d[:, 5].cuda(), 0.65)
         assert again.numel() == n[i]
+
+
+@pytest.mark.parametrize("kind", ["normal", "thin", "tiny", "any", "edge", "corner"])
+def test_nms_rotated_adversarial_sets_bit_exact(kind):
+    """Box sets made of adversarial pairs (tests/test_rotated_iou_host.adversarial_pairs: near-duplicates, thin slivers,
+    sub-unit boxes, flush edges, corner-on-edge contacts, 4096*cls offsets): survivor indices must equal the oracle's at
+    the three thresholds the reference uses.  These are the configurations where Appendix B departs from the geometric
+    IoU (values such as 1/3, 3, 55 for near-duplicates), i.e. where a fast-path shortcut would show."""
+    import ryolo_b200 as R
+    from tests.test_rotated_iou_host import THRESHOLDS, adversarial_pairs
+    rng = np.random.default_rng(len(kind))
+    A, B = adversarial_pairs(rng, 1200, kind)
+    boxes = torch.from_numpy(np.concatenate([A, B], 0))
+    perm = torch.from_numpy(rng.permutation(boxes.shape[0]))
+    boxes = boxes[perm].contiguous()
+    scores = torch.from_numpy(rng.random(boxes.shape[0]).astype(np.float32))
+    scores[::11] = scores[0]
+    for thr in THRESHOLDS:
+        ref = orot.nms_rotated(boxes, scores, thr)
+        out = R.nms_rotated(boxes.cuda(), scores.cuda(), thr).cpu()
+        assert torch.equal(out, ref), (kind, thr, out.numel(), ref.numel())
+    # pairwise matrix on the same boxes: bitwise
+    sub = boxes[:400]
+    assert torch.equal(R.pairwise_iou_rotated(sub.cuda(), sub.cuda()).cpu(), orot.pairwise_iou_rotated(sub, sub))
+
+
+def test_post_process_full_config5_bit_exact_vs_oracle():
+    """BASELINE configs[4] at full size: 64 images x 100 000 candidate rows (test.py:269-270 thresholds, clustered so
+    that NMS suppresses), survivor rows and detections bit-identical with the oracle for EVERY image.  The oracle's
+    greedy loop is single-threaded C++ (like upstream); images run on a thread pool (ctypes releases the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    import ryolo_b200 as R
+    gen = torch.Generator().manual_seed(64)
+    B, Rr, nc = 64, 100000, 2
+    pred = _synthetic_pred(gen, B, Rr, nc, True)
+    pred[:, ::9, 5] = pred[:, :1, 5]                        # many exactly tied scores in every image
+    pred[:, ::9, 6:] = pred[:, :1, 6:]
+    conf, iou = 0.001, 0.65
+    p = pred.clone().cuda()
+    outs, rows = R.post_process(p, conf, iou, return_indices=True)
+    torch.cuda.synchronize()
+
+    def one(i):
+        x = pred[i:i + 1].clone()
+        o, r = hp.post_process(x, conf, iou, return_indices=True)
+        return x[0], o[0], r[0]
+
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 1)) as ex:
+        refs = list(ex.map(one, range(B)))
+    kept = 0
+    for i, (mut, o, r) in enumerate(refs):
+        assert torch.equal(rows[i].cpu(), r), f"survivor rows differ for image {i}"
+        assert torch.equal(outs[i].cpu(), o), f"detections differ for image {i}"
+        assert torch.equal(p[i].cpu(), mut), f"in-place cls*=obj differs for image {i}"
+        kept += r.numel()
+    assert 0 < kept <= 64 * 1500
