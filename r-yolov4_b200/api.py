@@ -1,9 +1,8 @@
 """Public call surface: the three Python callables the reference's train.py /
 test.py / detect.py use, under their real names plus the aliases BASELINE.json's north_star uses."""
 from ._lib import RyoloError, SO_PATH, lib
-from .lib.general import (encode_labels, rescale_boxes, xywh2xyxy, xywha2xyxyxyxy, xyxyxyxy2xywha, nms_rotated, non_max_suppression, norm_angle, pairwise_iou_rotated, post_process,
-                          post_process_device)
-from .lib import labels_io
+from .lib.general import (encode_labels, xyxyxyxy2xywha, nms_rotated, non_max_suppression, norm_angle,
+                          pairwise_iou_rotated, post_process, post_process_device)
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
 from .lib.metrics import ap_per_class, calculate_eval_stats, compute_ap, fitness, get_batch_statistics
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
@@ -24,4 +23,6 @@ def compute_loss(model, hyp, mode="csl"):
 
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
-           "encode_labels", "xyxyxyxy2xywha", "xywha2xyxyxyxy", "xywh2xyxy", "rescale_boxes", "labels_io", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle", "get_batch_statistics", "ap_per_class", "compute_ap", "calculate_eval_stats", "fitness", "RyoloError", "SO_PATH", "lib"]
+           "encode_labels", "xyxyxyxy2xywha", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle",
+           "get_batch_statistics", "ap_per_class", "compute_ap", "calculate_eval_stats", "fitness", "RyoloError", "SO_PATH",
+           "lib"]

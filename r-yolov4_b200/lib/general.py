@@ -123,51 +123,3 @@ def xyxyxyxy2xywha(boxes):
     L.require_cuda(boxes, "boxes")
     polys = torch.cat((boxes.new_zeros(boxes.shape[0], 2), boxes.float()), 1)
     return encode_labels(polys, csl=False)[:, 2:]
-
-
-def xywh2xyxy(x):
-    """(x, y, w, h) -> (x1, y1, x2, y2)  (lib/general.py:23-38)."""
-    y = x.new_empty(x.shape)
-    y[..., 0] = x[..., 0] - x[..., 2] / 2
-    y[..., 1] = x[..., 1] - x[..., 3] / 2
-    y[..., 2] = x[..., 0] + x[..., 2] / 2
-    y[..., 3] = x[..., 1] + x[..., 3] / 2
-    return y
-
-
-def xywha2xyxyxyxy(boxes):
-    """(x, y, w, h, theta) -> [N, 4, 2] corner points, drop-in for lib/general.py:41-67 without its per-box Python loop
-    and cv2 call: cv2.getRotationMatrix2D(centre, deg, 1) = [[a, b, (1-a)cx - b cy], [-b, a, b cx + (1-a) cy]] with
-    a = cos, b = sin evaluated in double and stored as float32, as the reference does.  Works on any device."""
-    x, y, w, h, theta = boxes.unbind(dim=-1)
-    ang = (theta * 180 / math.pi).double() * math.pi / 180          # the reference's float32 degrees, cv2's double radians
-    a, b = torch.cos(ang), torch.sin(ang)
-    cx, cy = x.double(), y.double()
-    Rs = torch.stack((a, b, (1 - a) * cx - b * cy, -b, a, b * cx + (1 - a) * cy), -1).view(-1, 2, 3).to(torch.float32)
-    x1, y1 = x - h / 2, y - w / 2
-    x2, y2 = x + h / 2, y - w / 2
-    x3, y3 = x + h / 2, y + w / 2
-    x4, y4 = x - h / 2, y + w / 2
-    p = torch.stack((x1, y1, x2, y2, x3, y3, x4, y4), dim=-1).reshape(-1, 4, 2)
-    p = torch.cat((p, torch.ones((p.shape[0], 4, 1), dtype=p.dtype, device=p.device)), dim=-1)
-    return torch.bmm(p, Rs.permute((0, 2, 1)))
-
-
-def rescale_boxes(boxes, current_dim, original_shape):
-    """Undo pad_to_square + resize on [N, >=4] (x, y, w, h, ...) boxes, in place like lib/plot.py:9-29."""
-    orig_h, orig_w = original_shape
-    pad_x = max(orig_h - orig_w, 0) * (current_dim / max(original_shape))
-    pad_y = max(orig_w - orig_h, 0) * (current_dim / max(original_shape))
-    unpad_h = current_dim - pad_y
-    unpad_w = current_dim - pad_x
-    boxes[:, :4] = xywh2xyxy(boxes[:, :4])
-    x1, y1, x2, y2 = boxes[:, 0], boxes[:, 1], boxes[:, 2], boxes[:, 3]
-    x1 = ((x1 - pad_x // 2) / unpad_w) * orig_w
-    y1 = ((y1 - pad_y // 2) / unpad_h) * orig_h
-    x2 = ((x2 - pad_x // 2) / unpad_w) * orig_w
-    y2 = ((y2 - pad_y // 2) / unpad_h) * orig_h
-    boxes[:, 0] = (x1 + x2) / 2
-    boxes[:, 1] = (y1 + y2) / 2
-    boxes[:, 2] = (x2 - x1)
-    boxes[:, 3] = (y2 - y1)
-    return boxes

@@ -327,18 +327,46 @@ def _plog(rec):
         f.write(json.dumps(rec) + "\n")
 
 
-@pytest.mark.parametrize("ver,mode,nc", [("yolov4", "csl", 2), ("yolov7", "csl", 16), ("yolov5", "csl", 2),
-                                         ("yolov4", "kfiou", 2)])
-def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc):
+def _calm(m, g=0.1):
+    """Well-conditioned fixture.  At the reference's init (train.py:28-33) a train-mode BatchNorm stack this deep is
+    chaotic: 1e-6 of input noise grows to 1e-3 at the heads in pure fp32, bf16 storage (2^-9 per layer) saturates to
+    O(1) — measured on the oracle itself, fp32 vs its own bf16 emulation: 0.6-0.9 relative L2 — so no
+    reduced-precision implementation can be compared end to end there.  Small BatchNorm gains keep Mish / SiLU in their
+    near-linear range and a positive shift keeps LeakyReLU off its kink: perturbations then grow ~1x per layer and a
+    whole-network comparison becomes meaningful (0.5 % at the heads).  The wiring under test — concat slices, residual
+    and up-sampling paths, gradient accumulation — does not depend on the parameter values."""
+    from ryolo_b200.model.blocks import Conv, RepConv
+    gen = torch.Generator().manual_seed(0)
+    with torch.no_grad():
+        for mod in m.modules():
+            bns = []
+            if isinstance(mod, Conv) and mod.has_bn:
+                bns.append((mod.conv[1], 4.0 * g if mod.act == "leaky" else 0.0))
+            elif isinstance(mod, RepConv):
+                bns += [(mod.rbr_dense[1], 0.0), (mod.rbr_1x1[1], 0.0)]
+            for bn, shift in bns:
+                bn.weight.copy_(g * (1 + 0.1 * torch.randn(bn.weight.shape, generator=gen)))
+                bn.bias.copy_(shift + 0.02 * torch.randn(bn.bias.shape, generator=gen))
+    return m
+
+
+@pytest.mark.parametrize("ver,mode,nc,only", [("yolov4", "csl", 2, None), ("yolov7", "csl", 16, None),
+                                              ("yolov5", "csl", 2, None), ("yolov4", "kfiou", 2, None),
+                                              ("yolov4", "csl", 2, 0), ("yolov4", "csl", 2, 1), ("yolov4", "csl", 2, 2),
+                                              ("yolov7", "csl", 16, 0), ("yolov7", "csl", 16, 2)])
+def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc, only):
     """Yolo.backward (tape walk: concat slices across blocks, up-sampling paths, GradStore accumulation, side-stream
     wgrad, flat-gradient unpack) against torch autograd on the oracle's bf16-emulating restatement of the WHOLE network
-    (oracle/model_cpu.py, pinned to the reference's forward and backward by tests/test_config1.py), per parameter
-    tensor.  Fixture: 256x256, bs=4 so that every BatchNorm sees >= 256 samples per channel; the SAME upstream gradient
-    (the product's fused CSL/KFIoU loss gradient on its own head tensors) is pushed through both."""
+    (oracle/model_cpu.py, pinned to the reference's forward AND backward by tests/test_config1.py), per parameter
+    tensor, on the calm fixture (see _calm).  256x256, bs=4: every BatchNorm sees >= 256 samples per channel.  The SAME
+    upstream gradient is pushed through both: the product's fused loss gradient on its own head tensors (`only` = None),
+    or that of a single pyramid level (`only` = 0/1/2), which isolates the PANet paths from one another."""
     import os
-    R, m, img, tg, crit = _model_and_batch(ver, mode, nc, S=256, bs=4)
+    import ryolo_b200 as R
+    m = _calm(det_init(R.Yolo(nc, CFG, mode, ver))).cuda().train()
+    crit = (R.ComputeCSLLoss if mode == "csl" else R.ComputeKFIoULoss)(m, HYP)
+    img = torch.rand(4, 3, 256, 256, generator=torch.Generator().manual_seed(1)).bfloat16().float().cuda()
     tg = make_targets(5, 4, 12, nc, mode == "csl").cuda()
-    img = img.bfloat16().float()                        # both sides see bf16-exact pixels (the stem stores bf16)
     pn = {k for k, _ in m.named_parameters()}
     sd = {k: v.detach().cpu().clone().requires_grad_(k in pn) for k, v in m.state_dict().items()}
     m.autograd = False
@@ -346,23 +374,34 @@ def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc):
     grad.zero_()
     levels = m(img, training=True)
     items, dl = crit.value_and_grad(levels, tg)
+    if only is not None:
+        dl = [d if i == only else torch.zeros_like(d) for i, d in enumerate(dl)]
     m.backward(dl)
     torch.cuda.synchronize()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     ref_levels, _ = _oracle_levels(sd, img.cpu(), ver, mode, nc, True)
     fwd = [_l2(a.cpu(), b.detach()) for a, b in zip(levels, ref_levels)]
     torch.autograd.backward(ref_levels, [d.cpu() for d in dl])
-    errs = {k: _l2(p.grad.cpu(), sd[k].grad) for k, p in m.named_parameters()}
+    errs, dead = {}, []
+    for k, p in m.named_parameters():
+        r = sd[k].grad
+        if r is None or float(r.abs().max()) == 0.0:          # not upstream of this level
+            assert float(p.grad.abs().max()) == 0.0, k
+            dead.append(k)
+            continue
+        errs[k] = _l2(p.grad.cpu(), r)
     e = torch.tensor(list(errs.values()))
     worst = sorted(errs, key=errs.get)[-5:]
-    rec = dict(case=f"{ver}_{mode}", fwd_rel_l2=fwd, n=len(errs), median=float(e.median()), p95=float(e.quantile(0.95)),
-               max=float(e.max()), worst={k: errs[k] for k in worst})
+    rec = dict(case=f"{ver}_{mode}_level{only}", fwd_rel_l2=fwd, n=len(errs), untouched=len(dead),
+               median=float(e.median()), p95=float(e.quantile(0.95)), max=float(e.max()),
+               worst={k: errs[k] for k in worst})
     _plog(rec)
-    assert max(fwd) < 5e-2, rec
-    # tolerance: bf16 storage of activations and activation gradients (2^-9 per rounding, ~60 roundings deep) on both
-    # sides, decided independently at every LeakyReLU kink / max-pool tie; a dropped or mis-routed branch gradient
-    # shows as an O(1) error on every tensor upstream of it
-    assert float(e.median()) < 4e-2 and float(e.quantile(0.95)) < 8e-2 and float(e.max()) < 0.2, rec
+    assert max(fwd) < 3e-2, rec
+    # bf16 storage of activations / activation gradients on both sides (the oracle emulates the forward storage points
+    # only), max-pool arg-max ties decided on values that differ by an ulp: the oracle's own fp32-vs-emulated spread on
+    # this fixture is 0.06-0.14 median, 0.2-0.27 p95.  A dropped or mis-routed branch gradient is an O(1) error on every
+    # tensor upstream of it.
+    assert float(e.median()) < 0.1 and float(e.quantile(0.95)) < 0.25 and float(e.max()) < 0.5, rec
 
 
 def test_loss_curve_bf16_gpu_vs_fp32_oracle_20_steps():
