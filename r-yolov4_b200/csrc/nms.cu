@@ -90,8 +90,8 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
     int gi = rb * kTile + i, gj = cb * kTile + j;
     bool live = (gi < gj) && (gj < K);
     if (live && use_reject) {
-      float dx = qx[0][i] - qx[1][j], dy = qy[0][i] - qy[1][j], rr = qr[0][i] + qr[1][j];
-      live = !(dx * dx + dy * dy > rr * rr);
+      live = !rbox_far_soa(qx[0][i], qy[0][i], qw[0][i], qh[0][i], qr[0][i], qx[1][j], qy[1][j], qw[1][j], qh[1][j],
+                           qr[1][j]);
       if (live && use_bounds)
         live = !rbox_cannot_exceed(qx[0][i], qy[0][i], qw[0][i], qh[0][i], qc[0][i], qs[0][i], qa[0][i], qx[1][j],
                                    qy[1][j], qw[1][j], qh[1][j], qc[1][j], qs[1][j], qa[1][j], thr);

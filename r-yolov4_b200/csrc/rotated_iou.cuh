@@ -58,10 +58,26 @@ RY_RDEV RPrep rprep(float cx, float cy, float w, float h, float deg) {
   return r;
 }
 
+// Appendix B shifts both centres by the pair's midpoint before it builds the corners, so each box ends up ~|d|/2 from the
+// origin.  A box whose sides are below the fp32 spacing at that magnitude (ulp(|d|/2) ~ 6e-8 |d|) collapses to a point
+// there; its edge vectors become exactly 0 and the "corner inside" test (0 > -EPS && 0 < 0 + EPS) then accepts EVERY
+// corner of the other box, wherever it is: the frozen spec reports IoU = area ratio >> 1 for such a pair even 80 000
+// units apart (a sub-0.01 px box against any box of another class, 4096*cls offsets).  Geometric early-outs are only
+// sound when both boxes stay resolvable: smallest side > 160 spacings of the centre distance.
+RY_RDEV bool rbox_resolvable(float smin, float dx, float dy) {
+  return smin > 1e-5f * fmaxf(fabsf(dx), fabsf(dy));
+}
+
 // true => the two boxes are certainly disjoint (IoU == 0 exactly under Appendix B)
+RY_RDEV bool rbox_far_soa(float acx, float acy, float aw, float ah, float areach, float bcx, float bcy, float bw,
+                          float bh, float breach) {
+  const float dx = acx - bcx, dy = acy - bcy, rr = areach + breach;
+  if (!(dx * dx + dy * dy > rr * rr)) return false;
+  const float smin = fminf(fminf(fabsf(aw), fabsf(ah)), fminf(fabsf(bw), fabsf(bh)));
+  return rbox_resolvable(smin, dx, dy);
+}
 RY_RDEV bool rbox_far(const RPrep& a, const RPrep& b) {
-  float dx = a.cx - b.cx, dy = a.cy - b.cy, rr = a.reach + b.reach;
-  return dx * dx + dy * dy > rr * rr;
+  return rbox_far_soa(a.cx, a.cy, a.w, a.h, a.reach, b.cx, b.cy, b.w, b.h, b.reach);
 }
 
 // Sound early-outs for the NMS decision  IoU(A,B) > thr  (thr >= 1e-6): true => the reference IoU certainly does not
@@ -75,7 +91,7 @@ RY_RDEV bool rbox_cannot_exceed(float acx, float acy, float aw, float ah, float 
   // Appendix B's absolute EPS = 1e-5 slack (on squared-length quantities) dominates sub-unit boxes: disjoint slivers
   // can "overlap" there, so no geometric bound is sound for them.
   const float smin = fminf(fminf(fabsf(aw), fabsf(ah)), fminf(fabsf(bw), fabsf(bh)));
-  if (!(smin >= 1.f)) return false;
+  if (!(smin >= 1.f) || !rbox_resolvable(smin, bcx - acx, bcy - acy)) return false;
   // The area bound assumes intersection <= min(area).  With (nearly) parallel edges Appendix B can mis-order its
   // near-duplicate points and report up to a few times the smaller area (see rbox_fast_ok), so it only applies to
   // skewed pairs.
@@ -284,10 +300,16 @@ RY_RDEV float rbox_iou_fast(const RPrep& A, const RPrep& B) {
 // pairs: thin slivers, sub-unit boxes, near-coincident edges, near-duplicates, 4096*cls offsets); everything else,
 // and every estimate within kFastBand of the threshold, takes the bit-exact path.
 constexpr float kFastBand = 2e-3f;
-constexpr float kFastMinSkew = 0.02f;     // |sin| / |cos| of the angle between the boxes (~1.15 degrees)
+#ifndef RY_FAST_MIN_SKEW
+#define RY_FAST_MIN_SKEW 0.002f
+#endif
+#ifndef RY_FAST_CORNER_DELTA
+#define RY_FAST_CORNER_DELTA 2.5e-4f
+#endif
+constexpr float kFastMinSkew = RY_FAST_MIN_SKEW;     // |sin| / |cos| of the angle between the boxes (0.002 ~ 0.11 degrees)
 RY_RDEV bool rbox_fast_ok(const RPrep& A, const RPrep& B) {
   const float sa = fminf(fabsf(A.w), fabsf(A.h)), sb = fminf(fabsf(B.w), fabsf(B.h));
-  if (!(sa >= 1.f && sb >= 1.f)) return false;
+  if (!(sa >= 1.f && sb >= 1.f) || !rbox_resolvable(fminf(sa, sb), A.cx - B.cx, A.cy - B.cy)) return false;
   const float L = 2.f * (A.reach + B.reach);
   if (!(L * L <= 256.f * fmaxf(A.area, B.area))) return false;
   // (3) near-parallel edges: Appendix B intersects (almost) coincident edge lines with a tiny determinant and then
@@ -300,8 +322,10 @@ RY_RDEV bool rbox_fast_ok(const RPrep& A, const RPrep& B) {
   // (4) a corner of one box (almost) on an edge line of the other: two or three of Appendix B's candidate points then
   //     (almost) coincide, its Graham scan orders the near-duplicate of the start point by a meaningless angle and
   //     drops real vertices (observed: 0.318 where the overlap is 0.877, corner 3e-5 px from the edge).  The damage
-  //     stops ~2.5e-5 of the box size away from the singular position; the gate keeps 40x that distance.
-  const float delta = 1e-3f * (A.reach + B.reach);
+  //     stops ~2.5e-5 of the box size away from the singular position; the gate keeps 10x that distance (a sweep over
+  //     21.6 M adversarial decisions found no disagreement down to 4x; flush / nearly coincident edges are this case
+  //     too, which is why the skew gate (3) can be two orders of magnitude tighter than the corner gate).
+  const float delta = RY_FAST_CORNER_DELTA * (A.reach + B.reach);
   const float dx = A.cx - B.cx, dy = A.cy - B.cy;
   // half-extent vectors (see rcorners): w-axis (c2 w, -s2 w), h-axis (s2 h, c2 h); unit axes are 2*(c2, -s2), 2*(s2, c2)
   const float apx = A.c2 * A.w, apy = -A.s2 * A.w, aqx = A.s2 * A.h, aqy = A.c2 * A.h;

@@ -163,17 +163,20 @@ class _WgradSink:
         torch.cuda.current_stream().wait_stream(self.side)      # join before anything the GEMMs read is released
         self.keep.clear()
         if self.fused:
-            self.model.unpack_wgrads()
+            if not getattr(self.model, "_bucketed_unpack", False):     # TrainStep unpacks bucket by bucket itself
+                self.model.unpack_wgrads()
             return
         for weight, buf, stem in self.pending:
             Cout, Cin, k, _ = weight.shape
             self.param_grads[id(weight)].add_(ops.wgrad_to_oihw(buf, Cout, Cin, k, stem))
 
 
-def run_backward(model, ctx, dlevels, param_grads, seed=()):
+def run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
     """dlevels: 3 fp32 tensors [B, na, gs, gs, ch] (d loss / d level, strides 8, 16, 32).
     param_grads: dict id(parameter) -> fp32 tensor (same shape) that receives += d loss / d parameter.
-    seed: optional [(activation, gradient Act)] pairs that pre-load output gradients (block-level tests)."""
+    seed: optional [(activation, gradient Act)] pairs that pre-load output gradients (block-level tests).
+    on_entry: optional callback(i, sink) after the i-th tape entry (reverse order) has launched all of its kernels —
+    TrainStep uses it to hand finished gradient buckets to the all-reduce while the backward pass keeps going."""
     from .blocks import Conv
     tape = ctx.tape
     assert tape is not None, "backward needs a training-mode forward"
@@ -185,18 +188,19 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
         G.mark(act)
     sums = torch.zeros(2 * model._bn_channels + 16, dtype=torch.float32, device=dev)
     soff = 0
-    head_i = 2
+    state = {"head_i": 2, "soff": 0}
     na, ch = model.na, model.ch
 
     def pg(p):
         return param_grads[id(p)]
 
-    for e in reversed(tape):
+    def handle(e):
+        soff, head_i = state["soff"], state["head_i"]
         kind = e[0]
         if kind == "head":
             _, mod, x, y, mul = e
             gl = dlevels[head_i]
-            head_i -= 1
+            state["head_i"] = head_i - 1
             conv = mod.conv[0]
             Cout = na * ch
             Cpad = (Cout + 7) // 8 * 8
@@ -214,7 +218,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
         elif kind == "conv":
             _, mod, x, raw, out, residual, scale, shift, mean, invstd = e
             if not G.is_init(out):
-                continue                                   # output never used downstream (cannot happen in these nets)
+                return                                     # output never used downstream (cannot happen in these nets)
             dout = G.view(out)
             if residual is not None:                       # out = residual + act(bn(raw)): identity path
                 _accumulate(G, residual, dout)
@@ -222,7 +226,7 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             C = mod.c2
             ops.bn_act_bwd(dout, raw, scale, shift, mean, invstd, mod.act, sums[soff:soff + 2 * C], raw,
                            pg(bn.weight), pg(bn.bias))     # d raw overwrites raw in place
-            soff += 2 * C
+            state["soff"] = soff + 2 * C
             k, st = (1, 1) if mod.stem else (mod.k, mod.s)
             sink.wgrad(x, raw, C, k, st, mod.conv[0].weight, mod.stem)
             if not mod.stem:
@@ -233,18 +237,18 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             _, mod, x, rd, r1, out, affs = e
             dout = G.view(out)
             _repconv_backward(mod, x, rd, r1, dout, affs, G, sums[soff:soff + 4 * mod.c2], param_grads, sink)
-            soff += 4 * mod.c2
+            state["soff"] = soff + 4 * mod.c2
         elif kind == "maxpool":
             _, src, dst, k, s, p = e
             if not G.is_init(dst):
-                continue
+                return
             gs, acc = G.writable(src)
             ops.maxpool_bwd(src, G.view(dst), k, s, p, gs, acc)
             G.mark(src)
         elif kind == "resize":
             _, src, dst, factor = e
             if not G.is_init(dst):
-                continue
+                return
             gs, acc = G.writable(src)
             if factor == 2:
                 ops.upsample2x_bwd(G.view(dst), gs, acc)
@@ -253,6 +257,11 @@ def run_backward(model, ctx, dlevels, param_grads, seed=()):
             G.mark(src)
         else:
             raise RuntimeError(f"unknown tape entry {kind}")
+
+    for i, e in enumerate(reversed(tape)):
+        handle(e)
+        if on_entry is not None:
+            on_entry(i, sink)
     sink.finish()
     ctx.tape = None            # the tape's raw buffers now hold gradients: a second backward would be wrong
     return G

@@ -109,8 +109,9 @@ class Yolo(nn.Module):
         total = sum(sizes)
         flat = torch.empty(total, dtype=torch.float32, device=dev)
         grad = torch.zeros(total, dtype=torch.float32, device=dev)
-        off, views = 0, {}
+        off, views, self._flat_offsets = 0, {}, {}
         for p, n in zip(params, sizes):
+            self._flat_offsets[id(p)] = (off, p.numel())
             flat[off:off + p.numel()].copy_(p.data.reshape(-1))
             p.data = flat[off:off + p.numel()].view(p.shape)
             g = grad[off:off + p.numel()].view(p.shape)
@@ -179,6 +180,27 @@ class Yolo(nn.Module):
         from .. import _lib as L_
         L_.check(L_.lib().ryolo_unpack_wgrad_multi(L_.ptr(self._wg_table), len(self._pack_meta), self._pack_total,
                                                    L_.stream()))
+        L_.count(1)
+
+    def wgrad_subtable(self, param_ids):
+        """Table for ryolo_unpack_wgrad_multi restricted to the conv weights in `param_ids` (element offsets re-based):
+        lets TrainStep fold one gradient bucket at a time.  Returns (device table, rows, elements) or None."""
+        self.wgrad_scratch()
+        rows = self._wg_table.cpu().numpy()
+        keep = [i for i, p in enumerate(self._pack_params) if id(p) in param_ids]
+        if not keep:
+            return None
+        sub = rows[keep].copy()
+        first = 0
+        for j, i in enumerate(keep):
+            sub[j, 3] = first
+            first += self._pack_params[i].numel()
+        return torch.from_numpy(sub).to(self._flat_grad.device), len(keep), first
+
+    def unpack_wgrads_sub(self, sub):
+        from .. import _lib as L_
+        table, n, total = sub
+        L_.check(L_.lib().ryolo_unpack_wgrad_multi(L_.ptr(table), n, total, L_.stream()))
         L_.count(1)
 
     def repack_weights(self):

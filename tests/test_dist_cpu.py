@@ -39,3 +39,27 @@ def test_gloo_world2(tmp_path):
     out = str(tmp_path / "ok")
     mp.spawn(_worker, args=(2, 29533, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def test_plan_buckets_covers_the_buffer_and_orders_by_readiness():
+    """Host logic of the bucketed all-reduce (train_step.py): contiguous cover of the flat buffer, ~equal bytes, each
+    bucket due when its LAST member is final, flush order = backward order."""
+    import random
+    from ryolo_b200.dist import plan_buckets
+    rnd = random.Random(0)
+    for n, nb in ((1, 4), (5, 3), (327, 4), (327, 1), (40, 8)):
+        sizes = [rnd.choice((8, 64, 4096, 1 << 16)) for _ in range(n)]
+        spans, off = [], 0
+        for s in sizes:
+            spans.append((off, off + s))
+            off += s
+        final = [n - 1 - i + rnd.choice((-2, 0, 3)) for i in range(n)]          # roughly reverse, locally permuted
+        b = plan_buckets(spans, final, nb)
+        assert 1 <= len(b) <= nb
+        assert b[0][1] == off and b[-1][0] == 0
+        for (lo, hi, when, mem), nxt in zip(b, b[1:] + [None]):
+            assert lo == spans[mem[0]][0] and hi == spans[mem[-1]][1]
+            assert when >= max(final[j] for j in mem)
+            if nxt is not None:
+                assert nxt[1] == lo and nxt[2] >= when
+        assert sorted(j for x in b for j in x[3]) == list(range(n))

@@ -379,10 +379,17 @@ def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc, only):
     m.backward(dl)
     torch.cuda.synchronize()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
+    dl_cpu = [d.cpu() for d in dl]
     ref_levels, _ = _oracle_levels(sd, img.cpu(), ver, mode, nc, True)
     fwd = [_l2(a.cpu(), b.detach()) for a, b in zip(levels, ref_levels)]
-    torch.autograd.backward(ref_levels, [d.cpu() for d in dl])
-    errs, dead = {}, []
+    torch.autograd.backward(ref_levels, dl_cpu)
+    # yardstick: the SAME oracle in plain fp32.  Its distance to its own bf16 emulation is the sensitivity of this
+    # network's gradients to bf16 storage of the forward activations alone (BatchNorm backward projects out the
+    # mean / xhat components at ~70 consecutive layers; sub-percent activation differences compound to 10-20 %).
+    sd32 = {k: v.detach().clone().requires_grad_(k in pn) for k, v in sd.items()}
+    lv32, _ = _oracle_levels(sd32, img.cpu(), ver, mode, nc, False)
+    torch.autograd.backward(lv32, dl_cpu)
+    errs, spread, dead = {}, {}, []
     for k, p in m.named_parameters():
         r = sd[k].grad
         if r is None or float(r.abs().max()) == 0.0:          # not upstream of this level
@@ -390,18 +397,24 @@ def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc, only):
             dead.append(k)
             continue
         errs[k] = _l2(p.grad.cpu(), r)
+        spread[k] = _l2(sd32[k].grad, r)
     e = torch.tensor(list(errs.values()))
+    sp = torch.tensor(list(spread.values()))
+    out = [k for k in errs if errs[k] > 3 * spread[k] + 0.15]
     worst = sorted(errs, key=errs.get)[-5:]
     rec = dict(case=f"{ver}_{mode}_level{only}", fwd_rel_l2=fwd, n=len(errs), untouched=len(dead),
                median=float(e.median()), p95=float(e.quantile(0.95)), max=float(e.max()),
-               worst={k: errs[k] for k in worst})
+               oracle_fp32_vs_emulated=dict(median=float(sp.median()), p95=float(sp.quantile(0.95)), max=float(sp.max())),
+               outliers=out, worst={k: (errs[k], spread[k]) for k in worst})
     _plog(rec)
     assert max(fwd) < 3e-2, rec
-    # bf16 storage of activations / activation gradients on both sides (the oracle emulates the forward storage points
-    # only), max-pool arg-max ties decided on values that differ by an ulp: the oracle's own fp32-vs-emulated spread on
-    # this fixture is 0.06-0.14 median, 0.2-0.27 p95.  A dropped or mis-routed branch gradient is an O(1) error on every
-    # tensor upstream of it.
-    assert float(e.median()) < 0.1 and float(e.quantile(0.95)) < 0.25 and float(e.max()) < 0.5, rec
+    # The product must sit as close to the bf16-emulating oracle as that oracle sits to its own fp32 run (x1.5: the
+    # product also stores the activation GRADIENTS in bf16, the emulation does not).  A dropped or mis-routed branch
+    # gradient is an O(1) error on every tensor upstream of it: it moves the median / p95 or shows up as a cluster of
+    # outliers (err > 3x the tensor's own spread + 0.15; BatchNorm-bias sums that cancel to ~0 are allowed 1 %).
+    assert float(e.median()) < 1.5 * float(sp.median()) + 0.03, rec
+    assert float(e.quantile(0.95)) < 1.5 * float(sp.quantile(0.95)) + 0.05, rec
+    assert len(out) <= max(2, len(errs) // 100), rec
 
 
 def test_loss_curve_bf16_gpu_vs_fp32_oracle_20_steps():

@@ -38,9 +38,11 @@ def run_pairs(hr, a, b, thr):
     n = a.shape[0]
     fast, full = np.zeros(n, np.float32), np.zeros(n, np.float32)
     gate, dec = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+    pair = np.zeros(n, np.float32)
     hr.hr_pairs(ctypes.c_int64(n), a.ctypes.data_as(F32P), b.ctypes.data_as(F32P), ctypes.c_float(thr),
                 fast.ctypes.data_as(F32P), full.ctypes.data_as(F32P), gate.ctypes.data_as(U8P),
-                dec.ctypes.data_as(U8P))
+                dec.ctypes.data_as(U8P), pair.ctypes.data_as(F32P))
+    run_pairs.last_pairwise = pair
     return fast, full, gate.astype(bool), dec.astype(bool)
 
 
@@ -65,6 +67,15 @@ def adversarial_pairs(rng, n, kind):
     edge    B shares an edge LINE with A (same axes, one side flush, sizes differ): the area-bound / hull-order trap
     corner  B's corner sits on A's corner or edge, arbitrary relative angle
     Perturbation magnitudes are log-uniform in 1e-7 .. 2; half the pairs carry a 4096*cls offset (lib/general.py:171)."""
+    if kind == "cross":
+        # UNRELATED boxes of wildly different scales at unrelated places (what an NMS set is mostly made of): a
+        # sub-0.01 px box collapses to a point at the magnitude of the midpoint-shifted centres and then "contains"
+        # every corner of the other box (see rbox_resolvable in rotated_iou.cuh)
+        A1, _ = adversarial_pairs(rng, n, "any")
+        B1, _ = adversarial_pairs(rng, n, "any")
+        near = rng.random(n) < 0.3                           # some of them on top of each other
+        B1[near, :2] = A1[near, :2] + (rng.normal(0, 1, (int(near.sum()), 2)) * A1[near, 2:3]).astype(np.float32)
+        return A1, B1
     base = "any" if kind in ("edge", "corner") else kind
     scale = 10 ** rng.uniform(-3, 3, n) if base in ("tiny", "any") else rng.uniform(4, 120, n)
     asp = {"thin": 10 ** rng.uniform(0, 3, n), "any": 10 ** rng.uniform(0, 2.5, n)}.get(base, rng.uniform(1, 4, n))
@@ -117,14 +128,14 @@ def adversarial_pairs(rng, n, kind):
 def test_host_build_of_product_iou_is_bitwise_the_oracle(hr):
     """rbox_iou_full (product source, host build) == oracle/rotated_ops.cpp bit for bit, degenerate regimes included."""
     rng = np.random.default_rng(1)
-    for kind in ("normal", "thin", "tiny", "edge", "corner"):
+    for kind in ("normal", "thin", "tiny", "edge", "corner", "cross"):
         A, B = adversarial_pairs(rng, 4000, kind)
         _, full, _, _ = run_pairs(hr, A, B, 0.4)
         ref = oracle_pairs(A, B)
         assert np.array_equal(full.view(np.uint32), ref.view(np.uint32)), kind
 
 
-@pytest.mark.parametrize("kind", ["normal", "thin", "tiny", "any", "edge", "corner"])
+@pytest.mark.parametrize("kind", ["normal", "thin", "tiny", "any", "edge", "corner", "cross"])
 def test_nms_pair_decisions_match_oracle_on_adversarial_pairs(hr, kind):
     """Every pair decision of nms_mask_kernel's logic (bounding circle -> area / separating-axis bound -> gated fast
     estimate with the exact path inside the band) equals `oracle IoU > thr`; the gated estimate stays >= 20x inside
@@ -137,6 +148,8 @@ def test_nms_pair_decisions_match_oracle_on_adversarial_pairs(hr, kind):
         want = full > thr                      # == the oracle (previous test)
         bad = np.nonzero(dec != want)[0]
         assert bad.size == 0, (kind, thr, bad.size, A[bad[:3]], B[bad[:3]], fast[bad[:3]], full[bad[:3]])
+        pw = run_pairs.last_pairwise           # pairwise_iou_kernel's value (bounding-circle reject, else exact)
+        assert np.array_equal(pw.view(np.uint32), full.view(np.uint32)), (kind, int((pw != full).sum()))
         if gate.any():
             worst = max(worst, float(np.abs(fast - full)[gate].max()))
         near += int((np.abs(full - thr) <= 1e-6).sum())
