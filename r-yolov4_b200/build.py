@@ -25,7 +25,7 @@ SOURCES = {
     "loss.cu": ["--fmad=false"],
     "labels.cu": ["--fmad=false"],
 }
-for _opt in ("conv.cu", "elementwise.cu", "wgrad.cu", "backward.cu"):
+for _opt in ("conv.cu", "elementwise.cu", "wgrad.cu", "backward.cu", "kfloss.cu"):
     if os.path.exists(os.path.join(CSRC, _opt)):
         SOURCES[_opt] = []
 

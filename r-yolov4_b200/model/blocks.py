@@ -377,6 +377,21 @@ class RepConv(nn.Module):
         self._pd, self._p1, self._ad, self._a1 = _Packed(), _Packed(), {}, {}
         self._pdt, self._p1t = _Packed(), _Packed()
 
+    def reparam(self):
+        """(bf16 packed [c2, k*k*c1] weight, fp32 bias[c2]) of the single k x k conv this block equals in eval mode.
+        Cached until a parameter or a running statistic changes."""
+        sd, bd = _bn_eval_affine(self.rbr_dense[1], self._ad)
+        s1, b1 = _bn_eval_affine(self.rbr_1x1[1], self._a1)
+        wd_, w1_ = self.rbr_dense[0].weight, self.rbr_1x1[0].weight
+        key = (self._ad["key"], self._a1["key"], wd_._version, w1_._version, wd_.data_ptr(), w1_.data_ptr())
+        if getattr(self, "_rep_key", None) != key:
+            w = wd_.data.float() * sd.view(-1, 1, 1, 1)
+            c = self.k // 2
+            w[:, :, c, c] += w1_.data.float()[:, :, 0, 0] * s1.view(-1, 1)
+            self._rep = (ops.pack_weights(w), (bd + b1).contiguous())
+            self._rep_key = key
+        return self._rep
+
     def forward(self, ctx, x, out=None):
         if self.rbr_identity is not None:
             raise NotImplementedError("RepConv identity branch is not used by any reference network")
@@ -384,11 +399,11 @@ class RepConv(nn.Module):
         if out is None:
             out = ctx.new(x.N, x.H, x.W, self.c2)
         if not ctx.training:
-            rd = ops.conv2d(x, wd, self.c2, self.k, self.s)
-            r1 = ops.conv2d(x, w1, self.c2, 1, self.s)
-            sd, bd = _bn_eval_affine(self.rbr_dense[1], self._ad)
-            s1, b1 = _bn_eval_affine(self.rbr_1x1[1], self._a1)
-            return ops.scale_shift_act(rd, sd, bd, "swish", out, x2=r1, scale2=s1, shift2=b1)
+            # Inference-time re-parameterisation (RepVGG, the paper model/utils.py:189-191 cites): with BatchNorm folded,
+            #   SiLU(s_d * conv3x3(x) + b_d + s_1 * conv1x1(x) + b_1) = SiLU(conv3x3(x; s_d W_d + pad(s_1 W_1)) + b_d + b_1)
+            # ONE tensor-core launch with the bias + SiLU epilogue instead of two convs and an elementwise pass.
+            wf, bf = self.reparam()
+            return ops.conv2d(x, wf, self.c2, self.k, self.s, out=out, shift=bf, act="swish")
         affs, raws = [], []
         for wgt, kk, bn in ((wd, self.k, self.rbr_dense[1]), (w1, 1, self.rbr_1x1[1])):
             part, ctr = ctx.stat_slot(self.c2)

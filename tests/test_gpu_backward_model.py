@@ -389,12 +389,22 @@ def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc, only):
     sd32 = {k: v.detach().clone().requires_grad_(k in pn) for k, v in sd.items()}
     lv32, _ = _oracle_levels(sd32, img.cpu(), ver, mode, nc, False)
     torch.autograd.backward(lv32, dl_cpu)
-    errs, spread, dead = {}, {}, []
-    for k, p in m.named_parameters():
+    errs, spread, dead, null = {}, {}, [], []
+    named = dict(m.named_parameters())
+    bias_scale = torch.tensor([float(sd[k].grad.norm()) for k in named
+                               if k.endswith("conv.1.bias") and sd[k].grad is not None]).median()
+    for k, p in named.items():
         r = sd[k].grad
         if r is None or float(r.abs().max()) == 0.0:          # not upstream of this level
             assert float(p.grad.abs().max()) == 0.0, k
             dead.append(k)
+            continue
+        if k.endswith("conv.1.bias") and float(r.norm()) < 0.02 * float(bias_scale):
+            # exactly zero in exact arithmetic: on this fixture LeakyReLU runs in its linear range, and a constant
+            # added in front of a conv + BatchNorm is removed by that BatchNorm; what is left is rounding noise on
+            # both sides, so only its size is checked
+            assert float(p.grad.norm()) < 0.05 * float(bias_scale), (k, float(p.grad.norm()), float(bias_scale))
+            null.append(k)
             continue
         errs[k] = _l2(p.grad.cpu(), r)
         spread[k] = _l2(sd32[k].grad, r)
@@ -402,7 +412,7 @@ def test_whole_model_backward_vs_oracle_autograd(ver, mode, nc, only):
     sp = torch.tensor(list(spread.values()))
     out = [k for k in errs if errs[k] > 3 * spread[k] + 0.15]
     worst = sorted(errs, key=errs.get)[-5:]
-    rec = dict(case=f"{ver}_{mode}_level{only}", fwd_rel_l2=fwd, n=len(errs), untouched=len(dead),
+    rec = dict(case=f"{ver}_{mode}_level{only}", fwd_rel_l2=fwd, n=len(errs), untouched=len(dead), null=len(null),
                median=float(e.median()), p95=float(e.quantile(0.95)), max=float(e.max()),
                oracle_fp32_vs_emulated=dict(median=float(sp.median()), p95=float(sp.quantile(0.95)), max=float(sp.max())),
                outliers=out, worst={k: (errs[k], spread[k]) for k in worst})
