@@ -222,6 +222,11 @@ int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch,
  *   g = grad + wd*p;  buf = first ? g : momentum*buf + g;  p -= lr * (nesterov ? g + momentum*buf : buf)      */
 int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, float lr, float momentum,
                    float weight_decay, int nesterov, int first, void* stream);
+/* The same SGD update with the learning rate read from DEVICE memory (momentum buffer must already hold valid numbers,
+ * zeros before the first step): lets a whole training step captured in a CUDA graph follow the reference's warm-up /
+ * one-cycle schedule (train.py:189-193,220) by rewriting one float between replays.                                 */
+int ryolo_sgd_step_lrdev(float* param, const float* grad, float* buf, long long n, const float* lr_dev, float momentum,
+                         float weight_decay, int nesterov, void* stream);
 /* torch.optim.Adam step (train.py:153-154) on flat fp32 buffers; step counts from 1 (bias correction)           */
 int ryolo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
                     float beta1, float beta2, float eps, float weight_decay, int step, void* stream);

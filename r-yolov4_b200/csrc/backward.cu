@@ -685,6 +685,20 @@ sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict
   }
 }
 
+// Same update with the learning rate read from device memory: a step captured in a CUDA graph keeps following the
+// warm-up / one-cycle schedule (train.py:189-193,220) by rewriting one float between replays.
+__global__ void __launch_bounds__(256)
+sgd_lrdev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf, long long n,
+                 const float* __restrict__ lr_dev, float momentum, float wd, int nesterov) {
+  const float lr = *lr_dev;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] + wd * p[i];
+    float b = momentum * buf[i] + gi;
+    buf[i] = b;
+    p[i] -= lr * (nesterov ? gi + momentum * b : b);
+  }
+}
+
 // torch.optim.Adam (train.py:154): m = b1*m + (1-b1)*g; v = b2*v + (1-b2)*g*g; p -= lr * (m/(1-b1^t)) / (sqrt(v/(1-b2^t)) + eps)
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
@@ -843,6 +857,16 @@ int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, flo
   if (n <= 0) return RYOLO_OK;
   sgd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, buf, n, lr, momentum, weight_decay,
                                                                 nesterov, first);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+int ryolo_sgd_step_lrdev(float* param, const float* grad, float* buf, long long n, const float* lr_dev, float momentum,
+                         float weight_decay, int nesterov, void* stream) {
+  RY_CHECK_ARG(lr_dev != nullptr, "sgd_step_lrdev: lr_dev must point at a device float");
+  if (n <= 0) return RYOLO_OK;
+  sgd_lrdev_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, buf, n, lr_dev, momentum, weight_decay,
+                                                                      nesterov);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

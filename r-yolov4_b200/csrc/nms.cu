@@ -61,9 +61,9 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
   __shared__ RPrep srow[kTile], scol[kTile];
   __shared__ float qx[2][kTile], qy[2][kTile], qr[2][kTile];
   __shared__ float qw[2][kTile], qh[2][kTile], qc[2][kTile], qs[2][kTile], qa[2][kTile];   // SoA for the early-outs
-  __shared__ unsigned short queue[kTile * kTile];
+  __shared__ unsigned short queue[kTile * kTile], queue2[kTile * kTile];
   __shared__ unsigned long long tmask[kTile];
-  __shared__ int qn;
+  __shared__ int qn, qn2;
 
   const int tid = threadIdx.x;
   if (tid < kTile) {
@@ -78,7 +78,7 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
     scol[t] = p; qx[1][t] = p.cx; qy[1][t] = p.cy; qr[1][t] = p.reach;
     qw[1][t] = p.w; qh[1][t] = p.h; qc[1][t] = p.c2; qs[1][t] = p.s2; qa[1][t] = p.area;
   }
-  if (tid == 0) qn = 0;
+  if (tid == 0) { qn = 0; qn2 = 0; }
   __syncthreads();
 
   const bool use_reject = thr >= 0.f;  // IoU==0 pairs only matter when thr < 0
@@ -106,11 +106,30 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
   }
   __syncthreads();
   const int nq = qn;
-  for (int q = tid; q < nq; q += 256) {
-    int p = queue[q], i = p >> 6, j = p & 63;
-    // cheap fp32 estimate where its error is provably small (rbox_fast_ok) and far from the threshold; the bit-exact
-    // Appendix-B computation everywhere else
-    if (rbox_iou_exceeds(srow[i], scol[j], thr)) atomicOr(&tmask[i], 1ull << j);
+  // phase 2: cheap fp32 estimate where its error is provably small (rbox_fast_ok) and far from the threshold; the
+  // undecided pairs (~1 %) are compacted into a second queue ...
+  for (int q0 = 0; q0 < nq; q0 += 256) {
+    const int q = q0 + tid;
+    int verdict = 0, p = 0;
+    if (q < nq) {
+      p = queue[q];
+      verdict = rbox_iou_exceeds_quick(srow[p >> 6], scol[p & 63], thr);
+      if (verdict > 0) atomicOr(&tmask[p >> 6], 1ull << (p & 63));
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, verdict < 0);
+    if (b) {
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&qn2, __popc(b));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (verdict < 0) queue2[base + __popc(b & ((1u << lane) - 1))] = (unsigned short)p;
+    }
+  }
+  __syncthreads();
+  // ... phase 3: and take the bit-exact Appendix-B path on fully populated warps
+  const int nq2 = qn2;
+  for (int q = tid; q < nq2; q += 256) {
+    const int p = queue2[q], i = p >> 6, j = p & 63;
+    if (rbox_iou_full(srow[i], scol[j]) > thr) atomicOr(&tmask[i], 1ull << j);
   }
   __syncthreads();
   if (tid < kTile) {

@@ -357,16 +357,22 @@ RY_RDEV bool rbox_fast_ok(const RPrep& A, const RPrep& B) {
   return true;
 }
 
-// NMS decision "IoU(A, B) > thr" for a pair that survived the early-outs: bit-identical with Appendix B.
+// NMS decision "IoU(A, B) > thr" for a pair that survived the early-outs, from the fast estimate alone:
+// 1 = exceeds, 0 = does not, -1 = undecided (gate closed, or estimate within kFastBand of thr): take the exact path.
+RY_RDEV int rbox_iou_exceeds_quick(const RPrep& A, const RPrep& B, float thr) {
+  if (!rbox_fast_ok(A, B)) return -1;
+  const float v = rbox_iou_fast(A, B);
+  if (fabsf(v - thr) <= kFastBand) return -1;
+  return v > thr ? 1 : 0;
+}
+
+// The complete decision: bit-identical with Appendix B.  (The NMS kernel runs the two halves as separate passes so
+// that the ~10x more expensive exact path executes on compacted, fully populated warps instead of stalling 31 lanes
+// whenever one lane of a warp is undecided.)
 RY_RDEV bool rbox_iou_exceeds(const RPrep& A, const RPrep& B, float thr) {
-  float v;
-  if (rbox_fast_ok(A, B)) {
-    v = rbox_iou_fast(A, B);
-    if (fabsf(v - thr) <= kFastBand) v = rbox_iou_full(A, B);
-  } else {
-    v = rbox_iou_full(A, B);
-  }
-  return v > thr;
+  const int q = rbox_iou_exceeds_quick(A, B, thr);
+  if (q >= 0) return q != 0;
+  return rbox_iou_full(A, B) > thr;
 }
 
 // IoU(A, B) with A = the higher-scored ("row") box, B = the candidate ("column") box.

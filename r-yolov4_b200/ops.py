@@ -287,6 +287,13 @@ def sgd_step(param, grad, buf, lr, momentum, weight_decay, nesterov, first):
     L.count(1)
 
 
+def sgd_step_lrdev(param, grad, buf, lr_dev, momentum, weight_decay, nesterov):
+    """SGD update with the learning rate in a device float (CUDA-graph friendly, see TrainStep.capture)."""
+    L.check(L.lib().ryolo_sgd_step_lrdev(_tp(param), _tp(grad), _tp(buf), param.numel(), _tp(lr_dev), float(momentum),
+                                         float(weight_decay), 1 if nesterov else 0, L.stream()))
+    L.count(1)
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, lr, step, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
     L.check(L.lib().ryolo_adam_step(_tp(param), _tp(grad), _tp(exp_avg), _tp(exp_avg_sq), param.numel(), float(lr),
                                     float(betas[0]), float(betas[1]), float(eps), float(weight_decay), int(step),

@@ -38,6 +38,8 @@ class TrainStep:
         self.n_buckets = n_buckets
         self._plan = self._comm = None
         self._works = []
+        self._graph = None
+        self._lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=self.flat.device)
         if self.world > 1:   # identical replicas
             dist.broadcast(self.flat, 0, group=self.pg)
 
@@ -150,6 +152,8 @@ class TrainStep:
             if self.first:
                 self.buf2 = torch.zeros_like(self.flat)
             ops.adam_step(self.flat, self.grad, self.buf, self.buf2, self.lr, self.nstep, weight_decay=self.wd)
+        elif self._capturing:
+            ops.sgd_step_lrdev(self.flat, self.grad, self.buf, self._lr_dev, self.momentum, self.wd, self.nesterov)
         else:
             ops.sgd_step(self.flat, self.grad, self.buf, self.lr, self.momentum, self.wd, self.nesterov, self.first)
         self.first = False
@@ -161,6 +165,78 @@ class TrainStep:
         items = self.forward_backward(imgs, targets)
         self.step()
         return items
+
+    # ---- whole-step CUDA graph -------------------------------------------------------------------------------
+    _capturing = False
+
+    def capture(self, imgs, targets, target_capacity=None, warmup=2):
+        """Capture ONE WHOLE optimizer step — zero_grad, train-mode forward, fused loss value + gradient, conv-stack
+        backward (side-stream weight-gradient GEMMs included), SGD, bf16 weight repack — into a single CUDA graph
+        (SURVEY.md §7 step 5): `replay()` is then one cudaGraphLaunch per step with no host synchronisation; the ~580
+        ctypes launches, tensor-map encodes and allocator calls of the eager path happen once, here.
+
+        imgs: [B,3,S,S] example batch (shape is frozen).  targets: example label rows; the graph is captured for
+        `target_capacity` rows (default: 2x the example): replay() pads shorter label sets with image index -1, which
+        the assignment kernel drops (csrc/assign.cuh), so a variable number of boxes per batch needs no re-capture.
+        The learning rate lives in a device float (`set_lr`).  SGD only (Adam's bias correction is host arithmetic).
+        Single-GPU path; with world > 1 use the eager step (the bucketed all-reduce is host-driven)."""
+        if self.optimizer != "SGD":
+            raise NotImplementedError("capture(): SGD only")
+        if self.world > 1:
+            raise NotImplementedError("capture(): single-GPU path (the bucketed all-reduce is host-driven)")
+        cols = targets.shape[1]
+        cap = int(target_capacity or max(64, 2 * targets.shape[0]))
+        assert targets.shape[0] <= cap
+        dev = self.flat.device
+        self._g_imgs = torch.empty_like(imgs)
+        self._g_tg = torch.full((cap, cols), -1.0, dtype=torch.float32, device=dev)
+        self._g_cap = cap
+        self._stage(imgs, targets)
+        self.crit.sync_items = False
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # eager warm-up on a side stream (workspaces, tables, momentum)
+            for _ in range(max(1, warmup)):
+                self(self._g_imgs, self._g_tg)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.set_lr(self.lr)
+        g = torch.cuda.CUDAGraph()
+        self._capturing = True
+        try:
+            with torch.cuda.graph(g):
+                self._g_items = self(self._g_imgs, self._g_tg)
+        finally:
+            self._capturing = False
+        self._graph = g
+        return self
+
+    def set_lr(self, lr):
+        self.lr = float(lr)
+        self._lr_dev.fill_(self.lr)
+
+    def _stage(self, imgs, targets):
+        self._g_imgs.copy_(imgs, non_blocking=True)
+        n = targets.shape[0]
+        if n > self._g_cap:
+            raise ValueError(f"{n} label rows exceed the captured capacity {self._g_cap}: capture() again")
+        self._g_tg[:n].copy_(targets, non_blocking=True)
+        if n < self._g_cap:
+            self._g_tg[n:, 0].fill_(-1.0)
+
+    def replay(self, imgs, targets):
+        """One captured step on new data: two device copies into the graph's input buffers + one graph launch.
+        Returns the device loss items (valid until the next replay)."""
+        assert self._graph is not None, "capture() first"
+        if self.model._pack_signature() != self.model._pack_sig:     # load_state_dict / init since the last step
+            self.model.repack_weights()
+        self._stage(imgs, targets)
+        self._graph.replay()
+        self.nstep += 1
+        blocks.WEIGHT_EPOCH[0] += 1          # weights and running statistics moved without any torch-visible write
+        blocks.BN_EPOCH[0] += 1
+        self.model._pack_sig = self.model._pack_signature()          # the graph's last node repacked the operands
+        return self._g_items
 
     def train_batch(self, imgs, targets, schedule, epoch, batch):
         """One iteration of the reference's inner loop (train.py:183-202) under a `schedule.Schedule`: warm-up lr /

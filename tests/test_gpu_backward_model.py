@@ -504,3 +504,51 @@ def test_parameter_writes_after_trainstep_refresh_the_packed_operands():
     for x, y, z in zip(c, d, a):
         assert torch.equal(x, y)
         assert not torch.equal(x, z)
+
+
+def test_whole_step_cuda_graph_matches_eager():
+    """TrainStep.capture(): one cudaGraphLaunch per optimizer step.  First step: the same loss bits as the eager path
+    (the forward pass is bit-reproducible); afterwards the trajectories stay together (the backward's fp32 atomics are
+    order-dependent in both modes).  A batch with fewer label rows than the captured capacity needs no re-capture
+    (padding rows carry image index -1 and are dropped by the assignment kernel), and the learning rate is a device
+    scalar that set_lr() rewrites between replays."""
+    import ryolo_b200 as R
+    R_, m, img, tg, crit = _model_and_batch("yolov4", "csl", 2, S=128, bs=4)
+    tg = make_targets(9, 4, 10, 2, True).cuda()
+    tg_small = tg[tg[:, 0] < 2][:7].contiguous()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    eager = R.TrainStep(m, crit, lr=0.01)
+    ref = [float(eager(img, tg)[4]) for _ in range(4)]
+    ref_small = float(eager(img, tg_small)[4])
+    eager.lr = 0.0
+    w_before = eager.flat.clone()
+    eager(img, tg)
+    assert torch.equal(w_before, eager.flat)                        # lr = 0: nothing moves (sanity of the comparison)
+    # ---- same thing through the graph
+    m2 = det_init(R.Yolo(2, CFG, "csl", "yolov4")).cuda().train()
+    m2.load_state_dict(sd0)
+    crit2 = R.ComputeCSLLoss(m2, HYP)
+    g = R.TrainStep(m2, crit2, lr=0.01)
+    g.capture(img, tg, target_capacity=64, warmup=1)
+    m2.load_state_dict(sd0)                                          # the warm-up / capture steps trained: rewind
+    g.buf.zero_()
+    got = [float(g.replay(img, tg)[4]) for _ in range(4)]
+    assert got[0] == ref[0], (got, ref)
+    for a, b in zip(got, ref):
+        assert abs(a - b) <= 2e-3 * abs(b), (got, ref)
+    small = float(g.replay(img, tg_small)[4])
+    assert abs(small - ref_small) <= 5e-3 * abs(ref_small), (small, ref_small)
+    g.set_lr(0.0)
+    w_before = g.flat.clone()
+    g.replay(img, tg)
+    torch.cuda.synchronize()
+    assert torch.equal(w_before, g.flat)
+    # eval after graph training sees the trained weights / running statistics (epoch counters bumped by replay)
+    m2.eval()
+    fresh = det_init(R.Yolo(2, CFG, "csl", "yolov4")).cuda().eval()
+    fresh.load_state_dict(m2.state_dict())
+    with torch.no_grad():
+        a, _ = m2(img, training=False)
+        b, _ = fresh(img, training=False)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
