@@ -293,7 +293,7 @@ class Env:
     pass
 
 
-def bench_train(env, wl, steps, warm, sample_clocks):
+def bench_train(env, wl, steps, warm, sample_clocks, use_graph=True):
     """One training workload on this rank's GPU: resident (`value`), instrumented roofline pass, forward+loss only,
     and end to end from pinned host memory.  All timings are CUDA events, max over ranks."""
     import ryolo_b200 as R
@@ -377,7 +377,50 @@ def bench_train(env, wl, steps, warm, sample_clocks):
 
     e2e(2)
     ms_e2e = env.timed(e2e, steps)
+    eager = dict(img_s=world * BS * steps / ms_total * 1e3, ms_per_step=ms_total / steps,
+                 e2e_img_s=world * BS * steps / ms_e2e * 1e3)
+    execution = f"eager: {launches // steps} kernel launches per step through the C ABI"
+    # ---- the same step as ONE CUDA graph launch (TrainStep.capture; single-GPU path)
+    if world == 1 and use_graph:
+        try:
+            l1 = L.LAUNCHES[0]
+            trainer.capture(dev_imgs[0], dev_tg[0], target_capacity=dev_tg[0].shape[0], warmup=1)
+            per_step = (L.LAUNCHES[0] - l1) // 2                      # one warm-up step + the captured one
+
+            def resident_g(n):
+                for i in range(n):
+                    trainer.replay(dev_imgs[i & 1], dev_tg[i & 1])
+
+            def e2e_g(n):
+                cur = torch.cuda.current_stream()
+                for s in range(2):
+                    freed[s].record(cur)
+                upload(0)
+                for i in range(n):
+                    s = i & 1
+                    if i + 1 < n:
+                        upload(i + 1)
+                    cur.wait_event(ready[s])
+                    items = trainer.replay(stage_i[s], stage_t[s])
+                    freed[s].record(cur)
+                    out_host.copy_(items, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+
+            resident_g(2)
+            sampler = ClockSampler(env.local) if (sample_clocks and rank == 0) else None
+            ms_g = env.timed(resident_g, steps)
+            if sampler:
+                clocks = sampler.stop()
+            e2e_g(2)
+            ms_e2e_g = env.timed(e2e_g, steps)
+            if ms_g < ms_total:
+                ms_total, ms_e2e, launches = ms_g, ms_e2e_g, per_step * steps
+                execution = f"one CUDA graph launch per step ({per_step} kernels captured; TrainStep.capture/replay)"
+            eager["graph_img_s"] = world * BS * steps / ms_g * 1e3
+        except Exception as e:                                        # noqa: BLE001 - report and keep the eager numbers
+            eager["graph_error"] = repr(e)[:300]
     res = dict(value=world * BS * steps / ms_total * 1e3, ms_per_step=ms_total / steps, launches=launches, clocks=clocks,
+               eager=eager, execution=execution,
                tc_ms=tc_ms, fwd_loss_img_s=world * BS * fl_steps / ms_fl * 1e3, fwd_loss_ms=ms_fl / fl_steps,
                e2e=dict(value=world * BS * steps / ms_e2e * 1e3, unit=UNIT,
                         h2d_bytes_per_step=int(host_imgs[0].numel() * 4 + host_tg[0].numel() * 4),
@@ -532,15 +575,16 @@ def run_gpu(args):
     env.timed = timed
     warm = max(args.warmup, 3)
     wl = WORKLOADS[args.workload]
-    head = bench_train(env, wl, args.steps, warm, True)
+    head = bench_train(env, wl, args.steps, warm, True, not args.no_graph)
     aux = {}
     if not args.no_aux:
         other = "train_v7" if args.workload == "train_v4" else "train_v4"
-        o = bench_train(env, WORKLOADS[other], args.steps, warm, False)
+        o = bench_train(env, WORKLOADS[other], args.steps, warm, False, not args.no_graph)
         pk, pk_src = peaks()
         aux[other] = {"workload": WORKLOADS[other]["name"], "value": o["value"], "unit": UNIT,
                       "ms_per_step": o["ms_per_step"], "n_gpus": world, "per_gpu_batch": BS, "e2e": o["e2e"],
                       "fwd_loss_img_s": o["fwd_loss_img_s"], "gpu_launches": o["launches"],
+                      "execution": o["execution"], "eager": o["eager"],
                       "allreduce_mb": o["grad_mb"] if world > 1 else 0,
                       "roofline": roofline_of(o, WORKLOADS[other], pk, pk_src)}
         if world == 1:
@@ -557,6 +601,7 @@ def run_gpu(args):
                        "parallelism": f"dp{world}" + (" (bucketed NCCL all-reduce of the fp32 gradients, overlapped with "
                                                       "backward)" if world > 1 else ""),
                        "optimizer": "SGD lr .01 momentum .937 nesterov (train.py:156)",
+                       "execution": head["execution"], "eager": head["eager"],
                        "fwd_loss_img_s": head["fwd_loss_img_s"], "fwd_loss_ms_per_step": head["fwd_loss_ms"],
                        "l2": "inputs (246 MB images + multi-GB activations per step) exceed the 126 MB L2"},
             "e2e": head["e2e"], "gpu_launches": head["launches"], "clocks": head["clocks"],
@@ -583,6 +628,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-graph", action="store_true", help="time the eager step only (no CUDA-graph capture)")
     ap.add_argument("--no-aux", action="store_true", help="headline workload only (no aux.train_v7 / kfloss / post_process)")
     ap.add_argument("--workload", default="train_v4", choices=["train_v4", "train_v7"],
                     help="headline workload; the other one is reported under aux")

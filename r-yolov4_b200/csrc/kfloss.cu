@@ -1,6 +1,7 @@
 // Standalone KFLoss (BASELINE.json configs[3]) — split from loss.cu so that it is NOT compiled with --fmad=false:
 // nothing here is compared bit for bit (the assignment code in loss.cu is), the closed form is ~250 instructions per
 // pair and at 64 B/pair the kernel sits on the instruction-issue roof, where every un-fused multiply-add costs a slot.
+#define RY_KF_FAST_MATH 1
 #include "common.cuh"
 #include "loss_math.cuh"
 #include "ryolo_b200.h"

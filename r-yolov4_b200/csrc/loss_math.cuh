@@ -21,11 +21,32 @@
 #if defined(__CUDA_ARCH__)
 #define RY_SINF(x) __sinf(x)
 #define RY_COSF(x) __cosf(x)
+#if defined(RY_KF_FAST_MATH)
+// Standalone KFLoss (csrc/kfloss.cu): the kernel sits on the instruction-issue roof (ncu: 440 instructions per pair,
+// issue slots 74 % busy at 58 % of HBM), and nine IEEE-rounded reciprocals + accurate logf / expf / sqrtf are ~110 of
+// them.  The SFU forms are 1-2 ulp (1e-7 relative), three orders of magnitude inside the 1e-4 parity bar.
+#define RY_RCP(x) __fdividef(1.f, (x))
+#define RY_LOGF(x) __logf(x)
+#define RY_EXPF(x) __expf(x)
+static __device__ __forceinline__ float ry_sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+#define RY_SQRTF(x) ry_sqrt_approx(x)
+#else
 #define RY_RCP(x) __frcp_rn(x)
+#define RY_LOGF(x) logf(x)
+#define RY_EXPF(x) expf(x)
+#define RY_SQRTF(x) sqrtf(x)
+#endif
 #else
 #define RY_SINF(x) sinf(x)
 #define RY_COSF(x) cosf(x)
 #define RY_RCP(x) (1.f / (x))
+#define RY_LOGF(x) logf(x)
+#define RY_EXPF(x) expf(x)
+#define RY_SQRTF(x) sqrtf(x)
 #endif
 
 namespace ryolo {
@@ -134,7 +155,7 @@ RY_HD void kf_fwd_bwd(const Box5 p, const Box5 t, float* xy_loss, float* kf_loss
   const float idet = RY_RCP(s00 * s11 - s01 * s01);
   const float dx = p.x - t.x, dy = p.y - t.y;
   const float quad = (dx * dx * s11 - 2.f * dx * dy * s01 + dy * dy * s00) * idet;
-  const float xl = logf(quad + 1.f);
+  const float xl = RY_LOGF(quad + 1.f);
   const float P = wp * wp, Q = hp * hp, U = wt * wt, V = ht * ht;
   const float iP = RY_RCP(P), iQ = RY_RCP(Q), iU = RY_RCP(U), iV = RY_RCP(V);
   const float dr = p.r - t.r;
@@ -142,9 +163,9 @@ RY_HD void kf_fwd_bwd(const Box5 p, const Box5 t, float* xy_loss, float* kf_loss
   const float c2 = cd * cd, s2 = sd * sd;
   const float A2 = 1.f + (P * Q) * (iU * iV) + (P * iU + Q * iV) * c2 + (P * iV + Q * iU) * s2;
   const float B2 = 1.f + (U * V) * (iP * iQ) + (U * iP + V * iQ) * c2 + (U * iQ + V * iP) * s2;
-  const float A = sqrtf(A2), B = sqrtf(B2);
+  const float A = RY_SQRTF(A2), B = RY_SQRTF(B2);
   const float K = RY_RCP(A + B - 3.f);
-  const float e = expf(1.f - K);
+  const float e = RY_EXPF(1.f - K);
   const float kl = e - 1.f;
   *xy_loss = fmaxf(xl, 0.f);
   *kf_loss = fmaxf(kl, 0.f);

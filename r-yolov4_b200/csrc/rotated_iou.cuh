@@ -256,7 +256,8 @@ RY_RDEV float rbox_iou_fast(const RPrep& A, const RPrep& B) {
   int n = 4;
 #pragma unroll
   for (int i = 0; i < 4; i++) { px[i] = pa[i].x; py[i] = pa[i].y; }
-  const float orient = (pb[1].x - pb[0].x) * (pb[2].y - pb[1].y) - (pb[1].y - pb[0].y) * (pb[2].x - pb[1].x);
+  // (explicit fmaf: nms.cu is compiled with --fmad=false for the exact path; the estimate wants the fused forms)
+  const float orient = fmaf(pb[1].x - pb[0].x, pb[2].y - pb[1].y, -(pb[1].y - pb[0].y) * (pb[2].x - pb[1].x));
   const float sgn = orient >= 0.f ? 1.f : -1.f;
 #pragma unroll
   for (int e = 0; e < 4; e++) {
@@ -264,14 +265,15 @@ RY_RDEV float rbox_iou_fast(const RPrep& A, const RPrep& B) {
     const float bx = pb[e].x, by = pb[e].y;
     int m = 0;
     float sx = px[n - 1], sy = py[n - 1];
-    float ds = sgn * (ex * (sy - by) - ey * (sx - bx));
+    const float sex = sgn * ex, sey = sgn * ey;
+    float ds = fmaf(sex, sy - by, -sey * (sx - bx));
     for (int i = 0; i < n; i++) {
       const float cx = px[i], cy = py[i];
-      const float dc = sgn * (ex * (cy - by) - ey * (cx - bx));
+      const float dc = fmaf(sex, cy - by, -sey * (cx - bx));
       if ((dc >= 0.f) != (ds >= 0.f)) {            // edge s->c crosses the clip line
         const float t = ds / (ds - dc);
-        qx[m] = sx + t * (cx - sx);
-        qy[m] = sy + t * (cy - sy);
+        qx[m] = fmaf(t, cx - sx, sx);
+        qy[m] = fmaf(t, cy - sy, sy);
         m++;
       }
       if (dc >= 0.f) { qx[m] = cx; qy[m] = cy; m++; }
@@ -284,7 +286,7 @@ RY_RDEV float rbox_iou_fast(const RPrep& A, const RPrep& B) {
   float a2 = 0.f;
   for (int i = 0; i < n; i++) {
     const int j = (i + 1 == n) ? 0 : i + 1;
-    a2 += px[i] * py[j] - px[j] * py[i];
+    a2 = fmaf(px[i], py[j], fmaf(-px[j], py[i], a2));
   }
   const float inter = 0.5f * fabsf(a2);
   return inter / (A.area + B.area - inter);
@@ -300,6 +302,12 @@ RY_RDEV float rbox_iou_fast(const RPrep& A, const RPrep& B) {
 // pairs: thin slivers, sub-unit boxes, near-coincident edges, near-duplicates, 4096*cls offsets); everything else,
 // and every estimate within kFastBand of the threshold, takes the bit-exact path.
 constexpr float kFastBand = 2e-3f;
+// true when one of the four values |a +- S|, |a +- T| lies within delta of `half` (a corner on an edge line)
+RY_RDEV bool rbox_axis_touch(float a, float p, float q, float half, float delta) {
+  const float S = p + q, T = fabsf(p - q);
+  return fabsf(a + S - half) < delta || fabsf(fabsf(a - S) - half) < delta || fabsf(a + T - half) < delta ||
+         fabsf(fabsf(a - T) - half) < delta;
+}
 #ifndef RY_FAST_MIN_SKEW
 #define RY_FAST_MIN_SKEW 0.002f
 #endif
@@ -330,29 +338,21 @@ RY_RDEV bool rbox_fast_ok(const RPrep& A, const RPrep& B) {
   // half-extent vectors (see rcorners): w-axis (c2 w, -s2 w), h-axis (s2 h, c2 h); unit axes are 2*(c2, -s2), 2*(s2, c2)
   const float apx = A.c2 * A.w, apy = -A.s2 * A.w, aqx = A.s2 * A.h, aqy = A.c2 * A.h;
   const float bpx = B.c2 * B.w, bpy = -B.s2 * B.w, bqx = B.s2 * B.h, bqy = B.c2 * B.h;
+  // The four corners of A sit at uD +- uP +- uQ along an axis of B (D = centre offset, P / Q = A's half-extent vectors):
+  // their absolute values are |a + S|, |a - S|, |a + T|, |a - T| with a = |uD|, S = |uP| + |uQ|, T = ||uP| - |uQ||.
   {  // corners of A in B's frame
     const float ux = 2.f * B.c2, uy = -2.f * B.s2, vx = 2.f * B.s2, vy = 2.f * B.c2;
-    const float uD = ux * dx + uy * dy, uP = ux * apx + uy * apy, uQ = ux * aqx + uy * aqy;
-    const float vD = vx * dx + vy * dy, vP = vx * apx + vy * apy, vQ = vx * aqx + vy * aqy;
-    const float hw = 0.5f * fabsf(B.w), hh = 0.5f * fabsf(B.h);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const float sp = (k & 1) ? -1.f : 1.f, sq = (k & 2) ? -1.f : 1.f;
-      if (fabsf(fabsf(uD + sp * uP + sq * uQ) - hw) < delta) return false;
-      if (fabsf(fabsf(vD + sp * vP + sq * vQ) - hh) < delta) return false;
-    }
+    if (rbox_axis_touch(fabsf(fmaf(ux, dx, uy * dy)), fabsf(fmaf(ux, apx, uy * apy)), fabsf(fmaf(ux, aqx, uy * aqy)),
+                        0.5f * fabsf(B.w), delta)) return false;
+    if (rbox_axis_touch(fabsf(fmaf(vx, dx, vy * dy)), fabsf(fmaf(vx, apx, vy * apy)), fabsf(fmaf(vx, aqx, vy * aqy)),
+                        0.5f * fabsf(B.h), delta)) return false;
   }
   {  // corners of B in A's frame
     const float ux = 2.f * A.c2, uy = -2.f * A.s2, vx = 2.f * A.s2, vy = 2.f * A.c2;
-    const float uD = -(ux * dx + uy * dy), uP = ux * bpx + uy * bpy, uQ = ux * bqx + uy * bqy;
-    const float vD = -(vx * dx + vy * dy), vP = vx * bpx + vy * bpy, vQ = vx * bqx + vy * bqy;
-    const float hw = 0.5f * fabsf(A.w), hh = 0.5f * fabsf(A.h);
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const float sp = (k & 1) ? -1.f : 1.f, sq = (k & 2) ? -1.f : 1.f;
-      if (fabsf(fabsf(uD + sp * uP + sq * uQ) - hw) < delta) return false;
-      if (fabsf(fabsf(vD + sp * vP + sq * vQ) - hh) < delta) return false;
-    }
+    if (rbox_axis_touch(fabsf(fmaf(ux, dx, uy * dy)), fabsf(fmaf(ux, bpx, uy * bpy)), fabsf(fmaf(ux, bqx, uy * bqy)),
+                        0.5f * fabsf(A.w), delta)) return false;
+    if (rbox_axis_touch(fabsf(fmaf(vx, dx, vy * dy)), fabsf(fmaf(vx, bpx, vy * bpy)), fabsf(fmaf(vx, bqx, vy * bqy)),
+                        0.5f * fabsf(A.h), delta)) return false;
   }
   return true;
 }
