@@ -39,6 +39,17 @@ size_t ryolo_pairwise_iou_rotated_workspace(int64_t n, int64_t m);
 int ryolo_pairwise_iou_rotated(const float* a, int64_t n, const float* b, int64_t m, float* out,
                                void* workspace, size_t ws_bytes, void* stream);
 
+/* test.py:100-149 get_batch_statistics for a whole batch in ONE launch (eval matching):
+ *   dets [B,max_det,7] (x,y,w,h,theta RAD,score,class) with n_det[B] valid rows each (= ryolo_post_process outputs),
+ *   targets [T,tcols>=7] (image,class,x,y,w,h,theta RAD), iouv [niou<=32] ascending -> tp uint8 [B,max_det,niou].
+ *   Reference semantics verbatim: per target class ascending, detections in index order claim the target of their
+ *   class with the highest skew IoU (first maximum) if IoU > iouv[0] and unclaimed; tp[d,k] = IoU > iouv[k].
+ *   status int32[1] (zeroed by the caller) is set to 1 when an image has more than 1024 targets.                  */
+size_t ryolo_eval_match_workspace(int64_t B, int max_det);
+int ryolo_eval_match(const float* dets, const int32_t* n_det, int64_t B, int max_det, const float* targets, int64_t T,
+                     int tcols, const float* iouv, int niou, uint8_t* tp, int32_t* status, void* workspace,
+                     size_t ws_bytes, void* stream);
+
 /* detectron2.layers.nms.nms_rotated  (reference call site lib/general.py:4,177)
  *   boxes5 [n,5] (cx,cy,w,h,deg), scores [n]; keep int64[n] (indices into boxes5, score-descending,
  *   stable), n_keep int32[1]; suppression when IoU > iou_thr (CUDA-build semantics).            */

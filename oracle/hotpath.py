@@ -321,3 +321,42 @@ def post_process(predictions, conf_thres=0.5, iou_thres=0.4, return_indices=Fals
         outs.append(dets[keep])
         idxs.append(rows[keep])
     return (outs, idxs) if return_indices else outs
+
+
+def get_batch_statistics(outputs, targets, iouv, niou):
+    """ORACLE restatement of test.py:100-149 (per image, per target class, per detection; the C++ restatement of
+    detectron2's pairwise_iou_rotated behind it).  Pinned by tests/golden/metrics.pt (generated by running the
+    reference's own function).  Mutates the prediction angles to degrees in place like the reference (:124)."""
+    stats = []
+    for si, pred in enumerate(outputs):
+        tar = targets[targets[:, 0] == si, 1:]
+        nl = len(tar)
+        tcls = tar[:, 0].tolist() if nl else []
+        if len(pred) == 0:
+            if nl:
+                stats.append((np.zeros((0, niou), dtype=bool), np.empty(0), np.empty(0), tcls))
+            continue
+        tp = torch.zeros(pred.shape[0], niou, dtype=torch.bool)
+        if nl:
+            found = 0
+            pred[:, 4] = pred[:, 4] / np.pi * 180
+            tb = tar[:, 1:6].clone()
+            tb[:, 4] = tb[:, 4] / np.pi * 180
+            for c in torch.unique(tar[:, 0]):
+                ti = (tar[:, 0] == c).nonzero().view(-1)
+                pi = (pred[:, 6] == c).nonzero().view(-1)
+                if not pi.numel():
+                    continue
+                ious, arg = _rot.pairwise_iou_rotated(pred[pi, :5], tb[ti]).max(1)
+                taken = set()
+                for j in (ious > iouv[0]).nonzero().view(-1).tolist():
+                    d = int(ti[arg[j]])
+                    if d in taken:
+                        continue
+                    taken.add(d)
+                    found += 1
+                    tp[pi[j]] = ious[j] > iouv
+                    if found == nl:
+                        break
+        stats.append((tp, pred[:, 5].clone(), pred[:, 6].clone(), tcls))
+    return stats

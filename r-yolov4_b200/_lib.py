@@ -24,6 +24,8 @@ SIGNATURES = {
     "ryolo_knob": (_i32, [_i32]),
     "ryolo_pairwise_iou_rotated_workspace": (_sz, [_i64, _i64]),
     "ryolo_pairwise_iou_rotated": (_i32, [_vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
+    "ryolo_eval_match_workspace": (_sz, [_i64, _i32]),
+    "ryolo_eval_match": (_i32, [_vp, _vp, _i64, _i32, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_nms_rotated_workspace": (_sz, [_i64]),
     "ryolo_nms_rotated": (_i32, [_vp, _vp, _i64, _f32, _vp, _vp, _vp, _sz, _vp]),
     "ryolo_post_process_workspace": (_sz, [_i64, _i64, _i32, _i32]),

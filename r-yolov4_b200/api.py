@@ -4,7 +4,7 @@ from ._lib import RyoloError, SO_PATH, lib
 from .lib.general import (encode_labels, xyxyxyxy2xywha, nms_rotated, non_max_suppression, norm_angle,
                           pairwise_iou_rotated, post_process, post_process_device)
 from .lib.loss import ComputeCSLLoss, ComputeKFIoULoss, KFLoss
-from .lib.metrics import ap_per_class, calculate_eval_stats, compute_ap, fitness, get_batch_statistics
+from .lib.metrics import ap_per_class, calculate_eval_stats, compute_ap, fitness, get_batch_statistics, match_batch
 from .model.yololayer import YoloCSLLayer, YoloKFIoULayer
 from .schedule import Schedule, one_cycle
 from .train_step import TrainStep
@@ -24,5 +24,5 @@ def compute_loss(model, hyp, mode="csl"):
 __all__ = ["Yolo", "Model", "ComputeCSLLoss", "ComputeKFIoULoss", "KFLoss", "compute_loss", "post_process",
            "post_process_device", "non_max_suppression", "nms_rotated", "pairwise_iou_rotated", "norm_angle",
            "encode_labels", "xyxyxyxy2xywha", "YoloCSLLayer", "YoloKFIoULayer", "TrainStep", "Schedule", "one_cycle",
-           "get_batch_statistics", "ap_per_class", "compute_ap", "calculate_eval_stats", "fitness", "RyoloError", "SO_PATH",
+           "get_batch_statistics", "match_batch", "ap_per_class", "compute_ap", "calculate_eval_stats", "fitness", "RyoloError", "SO_PATH",
            "lib"]

@@ -44,6 +44,90 @@ __global__ void pairwise_iou_kernel(const RPrep* __restrict__ a, int64_t n, cons
   if (i < n && j < m) out[i * m + j] = rbox_iou(sa[ty], sb[tx]);
 }
 
+// ------------------------------------------------------------------------------------ eval matching (test.py:100-149)
+// get_batch_statistics on the device, one CTA per image.  Reference semantics, kept verbatim:
+//   * angles rad -> deg as (x / fl32(pi)) * 180 in fp32                                            (test.py:124-125)
+//   * per target class c (ascending, torch.unique): detections of class c in index order; each takes the target of
+//     its class with the highest skew IoU (first maximum, torch.max) and claims it if IoU > iouv[0] and nobody of
+//     this class claimed it before; a claim marks tp[d, k] = IoU > iouv[k]                          (test.py:127-141)
+//   * `if len(detected_boxes) == nl: break` leaves the CURRENT class only, and only at equality    (test.py:142-143)
+// Phase 1 (all threads): best target per detection — n_det x n_tgt exact IoUs (rbox_iou = Appendix B).
+// Phase 2 (one thread): the inherently sequential claim bookkeeping, <= n_classes_present * n_det steps.
+constexpr int kMatchMaxTgt = 1024;     // targets of ONE image held in shared memory
+
+__global__ void __launch_bounds__(256)
+eval_match_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_det, int max_det,
+                  const float* __restrict__ targets, int64_t T, int tcols, const float* __restrict__ iouv, int niou,
+                  uint8_t* __restrict__ tp, float* __restrict__ best_iou, int32_t* __restrict__ best_tgt,
+                  int32_t* __restrict__ status) {
+  __shared__ RPrep tprep[kMatchMaxTgt];
+  __shared__ float tcls[kMatchMaxTgt];
+  __shared__ unsigned char claimed[kMatchMaxTgt];
+  __shared__ int nt_s;
+  const int img = blockIdx.x, tid = threadIdx.x;
+  const int nd = min(n_det[img], max_det);
+  dets += (int64_t)img * max_det * 7;
+  tp += (int64_t)img * max_det * niou;
+  best_iou += (int64_t)img * max_det;
+  best_tgt += (int64_t)img * max_det;
+  for (int i = tid; i < nd * niou; i += blockDim.x) tp[i] = 0;
+  if (tid == 0) nt_s = 0;
+  __syncthreads();
+  // targets of this image, in row order (one thread: order matters for "first maximum" and T is small)
+  if (tid == 0) {
+    int n = 0;
+    for (int64_t t = 0; t < T; t++) {
+      const float* r = targets + t * tcols;
+      if ((int)r[0] != img) continue;
+      if (n < kMatchMaxTgt) {
+        tprep[n] = rprep(r[2], r[3], r[4], r[5], __fmul_rn(__fdiv_rn(r[6], kPiF), 180.f));
+        tcls[n] = r[1];
+        claimed[n] = 0;
+      }
+      n++;
+    }
+    nt_s = n;
+    if (n > kMatchMaxTgt) status[0] = 1;          // reported by the host wrapper (no silent truncation)
+  }
+  __syncthreads();
+  const int nt = min(nt_s, kMatchMaxTgt);
+  if (nd == 0 || nt == 0) return;
+  for (int d = tid; d < nd; d += blockDim.x) {
+    const float* r = dets + d * 7;
+    const RPrep P = rprep(r[0], r[1], r[2], r[3], __fmul_rn(__fdiv_rn(r[4], kPiF), 180.f));
+    float best = -1.f;
+    int bi = -1;
+    for (int t = 0; t < nt; t++) {
+      if (tcls[t] != r[6]) continue;
+      const float v = rbox_iou(P, tprep[t]);
+      if (bi < 0 || v > best) { best = v; bi = t; }
+    }
+    best_iou[d] = best;
+    best_tgt[d] = bi;
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  const float thr0 = iouv[0];
+  int n_detected = 0;
+  float prev = -INFINITY;
+  for (;;) {                                       // classes present among the targets, ascending
+    float c = INFINITY;
+    for (int t = 0; t < nt; t++) if (tcls[t] > prev && tcls[t] < c) c = tcls[t];
+    if (c == INFINITY) break;
+    prev = c;
+    for (int d = 0; d < nd; d++) {
+      if (dets[d * 7 + 6] != c) continue;
+      const int t = best_tgt[d];
+      const float v = best_iou[d];
+      if (t < 0 || !(v > thr0) || claimed[t]) continue;
+      claimed[t] = 1;
+      n_detected++;
+      for (int k = 0; k < niou; k++) tp[d * niou + k] = v > iouv[k] ? 1 : 0;
+      if (n_detected == nt_s) break;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------ NMS mask
 // grid (col block, row block, image); 256 threads.  Phase 1 rejects far-apart pairs with a
 // conservative bounding-circle test and compacts the survivors into a shared queue so that phase 2
@@ -461,6 +545,27 @@ int ryolo_pairwise_iou_rotated(const float* a, int64_t n, const float* b, int64_
   prep_boxes_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(b, nullptr, m, pb);
   dim3 grid((unsigned)((m + 15) / 16), (unsigned)((n + 15) / 16));
   pairwise_iou_kernel<<<grid, dim3(16, 16), 0, st>>>(pa, n, pb, m, out);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+// test.py:100-149 get_batch_statistics for a whole batch in one launch.
+//   dets [B, max_det, 7] (x, y, w, h, theta RAD, score, class) with n_det[B] valid rows each (post_process_device's
+//   outputs); targets [T, tcols>=7] (image, class, x, y, w, h, theta RAD) in any image order; iouv [niou] ascending.
+//   tp uint8 [B, max_det, niou]; workspace: ryolo_eval_match_workspace(B, max_det) bytes; status int32[1] (zeroed by
+//   the caller) becomes 1 if an image has more than 1024 targets (result then invalid).
+size_t ryolo_eval_match_workspace(int64_t B, int max_det) { return (size_t)B * max_det * 8 + 256; }
+
+int ryolo_eval_match(const float* dets, const int32_t* n_det, int64_t B, int max_det, const float* targets, int64_t T,
+                     int tcols, const float* iouv, int niou, uint8_t* tp, int32_t* status, void* workspace,
+                     size_t ws_bytes, void* stream) {
+  RY_CHECK_ARG(B >= 0 && max_det > 0 && T >= 0 && tcols >= 7 && niou > 0 && niou <= 32, "eval_match: bad arguments");
+  RY_CHECK_ARG(ws_bytes >= ryolo_eval_match_workspace(B, max_det), "eval_match: workspace too small");
+  if (B == 0) return RYOLO_OK;
+  float* best_iou = (float*)workspace;
+  int32_t* best_tgt = (int32_t*)(best_iou + (size_t)B * max_det);
+  eval_match_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(dets, n_det, max_det, targets, T, tcols, iouv, niou,
+                                                                  tp, best_iou, best_tgt, status);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }
