@@ -40,6 +40,7 @@ CFG = dict(anchors=[[12, 16, 19, 36, 40, 28], [36, 75, 76, 55, 72, 146], [142, 1
            angles=[-90, -60, -30, 0, 30, 60])                                   # data/hyp.yaml:2-7
 HYP = dict(fl_gamma=0.0, box=0.05, obj=1.0, obj_pw=1.0, cls=0.5, cls_pw=1.0)   # data/hyp.yaml:11-17
 S, BS, PER_IMG = 800, 32, 100
+NC = 2          # headline workload (tools/ import it)
 # 2*MAC over the convs @800^2: forward; dgrad = forward minus the stem; wgrad = forward
 WORKLOADS = {
     "train_v4": dict(ver="yolov4", nc=2, fwd_gflop=218.14, stem_gflop=1.106,

@@ -1,6 +1,7 @@
 """DRAM traffic of the conv_fwd_kernel launches of ONE training step, from an
 `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum -k regex:conv_fwd_kernel --csv` log.
-Writes profiles/r01_conv_traffic.json (bench.py reports its per-launch mean as roofline.traffic)."""
+Writes profiles/<round>_conv_traffic.json (bench.py reports its per-launch mean as roofline.traffic):
+    python tools/conv_traffic.py <ncu csv> [r02]"""
 import collections, csv, json, os, sys
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 rows = list(csv.reader(open(sys.argv[1])))
@@ -25,4 +26,5 @@ out = dict(launches=n, dram_read_bytes=rd, dram_write_bytes=wr, dram_bytes_per_l
            serialized_ms=ms, algorithmic_bytes=alg, algorithmic_bytes_per_launch=alg / max(n, 1),
            note="cold-cache ncu pass over the conv_fwd_kernel launches (forward + dgrad) of one yolov4 bs=32 800x800 step")
 print(json.dumps(out, indent=1))
-json.dump(out, open(os.path.join(ROOT, "profiles", "r01_conv_traffic.json"), "w"), indent=1)
+json.dump(out, open(os.path.join(ROOT, "profiles", (sys.argv[2] if len(sys.argv) > 2 else "r02") + "_conv_traffic.json"), "w"),
+          indent=1)
