@@ -11,6 +11,19 @@ import torch.nn.functional as F
 from . import hotpath as hp
 
 
+class _RoundBoth(torch.autograd.Function):
+    """bf16 storage point of the B200 stack in BOTH directions: the activation is stored in bf16 on the way forward
+    and its gradient (the dgrad / BN-backward output that lands in the mirrored gradient buffer) on the way back."""
+
+    @staticmethod
+    def forward(ctx, t):
+        return t.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
 class Net:
     """Evaluates the reference graph from a flat state_dict. train=True uses batch statistics
     (model/utils.py:16-17 BatchNorm2d in train mode) and records updated running stats."""
@@ -18,9 +31,15 @@ class Net:
     def __init__(self, sd, train, eps=1e-5, momentum=0.1, emulate_bf16=False):
         """emulate_bf16: round conv weights, raw conv outputs and block outputs to bf16 (straight-through
         gradient), i.e. the storage points of the B200 stack, so that discontinuous derivatives (LeakyReLU's
-        kink, max-pool arg-max) are decided on the same numbers.  Arithmetic stays fp32 like the product's."""
+        kink, max-pool arg-max) are decided on the same numbers.  Arithmetic stays fp32 like the product's.
+        emulate_bf16="grad" also rounds the GRADIENTS arriving at those storage points (the product keeps d out and
+        d raw in bf16 buffers): the yardstick for sums that cancel to ~0 in exact arithmetic (BatchNorm biases in front
+        of another conv + BatchNorm), where that rounding noise is the whole signal."""
         self.sd, self.train, self.eps, self.mom = sd, train, eps, momentum
-        self.q = (lambda t: t + (t.bfloat16().float() - t).detach()) if emulate_bf16 else (lambda t: t)
+        if emulate_bf16 == "grad":
+            self.q = _RoundBoth.apply
+        else:
+            self.q = (lambda t: t + (t.bfloat16().float() - t).detach()) if emulate_bf16 else (lambda t: t)
         self.new_stats = {}
         self.trace = None      # optional list of (module path, input, output) per Conv / RepConv
 

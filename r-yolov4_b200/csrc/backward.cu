@@ -20,6 +20,14 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[2 * j + 1] = t.y;
   }
 }
+// same values through integer ops on the packed words: the compiler keeps a prefetched uint4 as four 32-bit registers
+// across a loop back-edge (with the __nv_bfloat162 accessors it splits them into 16-bit halves with two PRMTs per word)
+__device__ __forceinline__ void unpack8u(const uint4& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 v;
   __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -379,6 +387,208 @@ bn_act_bwd_apply2_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, c
   }
 }
 
+// Variant 3 of the two passes (knob bn_bwd = 3, default): same traffic as variant 2 (4 + 6 B/element), rebuilt around the
+// two things ncu showed the variant-2 kernels waiting on (profiles/r02_elementwise_notes.txt):
+//   * memory latency: a thread's next two rows are requested BEFORE the current two are processed (register double
+//     buffer), so every resident warp keeps 64-128 bytes in flight through its ~300-instruction compute phase; the grid
+//     is exactly the resident capacity (2 blocks/SM x SMs, grid-stride) instead of 2.7 waves of short blocks;
+//   * issue slots: Mish' costs 13 instructions (ex2 and rcp on the SFU pipe, which has the headroom here: 2 x 8 pipe
+//     cycles against ~20 issue slots per warp row) instead of ~24 with the FMA-pipe reciprocal; out-of-range rows are
+//     loaded as zeros so the compute phase carries no predicates.
+__device__ __forceinline__ float ry_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ry_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// d act / d z at pre-activation z.  Mish: f = z*t, t = tanh(softplus(z)) = 1 - 2r, r = 1/((e+1)^2 + 1), e = e^z;
+// f' = t + 4 z e (e+1) r^2.  z > 20 is clamped inside the exponential only (r -> 4e-18, f' -> 1).
+template <int ACT>
+__device__ __forceinline__ float act_grad3(float z) {
+  if (ACT == RYOLO_ACT_MISH) {
+    const float e = ry_ex2(fminf(z * 1.4426950408889634f, 28.853900817779268f));
+    const float p = e + 1.f;
+    const float r = ry_rcp(fmaf(p, p, 1.f));
+    const float w = (e * p) * r;
+    return fmaf((z * w) * r, 4.f, fmaf(-2.f, r, 1.f));
+  }
+  if (ACT == RYOLO_ACT_SWISH) {           // sg (1 + z (1 - sg)), sg = 1/(1 + e^-z)
+    const float sg = ry_rcp(1.f + ry_ex2(fminf(z * -1.4426950408889634f, 86.f)));
+    return sg * fmaf(z, 1.f - sg, 1.f);
+  }
+  if (ACT == RYOLO_ACT_LEAKY) return z > 0.f ? 1.f : 0.1f;
+  return 1.f;
+}
+
+// Mish' with the pre-activation already in log2 units (zl = z * log2 e, the BatchNorm scale/shift carry the factor):
+// one instruction fewer than act_grad3 in the reduce pass, which is the issue-bound one (4 B/element).
+__device__ __forceinline__ float mish_grad_l2(float zl) {
+  const float e = ry_ex2(fminf(zl, 28.853900817779268f));
+  const float p = e + 1.f;
+  const float r = ry_rcp(fmaf(p, p, 1.f));
+  const float w = (e * p) * r;
+  return fmaf((zl * w) * r, 4.f * 0.6931471805599453f, fmaf(-2.f, r, 1.f));
+}
+
+// Rows of this thread: pix0, pix0 + stride, ... < P, walked as pairs; `n` = how many.
+__device__ __forceinline__ int rows_of(long long P, int pix0, int stride) {
+  return pix0 < P ? (int)((P - 1 - pix0) / stride) + 1 : 0;
+}
+__device__ __forceinline__ uint4 ldv(const __nv_bfloat16* p) { return *reinterpret_cast<const uint4*>(p); }
+
+template <int ACT>
+__device__ __forceinline__ void reduce_row(const uint4& vd, const uint4& vr, const float (&sc)[8], const float (&sh)[8],
+                                           float (&s1)[8], float (&s2)[8]) {
+  float d[8], x[8];
+  unpack8u(vd, d);
+  unpack8u(vr, x);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (ACT == RYOLO_ACT_MISH) d[j] *= mish_grad_l2(fmaf(x[j], sc[j], sh[j]));      // sc, sh pre-multiplied by log2 e
+    else if (ACT != RYOLO_ACT_LINEAR) d[j] *= act_grad3<ACT>(fmaf(x[j], sc[j], sh[j]));
+    s1[j] += d[j];
+    s2[j] = fmaf(d[j], x[j], s2[j]);
+  }
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
+                          float* __restrict__ sums) {
+  ry_pdl_wait();
+  extern __shared__ float red[];   // [rows][C] x 2
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  const int c = 8 * g;
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (r < rows) {
+    float sc[8], sh[8];
+    const float k = ACT == RYOLO_ACT_MISH ? 1.4426950408889634f : 1.f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { sc[j] = scale[c + j] * k; sh[j] = shift[c + j] * k; }
+    const int stride = (int)gridDim.x * rows;
+    const int pix0 = (int)blockIdx.x * rows + r;
+    const int n = rows_of(P, pix0, stride);
+    const long long sd = (long long)stride * dp, sr = (long long)stride * rp;      // one row step, in elements
+    const __nv_bfloat16* pd = dout + c + (long long)pix0 * dp;
+    const __nv_bfloat16* pr = raw + c + (long long)pix0 * rp;
+    const int pairs = n >> 1;
+    if (pairs) {
+      uint4 d0 = ldv(pd), d1 = ldv(pd + sd), r0 = ldv(pr), r1 = ldv(pr + sr);
+#pragma unroll 2
+      for (int i = 1; i < pairs; i++) {
+        pd += 2 * sd;
+        pr += 2 * sr;
+        const uint4 e0 = ldv(pd), e1 = ldv(pd + sd), q0 = ldv(pr), q1 = ldv(pr + sr);    // next pair: in flight while
+        reduce_row<ACT>(d0, r0, sc, sh, s1, s2);                                          // this one is processed
+        reduce_row<ACT>(d1, r1, sc, sh, s1, s2);
+        d0 = e0; d1 = e1; r0 = q0; r1 = q1;
+      }
+      reduce_row<ACT>(d0, r0, sc, sh, s1, s2);
+      reduce_row<ACT>(d1, r1, sc, sh, s1, s2);
+      pd += 2 * sd;
+      pr += 2 * sr;
+    }
+    if (n & 1) reduce_row<ACT>(ldv(pd), ldv(pr), sc, sh, s1, s2);
+#pragma unroll
+    for (int j = 0; j < 8; j++) s2[j] = invstd[c + j] * (s2[j] - mean[c + j] * s1[j]);
+  }
+  float* r1s = red;
+  float* r2s = red + (size_t)rows * C;
+  if (r < rows) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) { r1s[r * C + c + j] = s1[j]; r2s[r * C + c + j] = s2[j]; }
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+    float a = 0.f, b = 0.f;
+    for (int rr = 0; rr < rows; rr++) { a += r1s[rr * C + cc]; b += r2s[rr * C + cc]; }
+    atomicAdd(sums + cc, a);
+    atomicAdd(sums + C + cc, b);
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ uint4 apply_row(const uint4& vd, const uint4& vr, const float (&sc)[8], const float (&sh)[8],
+                                           const float (&nk1)[8], const float (&nk2)[8]) {
+  float d[8], x[8], o[8];
+  unpack8u(vd, d);
+  unpack8u(vr, x);
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    if (ACT != RYOLO_ACT_LINEAR) d[j] *= act_grad3<ACT>(fmaf(x[j], sc[j], sh[j]));
+    o[j] = fmaf(sc[j], d[j], fmaf(x[j], nk2[j], nk1[j]));
+  }
+  return pack8(o);
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                         long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
+                         long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  ry_pdl_wait();
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (blockIdx.x == 0) {
+    for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
+      if (dbeta) dbeta[cc] += sums[cc];
+      if (dgamma) dgamma[cc] += sums[C + cc];
+    }
+  }
+  if (r >= rows) return;
+  const int c = 8 * g;
+  const float invP = 1.f / (float)P;
+  // o = sc*(d - m1 - (x - mu)*is*m2) = sc*d + (x*nk2 + nk1)   with nk2 = -sc*is*m2, nk1 = -sc*(m1 - mu*is*m2)
+  float sc[8], sh[8], nk1[8], nk2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c + j]; sh[j] = shift[c + j];
+    const float is = invstd[c + j], mu = mean[c + j];
+    const float m1 = sums[c + j] * invP, m2 = sums[C + c + j] * invP;
+    nk2[j] = -(sc[j] * is * m2);
+    nk1[j] = -(sc[j] * (m1 - mu * is * m2));
+  }
+  const int stride = (int)gridDim.x * rows;
+  const int pix0 = (int)blockIdx.x * rows + r;
+  const int n = rows_of(P, pix0, stride);
+  const long long sd = (long long)stride * dp, sr = (long long)stride * rp, so = (long long)stride * op;
+  const __nv_bfloat16* pd = dout + c + (long long)pix0 * dp;
+  const __nv_bfloat16* pr = raw + c + (long long)pix0 * rp;
+  __nv_bfloat16* po = draw + c + (long long)pix0 * op;
+  const int pairs = n >> 1;
+  if (pairs) {
+    uint4 d0 = ldv(pd), d1 = ldv(pd + sd), r0 = ldv(pr), r1 = ldv(pr + sr);
+#pragma unroll 2
+    for (int i = 1; i < pairs; i++) {
+      pd += 2 * sd;
+      pr += 2 * sr;
+      const uint4 e0 = ldv(pd), e1 = ldv(pd + sd), q0 = ldv(pr), q1 = ldv(pr + sr);
+      *reinterpret_cast<uint4*>(po) = apply_row<ACT>(d0, r0, sc, sh, nk1, nk2);
+      *reinterpret_cast<uint4*>(po + so) = apply_row<ACT>(d1, r1, sc, sh, nk1, nk2);
+      po += 2 * so;
+      d0 = e0; d1 = e1; r0 = q0; r1 = q1;
+    }
+    *reinterpret_cast<uint4*>(po) = apply_row<ACT>(d0, r0, sc, sh, nk1, nk2);
+    *reinterpret_cast<uint4*>(po + so) = apply_row<ACT>(d1, r1, sc, sh, nk1, nk2);
+    pd += 2 * sd;
+    pr += 2 * sr;
+    po += 2 * so;
+  }
+  if (n & 1) *reinterpret_cast<uint4*>(po) = apply_row<ACT>(ldv(pd), ldv(pr), sc, sh, nk1, nk2);
+}
+
 // ds = dout * act'(x1*s1+b1 + x2*s2+b2)   (two-branch pre-activation, RepConv)
 template <int ACT>
 __global__ void __launch_bounds__(256)
@@ -732,6 +942,7 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
                      float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream) {
   RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && dp % 8 == 0 && rp % 8 == 0 && op % 8 == 0,
                "bn_act_bwd: channels must be a multiple of 8 in [8, 2048]");
+  RY_CHECK_ARG(P < (1ll << 31) - (1 << 20), "bn_act_bwd: more than 2^31 pixels");
   if (P == 0) return RYOLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const int groups = C / 8;
@@ -744,8 +955,16 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
   const __nv_bfloat16* r = (const __nv_bfloat16*)raw;
   __nv_bfloat16* o = (__nv_bfloat16*)draw;
   const int variant = threads == 256 ? ryolo_knob(RYOLO_KNOB_BN_BWD) : 0;
+  // variant 3: persistent grid = resident capacity (2 blocks of 256 threads per SM), two rows per trip
+  long long want3 = (P + 2ll * rows - 1) / (2ll * rows);
+  const int blocks3 = (int)(want3 > 2ll * ry_sm_count() ? 2ll * ry_sm_count() : (want3 < 1 ? 1 : want3));
 #define RY_BWD(ACT)                                                                                                  \
-  if (variant == 2) {                                                                                                \
+  if (variant == 3) {                                                                                                \
+    ry_launch(bn_act_bwd_reduce4_kernel<ACT>, dim3(blocks3), dim3(threads), smem, st, (const __nv_bfloat16*)d, dp, r, rp, \
+              scale, shift, mean, invstd, P, C, sums);                                                               \
+    ry_launch(bn_act_bwd_apply3_kernel<ACT>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp, \
+              scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                           \
+  } else if (variant == 2) {                                                                                                \
     ry_launch(bn_act_bwd_reduce3_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, (const __nv_bfloat16*)d, dp, r, rp, \
               scale, shift, mean, invstd, P, C, sums);                                                               \
     ry_launch(bn_act_bwd_apply2_kernel<ACT>, dim3(blocks * 2), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp, \

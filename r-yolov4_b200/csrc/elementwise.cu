@@ -31,6 +31,14 @@ __device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
     f[2 * j + 1] = t.y;
   }
 }
+// same values through integer ops on the packed words: the compiler keeps a prefetched uint4 as four 32-bit registers
+// across a loop back-edge (with the __nv_bfloat162 accessors it splits them into 16-bit halves with two PRMTs per word)
+__device__ __forceinline__ void unpack8u(const uint4& v, float (&f)[8]) {
+  f[0] = __uint_as_float(v.x << 16); f[1] = __uint_as_float(v.x & 0xffff0000u);
+  f[2] = __uint_as_float(v.y << 16); f[3] = __uint_as_float(v.y & 0xffff0000u);
+  f[4] = __uint_as_float(v.z << 16); f[5] = __uint_as_float(v.z & 0xffff0000u);
+  f[6] = __uint_as_float(v.w << 16); f[7] = __uint_as_float(v.w & 0xffff0000u);
+}
 __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   uint4 v;
   __nv_bfloat162* b = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -163,12 +171,149 @@ scale_shift_act_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const 
   }
 }
 
+// Same pass, latency-proofed (knob ssa = 1, default): the grid is exactly the resident capacity (2 blocks of 256 threads
+// per SM, grid-stride), a thread requests its next U rows BEFORE it processes the current U (register double buffer:
+// every resident warp keeps U x (1-3 operands) 128-bit loads in flight through its compute phase), the row walk is
+// pointer increments with a 32-bit trip count, and Mish takes its reciprocal from the SFU (10 instructions; with the
+// FMA-pipe reciprocal the kernel above is issue-bound: 23 instructions per element against a budget of 22 at 4 B/element).
+// The kernel above issues four loads, waits, computes ~250 instructions with nothing in flight, and runs 2-3 waves of
+// short blocks (ncu: 3.8-3.9 TB/s, long-scoreboard + wait stalls).
+__device__ __forceinline__ float ssa_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ssa_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <int ACT>
+__device__ __forceinline__ float act_apply_sfu(float x) {
+  if (ACT == RYOLO_ACT_LEAKY) return x > 0.f ? x : 0.1f * x;
+  if (ACT == RYOLO_ACT_MISH) {           // x * n / (n + 2), n = e (e + 2); x > 20: the quotient rounds to 1
+    const float e = ssa_ex2(fminf(x * 1.4426950408889634f, 28.853900817779268f));
+    const float n = e * (e + 2.f);
+    return x * (n * ssa_rcp(n + 2.f));
+  }
+  if (ACT == RYOLO_ACT_SWISH) return x * ssa_rcp(1.f + ssa_ex2(fminf(x * -1.4426950408889634f, 86.f)));
+  return x;
+}
+
+template <int ACT, bool HAS_X2, bool HAS_RES>
+__device__ __forceinline__ uint4 ssa_row(const uint4& vx, const uint4& v2, const uint4& vr, const float (&sc)[8],
+                                         const float (&sh)[8], const float (&sc2)[8]) {
+  float f[8];
+  unpack8u(vx, f);
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = fmaf(f[j], sc[j], sh[j]);
+  if (HAS_X2) {
+    float h[8];
+    unpack8u(v2, h);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] = fmaf(h[j], sc2[j], f[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] = act_apply_sfu<ACT>(f[j]);
+  if (HAS_RES) {
+    float h[8];
+    unpack8u(vr, h);
+#pragma unroll
+    for (int j = 0; j < 8; j++) f[j] += h[j];
+  }
+  return pack8(f);
+}
+
+template <int ACT, bool HAS_X2, bool HAS_RES>
+__global__ void __launch_bounds__(256, 2)
+scale_shift_act_p_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const __nv_bfloat16* __restrict__ x2, long long x2p,
+                         const float* __restrict__ scale2, const float* __restrict__ shift2,
+                         const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
+                         long long P, int C) {
+  ry_pdl_wait();
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (r >= rows) return;
+  const int c = 8 * g;
+  float sc[8], sh[8], sc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c + j];
+    sh[j] = shift[c + j];
+    sc2[j] = 0.f;
+    if (HAS_X2) { sc2[j] = scale2[c + j]; sh[j] += shift2[c + j]; }
+  }
+  constexpr int U = (HAS_X2 || HAS_RES) ? 2 : 4;
+  const int stride = (int)gridDim.x * rows;
+  const int pix0 = (int)blockIdx.x * rows + r;
+  const int n = pix0 < P ? (int)((P - 1 - pix0) / stride) + 1 : 0;      // rows of this thread
+  const long long sx = (long long)stride * xp, s2 = (long long)stride * x2p, sr = (long long)stride * rp,
+                  sy = (long long)stride * yp;
+  const __nv_bfloat16* px = x + c + (long long)pix0 * xp;
+  const __nv_bfloat16* p2 = HAS_X2 ? x2 + c + (long long)pix0 * x2p : nullptr;
+  const __nv_bfloat16* pr = HAS_RES ? res + c + (long long)pix0 * rp : nullptr;
+  __nv_bfloat16* py = y + c + (long long)pix0 * yp;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  const int trips = n / U;
+  if (trips) {
+    uint4 vx[U], v2[U], vr[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      vx[u] = *reinterpret_cast<const uint4*>(px + u * sx);
+      v2[u] = HAS_X2 ? *reinterpret_cast<const uint4*>(p2 + u * s2) : z4;
+      vr[u] = HAS_RES ? *reinterpret_cast<const uint4*>(pr + u * sr) : z4;
+    }
+#pragma unroll 2
+    for (int i = 1; i < trips; i++) {
+      px += U * sx;
+      if (HAS_X2) p2 += U * s2;
+      if (HAS_RES) pr += U * sr;
+      uint4 nx[U], n2[U], nr[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        nx[u] = *reinterpret_cast<const uint4*>(px + u * sx);
+        n2[u] = HAS_X2 ? *reinterpret_cast<const uint4*>(p2 + u * s2) : z4;
+        nr[u] = HAS_RES ? *reinterpret_cast<const uint4*>(pr + u * sr) : z4;
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++)
+        *reinterpret_cast<uint4*>(py + u * sy) = ssa_row<ACT, HAS_X2, HAS_RES>(vx[u], v2[u], vr[u], sc, sh, sc2);
+      py += U * sy;
+#pragma unroll
+      for (int u = 0; u < U; u++) { vx[u] = nx[u]; v2[u] = n2[u]; vr[u] = nr[u]; }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++)
+      *reinterpret_cast<uint4*>(py + u * sy) = ssa_row<ACT, HAS_X2, HAS_RES>(vx[u], v2[u], vr[u], sc, sh, sc2);
+    px += U * sx;
+    if (HAS_X2) p2 += U * s2;
+    if (HAS_RES) pr += U * sr;
+    py += U * sy;
+  }
+  for (int i = trips * U; i < n; i++) {                      // at most U - 1 left-over rows
+    const uint4 a = *reinterpret_cast<const uint4*>(px);
+    const uint4 b = HAS_X2 ? *reinterpret_cast<const uint4*>(p2) : z4;
+    const uint4 d = HAS_RES ? *reinterpret_cast<const uint4*>(pr) : z4;
+    *reinterpret_cast<uint4*>(py) = ssa_row<ACT, HAS_X2, HAS_RES>(a, b, d, sc, sh, sc2);
+    px += sx;
+    if (HAS_X2) p2 += s2;
+    if (HAS_RES) pr += sr;
+    py += sy;
+  }
+}
+
 typedef void (*SsaFn)(const __nv_bfloat16*, long long, const float*, const float*, const __nv_bfloat16*, long long,
                       const float*, const float*, const __nv_bfloat16*, long long, __nv_bfloat16*, long long, long long,
                       int);
 
 template <int ACT>
-SsaFn ssa_pick(bool x2, bool res) {
+SsaFn ssa_pick(bool x2, bool res, bool pipelined) {
+  if (pipelined) {
+    if (x2) return res ? scale_shift_act_p_kernel<ACT, true, true> : scale_shift_act_p_kernel<ACT, true, false>;
+    return res ? scale_shift_act_p_kernel<ACT, false, true> : scale_shift_act_p_kernel<ACT, false, false>;
+  }
   if (x2) return res ? scale_shift_act_kernel<ACT, true, true> : scale_shift_act_kernel<ACT, true, false>;
   return res ? scale_shift_act_kernel<ACT, false, true> : scale_shift_act_kernel<ACT, false, false>;
 }
@@ -512,19 +657,23 @@ int ryolo_scale_shift_act(const void* x, long long xp, const float* scale, const
   RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && xp % 8 == 0 && yp % 8 == 0,
                "scale_shift_act: channels must be a multiple of 8 in [8, 2048]");
   RY_CHECK_ARG(scale && shift && (!x2 || (scale2 && shift2)), "scale_shift_act: missing scale/shift");
+  RY_CHECK_ARG(P < (1ll << 31) - (1 << 20), "scale_shift_act: more than 2^31 pixels");
   if (P == 0) return RYOLO_OK;
-  SsaFn fn;
-  switch (act) {
-    case RYOLO_ACT_LEAKY: fn = ssa_pick<RYOLO_ACT_LEAKY>(x2 != nullptr, residual != nullptr); break;
-    case RYOLO_ACT_MISH: fn = ssa_pick<RYOLO_ACT_MISH>(x2 != nullptr, residual != nullptr); break;
-    case RYOLO_ACT_SWISH: fn = ssa_pick<RYOLO_ACT_SWISH>(x2 != nullptr, residual != nullptr); break;
-    default: fn = ssa_pick<RYOLO_ACT_LINEAR>(x2 != nullptr, residual != nullptr); break;
-  }
   const int groups = C / 8;
   const int threads = groups >= 256 ? groups : 256;
   const int rows = threads / groups;
-  long long want = (P + (long long)rows * 4 - 1) / ((long long)rows * 4);
-  const int blocks = (int)(want > 148 * 16 ? 148 * 16 : (want < 1 ? 1 : want));
+  const bool pipelined = threads == 256 && ryolo_knob(RYOLO_KNOB_SSA) != 0;
+  SsaFn fn;
+  switch (act) {
+    case RYOLO_ACT_LEAKY: fn = ssa_pick<RYOLO_ACT_LEAKY>(x2 != nullptr, residual != nullptr, pipelined); break;
+    case RYOLO_ACT_MISH: fn = ssa_pick<RYOLO_ACT_MISH>(x2 != nullptr, residual != nullptr, pipelined); break;
+    case RYOLO_ACT_SWISH: fn = ssa_pick<RYOLO_ACT_SWISH>(x2 != nullptr, residual != nullptr, pipelined); break;
+    default: fn = ssa_pick<RYOLO_ACT_LINEAR>(x2 != nullptr, residual != nullptr, pipelined); break;
+  }
+  const int per_trip = pipelined ? ((x2 || residual) ? 2 : 4) : 4;
+  long long want = (P + (long long)rows * per_trip - 1) / ((long long)rows * per_trip);
+  const long long cap = pipelined ? 2ll * ry_sm_count() : 148 * 16;
+  const int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
   ry_launch(fn, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, xp, scale, shift,
             (const __nv_bfloat16*)x2, x2p, scale2, shift2, (const __nv_bfloat16*)residual, rp, (__nv_bfloat16*)y, yp, P, C);
   RY_CHECK_LAUNCH();

@@ -29,12 +29,15 @@ int ryolo_abi_version(void) { return 1; }
 //   nacc      conv: 1 = as many TMEM accumulators in rotation as fit (up to 8), 0 = two
 //   pdl       1 = the conv / wgrad / BatchNorm-backward / scale-shift-act kernels use programmatic dependent launch
 //   bn_bwd    BatchNorm backward: 0 = original passes, 1 = low-register reduce (stores dY), 2 = reduce without the dY
-//             store + an apply pass that recomputes the activation derivative
+//             store + an apply pass that recomputes the activation derivative, 3 (default) = variant 2's traffic with
+//             register double-buffered rows, a resident-capacity grid and the 13-instruction Mish derivative
+//   ssa       scale-shift-activation forward pass: 1 (default) = register double-buffered rows on a resident-capacity
+//             grid, 0 = the four-loads-then-compute kernel
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 2, 0, 1, 1, 1};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 
@@ -50,6 +53,17 @@ int ryolo_knob(int id) {
     g_knob_set[id] = true;
   }
   return g_knobs[id];
+}
+
+int ry_sm_count(void) {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 int ryolo_tune(const char* key, int value) {

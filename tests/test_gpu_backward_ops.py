@@ -211,3 +211,65 @@ def test_adam_step():
         opt.step()
         ops.adam_step(p, g.cuda(), m, v, 1e-3, it)
     assert torch.allclose(p.cpu(), ref.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
+@pytest.mark.parametrize("C,coff,Cbuf", [(32, 0, 32), (96, 8, 128), (256, 64, 384)])
+def test_pipelined_elementwise_kernels_many_rows_per_thread(act, C, coff, Cbuf):
+    """The register double-buffered kernels (knobs bn_bwd = 3, ssa = 1: resident-capacity grid, several trips per thread,
+    odd row counts so that the pair / quad loops, their last trip and the left-over rows all run) on channel slices of
+    wider buffers, against torch autograd, and against the original kernels (bn_bwd = 0, ssa = 0) at rounding level."""
+    import ryolo_b200._lib as L
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(C + len(act))
+    N, H, W = 1, 367, 373                                   # 136 891 pixels: 3-8 trips per thread at 296 blocks
+    raw = (torch.randn(N, H, W, Cbuf, generator=gen) * 1.5 + 0.3).bfloat16()
+    dout = torch.randn(N, H, W, Cbuf, generator=gen).bfloat16()
+    resid = torch.randn(N, H, W, Cbuf, generator=gen).bfloat16()
+    gamma = (torch.rand(C, generator=gen) + 0.5).requires_grad_(True)
+    beta = torch.randn(C, generator=gen).requires_grad_(True)
+    xr = raw[..., coff:coff + C].float().permute(0, 3, 1, 2).requires_grad_(True)
+    y = F.batch_norm(xr, None, None, gamma, beta, True, 0.1, 1e-5)
+    z = {"linear": y, "leaky": F.leaky_relu(y, 0.1), "mish": F.mish(y), "swish": F.silu(y)}[act]
+    z.backward(dout[..., coff:coff + C].float().permute(0, 3, 1, 2))
+    mean = raw[..., coff:coff + C].float().mean((0, 1, 2))
+    invstd = torch.rsqrt(raw[..., coff:coff + C].float().var((0, 1, 2), unbiased=False) + 1e-5)
+    scale = gamma.detach() * invstd
+    shift = beta.detach() - mean * scale
+    dev = [t.cuda() for t in (scale, shift, mean, invstd)]
+    rawc, doutc, resc = raw.cuda(), dout.cuda(), resid.cuda()
+    got = {}
+    try:
+        for variant in (3, 0):
+            L.tune(bn_bwd=variant, ssa=1 if variant else 0)
+            # forward: act(raw * scale + shift) (+ residual) into a slice of a wider buffer
+            for use_res in (False, True):
+                out = torch.full((N, H, W, Cbuf), 7.0, dtype=torch.bfloat16, device="cuda")
+                ops.scale_shift_act(ops.Act(rawc, C, coff), dev[0], dev[1], act, ops.Act(out, C, coff),
+                                    residual=ops.Act(resc, C, coff) if use_res else None)
+                assert float((out[..., :coff].float() - 7).abs().max() if coff else 0.0) == 0.0      # neighbours intact
+                assert float((out[..., coff + C:].float() - 7).abs().max() if coff + C < Cbuf else 0.0) == 0.0
+                got[("fwd", use_res, variant)] = out[..., coff:coff + C].float().cpu()
+            sums = torch.zeros(2 * C, device="cuda")
+            draw = torch.full((N, H, W, Cbuf), 7.0, dtype=torch.bfloat16, device="cuda")
+            dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+            ops.bn_act_bwd(ops.Act(doutc.clone(), C, coff), ops.Act(rawc, C, coff), *dev, act, sums, ops.Act(draw, C, coff),
+                           dg, db)
+            assert float((draw[..., coff + C:].float() - 7).abs().max() if coff + C < Cbuf else 0.0) == 0.0
+            got[("bwd", variant)] = (draw[..., coff:coff + C].float().cpu(), dg.cpu(), db.cpu())
+    finally:
+        L.tune(bn_bwd=3, ssa=1)
+    zr = z.detach().permute(0, 2, 3, 1)
+    for use_res in (False, True):
+        ref = zr + (resid[..., coff:coff + C].float() if use_res else 0.0)
+        a, b = got[("fwd", use_res, 3)], got[("fwd", use_res, 0)]
+        assert (a - ref).abs().max() < 1e-2 * ref.abs().max()
+        assert (a - b).abs().max() <= 2 ** -7 * ref.abs().max()              # both round the same value to bf16
+        assert float(((a - b).abs() > 0).float().mean()) < 0.02             # ... and almost always to the same one
+    ref = xr.grad.permute(0, 2, 3, 1)
+    d3, g3, b3 = got[("bwd", 3)]
+    d0, g0, b0 = got[("bwd", 0)]
+    assert (d3 - ref).abs().max() < 2e-2 * ref.abs().max()
+    assert (d3 - d0).abs().max() < 2e-2 * ref.abs().max()
+    assert (g3 - gamma.grad).abs().max() < 5e-3 * gamma.grad.abs().max()
+    assert (b3 - beta.grad).abs().max() < 5e-3 * beta.grad.abs().max()
