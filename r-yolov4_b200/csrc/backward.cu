@@ -456,14 +456,17 @@ __device__ __forceinline__ void reduce_row(const uint4& vd, const uint4& vr, con
   }
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(256, 2)
+// MAXT only sets the register budget (the block is always 256 threads): 256 -> 128 registers, 304 -> 104, which lets
+// two blocks share an SM with one 192-thread x 56-register wgrad CTA.  The block-level combine needs 8*C bytes of shared
+// memory (C <= 768) or none (direct global atomics), so that it fits beside that CTA's 13 x 16 KB boxes.
+template <int ACT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
 bn_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
                           long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
                           float* __restrict__ sums) {
   ry_pdl_wait();
-  extern __shared__ float red[];   // [rows][C] x 2
+  extern __shared__ float red[];   // [2][C] when C <= 768
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -501,18 +504,32 @@ bn_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, 
 #pragma unroll
     for (int j = 0; j < 8; j++) s2[j] = invstd[c + j] * (s2[j] - mean[c + j] * s1[j]);
   }
-  float* r1s = red;
-  float* r2s = red + (size_t)rows * C;
-  if (r < rows) {
-#pragma unroll
-    for (int j = 0; j < 8; j++) { r1s[r * C + c + j] = s1[j]; r2s[r * C + c + j] = s2[j]; }
+  // block-level combine: lanes holding the same channel group first add up by shuffle (groups a power of two <= 32:
+  // every thread of the warp is active), then one lane per (warp, group) adds into the block's 2*C floats
+  const bool use_smem = C <= 768;
+  if (use_smem) {
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
   }
-  __syncthreads();
-  for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
-    float a = 0.f, b = 0.f;
-    for (int rr = 0; rr < rows; rr++) { a += r1s[rr * C + cc]; b += r2s[rr * C + cc]; }
-    atomicAdd(sums + cc, a);
-    atomicAdd(sums + C + cc, b);
+  int leader = r < rows;
+  if (groups <= 32 && (groups & (groups - 1)) == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      for (int o = groups; o < 32; o <<= 1) {
+        s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+        s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+      }
+    }
+    leader = (threadIdx.x & 31) < groups;
+  }
+  if (leader) {
+    float* dst = use_smem ? red : sums;
+#pragma unroll
+    for (int j = 0; j < 8; j++) { atomicAdd(dst + c + j, s1[j]); atomicAdd(dst + C + c + j, s2[j]); }
+  }
+  if (use_smem) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) atomicAdd(sums + i, red[i]);
   }
 }
 
@@ -530,8 +547,8 @@ __device__ __forceinline__ uint4 apply_row(const uint4& vd, const uint4& vr, con
   return pack8(o);
 }
 
-template <int ACT>
-__global__ void __launch_bounds__(256, 2)
+template <int ACT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
 bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -958,12 +975,32 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
   // variant 3: persistent grid = resident capacity (2 blocks of 256 threads per SM), two rows per trip
   long long want3 = (P + 2ll * rows - 1) / (2ll * rows);
   const int blocks3 = (int)(want3 > 2ll * ry_sm_count() ? 2ll * ry_sm_count() : (want3 < 1 ? 1 : want3));
+  const size_t smem3 = C <= 768 ? (size_t)2 * C * sizeof(float) : 0;
+  const bool lean = ryolo_knob(RYOLO_KNOB_EW_REGS) != 0;
+  // Blocks of these kernels are meant to share SMs with a resident wgrad CTA, which runs under the maximum shared-memory
+  // carveout; an SM serves one carveout at a time, so the co-tenants must ask for the same one.
+  static bool carved = false;
+  if (!carved && ryolo_knob(RYOLO_KNOB_EW_REGS) >= 1 && ryolo_knob(RYOLO_KNOB_EW_REGS) != 2) {
+#define RY_CARVE(ACT)                                                                                                   \
+    cudaFuncSetAttribute(bn_act_bwd_reduce4_kernel<ACT, 304>, cudaFuncAttributePreferredSharedMemoryCarveout,            \
+                         cudaSharedmemCarveoutMaxShared);                                                                \
+    cudaFuncSetAttribute(bn_act_bwd_apply3_kernel<ACT, 304>, cudaFuncAttributePreferredSharedMemoryCarveout,             \
+                         cudaSharedmemCarveoutMaxShared);
+    RY_CARVE(RYOLO_ACT_LINEAR) RY_CARVE(RYOLO_ACT_LEAKY) RY_CARVE(RYOLO_ACT_MISH) RY_CARVE(RYOLO_ACT_SWISH)
+#undef RY_CARVE
+    carved = true;
+  }
 #define RY_BWD(ACT)                                                                                                  \
-  if (variant == 3) {                                                                                                \
-    ry_launch(bn_act_bwd_reduce4_kernel<ACT>, dim3(blocks3), dim3(threads), smem, st, (const __nv_bfloat16*)d, dp, r, rp, \
-              scale, shift, mean, invstd, P, C, sums);                                                               \
-    ry_launch(bn_act_bwd_apply3_kernel<ACT>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, rp, \
-              scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                           \
+  if (variant == 3 && lean) {                                                                                        \
+    ry_launch(bn_act_bwd_reduce4_kernel<ACT, 304>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, \
+              r, rp, scale, shift, mean, invstd, P, C, sums);                                                        \
+    ry_launch(bn_act_bwd_apply3_kernel<ACT, 304>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, \
+              rp, scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                       \
+  } else if (variant == 3) {                                                                                         \
+    ry_launch(bn_act_bwd_reduce4_kernel<ACT, 256>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, \
+              r, rp, scale, shift, mean, invstd, P, C, sums);                                                        \
+    ry_launch(bn_act_bwd_apply3_kernel<ACT, 256>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, \
+              rp, scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                       \
   } else if (variant == 2) {                                                                                                \
     ry_launch(bn_act_bwd_reduce3_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, (const __nv_bfloat16*)d, dp, r, rp, \
               scale, shift, mean, invstd, P, C, sums);                                                               \

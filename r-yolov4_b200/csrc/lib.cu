@@ -33,11 +33,16 @@ int ryolo_abi_version(void) { return 1; }
 //             register double-buffered rows, a resident-capacity grid and the 13-instruction Mish derivative
 //   ssa       scale-shift-activation forward pass: 1 (default) = register double-buffered rows on a resident-capacity
 //             grid, 0 = the four-loads-then-compute kernel
+//   wg_boxes  wgrad: 16 KB shared-memory boxes per CTA (10..14).  14 (default) = the whole SM; 13 leaves 16 KB so that two
+//             blocks of the HBM-bound BatchNorm-backward kernels fit on the same SM and run UNDER the side-stream wgrad
+//   ew_regs   BatchNorm backward (variant 3): 0 (default) = the 128-register builds, 1 = the <=104-register builds (two
+//             blocks + one wgrad CTA per SM) with the maximum shared-memory carveout, 2 = those with the default carveout
+//             (co-residency experiment, with RYOLO_BWD_PRIO=1: measured neutral on the step)
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

@@ -135,6 +135,7 @@ struct WgradParams {
   int ks_first[10];                         // tap group g owns CTAs [ks_first[g], ks_first[g+1]) of a pair's ks_total
   int a_boxes;                              // 64-channel dY boxes per A slot: 2, or 1 when Cout <= 64 (upper atom = a shared zero box)
   int slot_rows;                            // rows per smem box slot: 128, or 64 for wide Cin tiles (deeper ring)
+  int smem_boxes;                           // 16 KB boxes this CTA owns (knob wg_boxes: 14 = the whole SM, fewer leaves room for co-resident blocks)
   uint32_t tmem_cols;
   int dbg;                                  // RYOLO_WG_DBG timing experiments: 1 = no MMAs, 2 = no X loads (results are wrong)
   float* dw;                                // fp32 K-major [Cout][k*k][Cin] (16-byte aligned)
@@ -169,9 +170,9 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   // costs a_boxes + ntap*nb boxes; a CTA whose tap group is short keeps more patches in flight (with two A slots a
   // one-tap item ran at two patches per memory round trip).
   const int zero_box = p.a_boxes == 1 ? 1 : 0;
-  int a_slots = (kSmemBoxes - zero_box) / (p.a_boxes + ntap * p.nb);
+  int a_slots = (p.smem_boxes - zero_box) / (p.a_boxes + ntap * p.nb);
   a_slots = max(2, min(kMaxASlots, a_slots));
-  const int b_stages = min(kMaxBStages, (kSmemBoxes - zero_box - a_slots * p.a_boxes) / p.nb);
+  const int b_stages = min(kMaxBStages, (p.smem_boxes - zero_box - a_slots * p.a_boxes) / p.nb);
   const uint32_t sA = smem_base;
   const uint32_t sZ = sA + (uint32_t)(a_slots * p.a_boxes) * kBoxBytes;           // all-zero box (a_boxes == 1)
   const uint32_t sB = sZ + (uint32_t)zero_box * kBoxBytes;
@@ -202,7 +203,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
     const int tail16 = (p.slot_rows - rows) * 8;                   // 16-byte words per box tail
     if (rows < ((rows + 15) & ~15)) {
-      for (int i = threadIdx.x; i < kSmemBoxes * tail16; i += kThreads) {
+      for (int i = threadIdx.x; i < p.smem_boxes * tail16; i += kThreads) {
         const int b = i / tail16, w = i - b * tail16;
         *reinterpret_cast<uint4*>(base + (size_t)b * kBoxBytes + (size_t)rows * 128 + (size_t)w * 16) =
             make_uint4(0, 0, 0, 0);
@@ -701,7 +702,11 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   p.ks_total = p.ks_first[p.n_tap_groups];
   p.a_boxes = Cout > 64 ? 2 : 1;
   const size_t kBoxBytes = (size_t)p.slot_rows * 128;
-  const size_t smem = 1024 + (size_t)kSmemBoxes * kBoxBytes;
+  int boxes = ryolo_knob(RYOLO_KNOB_WG_BOXES);
+  p.smem_boxes = boxes < 10 ? 10 : (boxes > kSmemBoxes ? kSmemBoxes : boxes);
+  const bool trans = ryolo_knob(RYOLO_KNOB_WG_TRANS) && p.nb <= 2;
+  if (trans) p.smem_boxes = kSmemBoxes;
+  const size_t smem = 1024 + (size_t)p.smem_boxes * kBoxBytes, smem_max = 1024 + (size_t)kSmemBoxes * kBoxBytes;
   p.dw = dwk;
   p.dbg = ryolo_knob(RYOLO_KNOB_WG_DBG);
   CUtensorMap tmG, tmX;
@@ -712,13 +717,13 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   }
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e == cudaSuccess)
-      e = cudaFuncSetAttribute(conv_wgrad_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      e = cudaFuncSetAttribute(conv_wgrad_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
     if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     configured = true;
   }
-  if (ryolo_knob(RYOLO_KNOB_WG_TRANS) && p.nb <= 2)
+  if (trans)
     ry_launch(conv_wgrad_t_kernel, dim3(pairs * p.ks_total), dim3(kThreads), smem, (cudaStream_t)stream, tmG, tmX, p);
   else
     ry_launch(conv_wgrad_kernel, dim3(pairs * p.ks_total), dim3(kThreads), smem, (cudaStream_t)stream, tmG, tmX, p);

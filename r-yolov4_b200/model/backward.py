@@ -6,6 +6,8 @@ Gradients of activations live in bf16 NHWC buffers that mirror the forward buffe
 concat buffer has its gradient in the same slice of the mirrored buffer); weight gradients are fp32 and
 are ACCUMULATED into the tensors handed in by `param_grads` (zeroed by the caller).
 """
+import os
+
 import torch
 
 from .. import ops
@@ -107,15 +109,33 @@ def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
 
 
 _SIDE = {}
+_MAIN = {}
 WGRAD_SIDE_STREAM = True      # False: weight-gradient GEMMs on the main stream (clean per-launch timings in tools/)
+# Experiment switch (RYOLO_BWD_PRIO=1, off by default: measured neutral on the whole step): the critical
+# path of the backward pass (BatchNorm backward -> dgrad -> BatchNorm backward ...) runs on a HIGH-priority stream, the
+# weight-gradient GEMMs on a default-priority one.  When a layer's BatchNorm backward finishes, its dgrad and
+# its wgrad become runnable together and both want every SM (one CTA with > 200 KB of shared memory each): with equal
+# priorities the wgrad, enqueued first, wins and the chain behind the dgrad waits.  With priorities the dgrad goes first,
+# and the wgrad then runs UNDER the next layer's HBM-bound BatchNorm backward, whose blocks fit on the same SMs (two
+# 96-register blocks + 16 KB next to the 56-register wgrad CTA with 13 x 16 KB boxes): tensor-core work hidden behind
+# memory-bound work instead of time-sliced with it.
+BACKWARD_HIGH_PRIORITY = os.environ.get("RYOLO_BWD_PRIO", "0") != "0"
 
 
 def _side_stream(dev):
     """One extra stream per device for the weight-gradient GEMMs (see run_backward)."""
     key = dev.index if dev.index is not None else torch.cuda.current_device()
     if key not in _SIDE:
-        _SIDE[key] = torch.cuda.Stream(dev)
+        _SIDE[key] = torch.cuda.Stream(dev, priority=0)
     return _SIDE[key]
+
+
+def _main_stream(dev):
+    """High-priority stream carrying the backward pass's critical path."""
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    if key not in _MAIN:
+        _MAIN[key] = torch.cuda.Stream(dev, priority=-1)
+    return _MAIN[key]
 
 
 class _WgradSink:
@@ -172,6 +192,20 @@ class _WgradSink:
 
 
 def run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
+    """Runs the backward pass (see _run_backward) on the high-priority stream, fenced against the caller's stream on
+    both sides, so callers keep ordinary single-stream semantics."""
+    if not (BACKWARD_HIGH_PRIORITY and WGRAD_SIDE_STREAM):
+        return _run_backward(model, ctx, dlevels, param_grads, seed, on_entry)
+    cur = torch.cuda.current_stream()
+    hi = _main_stream(ctx.device)
+    hi.wait_stream(cur)
+    with torch.cuda.stream(hi):
+        G = _run_backward(model, ctx, dlevels, param_grads, seed, on_entry)
+    cur.wait_stream(hi)
+    return G
+
+
+def _run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
     """dlevels: 3 fp32 tensors [B, na, gs, gs, ch] (d loss / d level, strides 8, 16, 32).
     param_grads: dict id(parameter) -> fp32 tensor (same shape) that receives += d loss / d parameter.
     seed: optional [(activation, gradient Act)] pairs that pre-load output gradients (block-level tests).

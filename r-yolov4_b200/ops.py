@@ -240,10 +240,14 @@ def wgrad_to_oihw(dwk, Cout, Cin, k, stem=False):
 
 
 def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, dbeta):
+    if PROFILE is not None:
+        _prof_begin()
     L.check(L.lib().ryolo_bn_act_bwd(_vp(dout.ptr), dout.pitch, _vp(raw.ptr), raw.pitch, _tp(scale), _tp(shift),
                                      _tp(mean), _tp(invstd), ACT[act], raw.P, raw.C, _tp(sums), _vp(draw.ptr),
                                      draw.pitch, _tp(dgamma), _tp(dbeta), L.stream()))
     L.count(2)
+    if PROFILE is not None:
+        _prof_end(('bn_bwd', raw.P, raw.C, 0))
 
 
 def act_bwd2(dout, x1, s1, b1, x2, s2, b2, act, ds):

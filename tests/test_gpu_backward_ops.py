@@ -269,7 +269,12 @@ def test_pipelined_elementwise_kernels_many_rows_per_thread(act, C, coff, Cbuf):
     ref = xr.grad.permute(0, 2, 3, 1)
     d3, g3, b3 = got[("bwd", 3)]
     d0, g0, b0 = got[("bwd", 0)]
-    assert (d3 - ref).abs().max() < 2e-2 * ref.abs().max()
-    assert (d3 - d0).abs().max() < 2e-2 * ref.abs().max()
-    assert (g3 - gamma.grad).abs().max() < 5e-3 * gamma.grad.abs().max()
-    assert (b3 - beta.grad).abs().max() < 5e-3 * beta.grad.abs().max()
+    # LeakyReLU's kink: the kernels form z = raw * scale + shift, torch (x - mean) * invstd * gamma + beta; where z is
+    # within rounding of 0 the derivative flips between 1 and 0.1, so isolated elements differ by 0.9 |d out|
+    for other in (ref, d0):
+        bad = (d3 - other).abs() > 2e-2 * ref.abs().max()
+        assert float(bad.float().mean()) < (1e-4 if act == "leaky" else 0.0) + 1e-12, float(bad.float().mean())
+        assert float((d3 - other).norm() / ref.norm()) < 1e-2
+    tol = 1.5e-2 if act == "leaky" else 5e-3                 # a flipped element moves its channel's sums by ~|d out|
+    assert (g3 - gamma.grad).abs().max() < tol * gamma.grad.abs().max()
+    assert (b3 - beta.grad).abs().max() < tol * beta.grad.abs().max()
