@@ -226,9 +226,13 @@ int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp
 /* nearest x2 upsample backward: dx[N,H,W,C] (+)= 2x2 block sums of dy[N,2H,2W,C]                             */
 int ryolo_upsample2x_bwd(const void* dy, long long dyp, int N, int H, int W, int C, void* dx, long long dxp,
                          int accumulate, void* stream);
-/* loss gradient fp32 [B,na,H,W,ch] -> bf16 NHWC [B,H,W,Cpad] (x mul[c] if given) + dbias[c] += column sums    */
+/* loss gradient fp32 [B,na,H,W,ch] -> bf16 NHWC [B,H,W,Cpad] (x mul[c] if given) + dbias[c] += column sums.
+ * yolov7's implicit head y = im * (conv(x + ia) + b) (model/utils.py:163-186, model/neck.py:201,208,215), all nullable:
+ *   yhead  the head's forward output (same layout as glev): dmul[c] += sum glev * yhead / mul[c]  (= d ImplicitM)
+ *   dsum   fp32[>= na*ch], zeroed by the caller: receives the same column sums as dbias (= sum over pixels of d pre,
+ *          from which the caller forms d ImplicitA = W^T dsum and the (sum d pre) (x) ia term of d W)            */
 int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch, int Cpad, const float* mul, void* out,
-                         float* dbias, void* stream);
+                         float* dbias, const float* yhead, float* dsum, float* dmul, void* stream);
 /* torch.optim.SGD step (train.py:156: momentum, nesterov) on flat fp32 buffers:
  *   g = grad + wd*p;  buf = first ? g : momentum*buf + g;  p -= lr * (nesterov ? g + momentum*buf : buf)      */
 int ryolo_sgd_step(float* param, const float* grad, float* buf, long long n, float lr, float momentum,

@@ -860,10 +860,12 @@ upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, long long dyp, int N
 // its 8 source offsets and bias partials stay in registers.
 __global__ void __launch_bounds__(256)
 head_grad_pack_kernel(const float* __restrict__ glev, int B, int na, int H, int W, int ch, int Cpad,
-                      const float* __restrict__ mul, __nv_bfloat16* __restrict__ out, float* __restrict__ dbias) {
-  extern __shared__ float sb[];    // [Cpad] block-level bias partials
+                      const float* __restrict__ mul, __nv_bfloat16* __restrict__ out, float* __restrict__ dbias,
+                      const float* __restrict__ yhead, float* __restrict__ dsum, float* __restrict__ dmul) {
+  extern __shared__ float sb[];    // [Cpad] block-level bias partials | [Cpad] sum of glev * yhead (ImplicitM gradient)
+  float* sy = sb + Cpad;
   const int C = na * ch;
-  for (int c = threadIdx.x; c < Cpad; c += blockDim.x) sb[c] = 0.f;
+  for (int c = threadIdx.x; c < 2 * Cpad; c += blockDim.x) sb[c] = 0.f;
   __syncthreads();
   const int chunks = Cpad >> 3;
   const int rows = blockDim.x / chunks;
@@ -872,7 +874,7 @@ head_grad_pack_kernel(const float* __restrict__ glev, int B, int na, int H, int 
   const long long plane = (long long)H * W * ch;
   if (r < rows) {
     long long off[8];
-    float m[8], acc[8];
+    float m[8], acc[8], accy[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const int c = 8 * g + j;
@@ -880,25 +882,38 @@ head_grad_pack_kernel(const float* __restrict__ glev, int B, int na, int H, int 
       off[j] = c < C ? (long long)a * plane + k : -1;
       m[j] = (mul && c < C) ? mul[c] : 1.f;
       acc[j] = 0.f;
+      accy[j] = 0.f;
     }
     const long long hw = (long long)H * W;
     for (long long pix = (long long)blockIdx.x * rows + r; pix < npix; pix += (long long)gridDim.x * rows) {
       const long long b = pix / hw, p = pix - b * hw;
       const float* src = glev + b * na * plane + p * ch;
-      float v[8];
+      float gv[8], v[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) v[j] = off[j] >= 0 ? __ldg(src + off[j]) * m[j] : 0.f;
+      for (int j = 0; j < 8; j++) gv[j] = off[j] >= 0 ? __ldg(src + off[j]) : 0.f;
+      if (yhead) {                                  // yolov7: d ImplicitM_c = sum glev * pre_c, pre = yhead / mul
+        const float* ys = yhead + b * na * plane + p * ch;
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] += v[j];
+        for (int j = 0; j < 8; j++)
+          if (off[j] >= 0) accy[j] = fmaf(gv[j], __ldg(ys + off[j]), accy[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++) { v[j] = gv[j] * m[j]; acc[j] += v[j]; }
       *reinterpret_cast<uint4*>(out + pix * Cpad + 8 * g) = pack8(v);
     }
 #pragma unroll
     for (int j = 0; j < 8; j++)
-      if (off[j] >= 0) atomicAdd(&sb[8 * g + j], acc[j]);
+      if (off[j] >= 0) {
+        atomicAdd(&sb[8 * g + j], acc[j]);
+        if (yhead) atomicAdd(&sy[8 * g + j], accy[j]);
+      }
   }
   __syncthreads();
-  if (dbias)
-    for (int c = threadIdx.x; c < C; c += blockDim.x) atomicAdd(dbias + c, sb[c]);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    if (dbias) atomicAdd(dbias + c, sb[c]);
+    if (dsum) atomicAdd(dsum + c, sb[c]);
+    if (yhead && dmul) atomicAdd(dmul + c, sy[c] / mul[c]);
+  }
 }
 
 __global__ void __launch_bounds__(256)
@@ -1139,16 +1154,17 @@ int ryolo_adam_step(float* param, const float* grad, float* exp_avg, float* exp_
 }
 
 int ryolo_head_grad_pack(const float* glev, int B, int na, int H, int W, int ch, int Cpad, const float* mul, void* out,
-                         float* dbias, void* stream) {
+                         float* dbias, const float* yhead, float* dsum, float* dmul, void* stream) {
   RY_CHECK_ARG(Cpad % 8 == 0 && Cpad >= na * ch && Cpad <= 2048, "head_grad_pack: bad padded channel count");
+  RY_CHECK_ARG(!yhead || (mul && dmul), "head_grad_pack: the ImplicitM gradient needs mul and dmul");
   RY_CHECK_ARG((((uintptr_t)out) & 15) == 0, "head_grad_pack: output must be 16-byte aligned");
   const long long npix = (long long)B * H * W;
   if (npix == 0) return RYOLO_OK;
   const int rows = 256 / (Cpad / 8);
   long long want = (npix + 4ll * rows - 1) / (4ll * rows);
   const int blocks = (int)(want > 148 * 8 ? 148 * 8 : (want < 1 ? 1 : want));
-  head_grad_pack_kernel<<<blocks, 256, (size_t)Cpad * sizeof(float), (cudaStream_t)stream>>>(
-      glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias);
+  head_grad_pack_kernel<<<blocks, 256, (size_t)2 * Cpad * sizeof(float), (cudaStream_t)stream>>>(
+      glev, B, na, H, W, ch, Cpad, mul, (__nv_bfloat16*)out, dbias, yhead, dsum, dmul);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

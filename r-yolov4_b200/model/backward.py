@@ -75,20 +75,18 @@ def _accumulate(G, act, src):
     G.mark(act)
 
 
-def _implicit_head_grads(model, conv, gl, y, mul, param_grads):
-    """yolov7 head y = im * (conv(x + ia) + b): gradients of ImplicitM / ImplicitA (model/utils.py:163-186)."""
+def _implicit_head_grads(model, conv, dpre_sum, param_grads):
+    """yolov7 head y = im * (conv(x + ia) + b) (model/utils.py:163-186): what is left of the ImplicitA gradient once
+    ryolo_head_grad_pack has produced dpre_sum[c] = sum over pixels of d pre_c (and d ImplicitM) in its one pass over the
+    head gradient: a [Cin] matrix-vector product and a rank-1 update on Cout x Cin numbers."""
     neck = model.neck
     i = {id(getattr(neck, f"conv{4 + j}")): j for j in (1, 2, 3)}[id(conv)]
-    ia, im = getattr(neck, f"ia{i}"), getattr(neck, f"im{i}")
-    B, na, H, W, ch = gl.shape
-    d_im = (gl * y).sum((0, 2, 3)).reshape(-1) / mul                     # d/d im_c = sum dY * pre_c
-    param_grads[id(im.implicit)].add_(d_im.view_as(im.implicit))
-    dpre_sum = (gl.sum((0, 2, 3)).reshape(-1) * mul)                      # sum over pixels of d pre
-    w = conv.conv[0].weight.data.float().flatten(1)                       # [Cout, Cin]
-    param_grads[id(ia.implicit)].add_((w.t() @ dpre_sum).view_as(ia.implicit))
+    ia = getattr(neck, f"ia{i}")
+    w = conv.conv[0].weight.data.flatten(1)                               # [Cout, Cin] fp32
+    param_grads[id(ia.implicit)].add_((dpre_sum @ w).view_as(ia.implicit))
     # the conv's input is x + ia: the wgrad GEMM sees x only, the constant part contributes (sum d pre) (x) ia
-    param_grads[id(conv.conv[0].weight)].add_(
-        torch.outer(dpre_sum, ia.implicit.data.float().flatten()).view_as(conv.conv[0].weight))
+    param_grads[id(conv.conv[0].weight)].view(w.shape).addr_(dpre_sum, ia.implicit.data.flatten())
+
 
 def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
     """out = silu(bn_d(conv3x3(x)) + bn_1(conv1x1(x)))   (model/utils.py:209-215)."""
@@ -110,7 +108,7 @@ def _repconv_backward(mod, x, rd, r1, dout, affs, G, sums, param_grads, sink):
 
 _SIDE = {}
 _MAIN = {}
-WGRAD_SIDE_STREAM = True      # False: weight-gradient GEMMs on the main stream (clean per-launch timings in tools/)
+WGRAD_SIDE_STREAM = os.environ.get("RYOLO_WGRAD_SIDE", "1") != "0"   # False: weight-gradient GEMMs on the main stream
 # Experiment switch (RYOLO_BWD_PRIO=1, off by default: measured neutral on the whole step): the critical
 # path of the backward pass (BatchNorm backward -> dgrad -> BatchNorm backward ...) runs on a HIGH-priority stream, the
 # weight-gradient GEMMs on a default-priority one.  When a layer's BatchNorm backward finishes, its dgrad and
@@ -239,8 +237,14 @@ def _run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
             Cout = na * ch
             Cpad = (Cout + 7) // 8 * 8
             if mul is not None:        # yolov7: y = im * (conv(x + ia) + b)   (model/neck.py:201,208,215)
-                _implicit_head_grads(model, mod, gl, y, mul, param_grads)
-            dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias))
+                j = {id(getattr(model.neck, f"conv{4 + q}")): q for q in (1, 2, 3)}[id(mod)]
+                im = getattr(model.neck, f"im{j}")
+                dsum = torch.zeros(Cout, dtype=torch.float32, device=dev)
+                dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias), yhead=y.detach().contiguous(), dsum=dsum,
+                                          dmul=pg(im.implicit).view(-1))
+                _implicit_head_grads(model, mod, dsum, param_grads)
+            else:
+                dpre = ops.head_grad_pack(gl, Cpad, mul, pg(conv.bias))
             sink.wgrad(x, dpre, Cout, 1, 1, conv.weight, keep=(dpre,))
             w = conv.weight.data
             if Cpad != Cout:

@@ -276,11 +276,15 @@ def upsample2x_bwd(dy, dx, accumulate):
     L.count(1)
 
 
-def head_grad_pack(glev, Cpad, mul, dbias):
+def head_grad_pack(glev, Cpad, mul, dbias, yhead=None, dsum=None, dmul=None):
+    """fp32 head gradient -> bf16 NHWC d pre (+ bias gradient); with `yhead` (yolov7's implicit head) the same pass also
+    returns sum d pre per channel in `dsum` and accumulates the ImplicitM gradient into `dmul`."""
     B, na, H, W, ch = glev.shape
     out = Act.empty(B, H, W, Cpad, glev.device)
+    if yhead is not None:
+        assert yhead.shape == glev.shape and yhead.dtype == torch.float32 and yhead.is_contiguous()
     L.check(L.lib().ryolo_head_grad_pack(_tp(glev.contiguous()), B, na, H, W, ch, Cpad, _tp(mul), _vp(out.ptr),
-                                         _tp(dbias), L.stream()))
+                                         _tp(dbias), _tp(yhead), _tp(dsum), _tp(dmul), L.stream()))
     L.count(1)
     return out
 
