@@ -146,3 +146,36 @@ def test_kfloss_standalone_golden_and_scale():
     assert rel_err(kfiou.cpu(), ref_k) < TOL
     empty = R.KFLoss()(torch.zeros(0, 5).cuda(), torch.zeros(0, 5).cuda())
     assert float(empty[0]) == 0.0 and empty[1].numel() == 0
+
+
+def test_decode_csl_angle_argmax_ties_and_saturation():
+    """The CSL angle is argmax over the fp32 SIGMOID of 180 logits, first maximum wins (model/yololayer.py:39,48).  The
+    kernel only evaluates the sigmoid of logits that can tie with the largest one: check the cases where that matters —
+    a saturated plateau (every logit >= 16.64 maps to 1.0f: the FIRST of them wins, not the largest), exact duplicates,
+    near-saturation neighbours that still differ, -inf rows, and plain rows (argmax of the logits)."""
+    import ryolo_b200 as R
+    nc, gs, B = 2, 4, 2
+    gen = torch.Generator().manual_seed(11)
+    head = torch.randn(B, 3, gs, gs, nc + 185, generator=gen) * 3
+    ang = head[..., 5 + nc:]
+    ang.clamp_(max=9.0)
+    expect = torch.sigmoid(ang.double()).float().argmax(-1)      # maxima far from saturation (first one on ties)
+    cells = [(0, 0, 0, 0), (0, 1, 2, 3), (1, 2, 1, 1), (1, 0, 3, 2), (0, 2, 2, 2), (1, 1, 0, 3)]
+    # plateau: three saturated logits, the largest one last -> first index wins
+    ang[cells[0]][[40, 100, 150]] = torch.tensor([20.0, 25.0, 30.0]); expect[cells[0]] = 40
+    # plateau reached from below the cut-off of a huge maximum: 17 saturates too, and comes first
+    ang[cells[1]][[7, 90]] = torch.tensor([17.0, 80.0]); expect[cells[1]] = 7
+    # exact duplicates of the maximum
+    ang[cells[2]][[33, 34, 170]] = 12.5; expect[cells[2]] = 33
+    # neighbours below saturation that still round to different sigmoid values: the larger logit wins
+    ang[cells[3]][[10, 20]] = torch.tensor([15.4, 15.9]); expect[cells[3]] = 20
+    # 16.0 is not saturated (1 - 1.1e-7), 16.7 is
+    ang[cells[4]][[5, 60]] = torch.tensor([16.0, 16.7]); expect[cells[4]] = 60
+    # a row of -inf: every sigmoid is 0, index 0 wins
+    ang[cells[5]][:] = float("-inf"); expect[cells[5]] = 0
+    layer = R.YoloCSLLayer(nc, AN_CSL, [8, 16, 32])
+    heads = [head.cuda(), torch.zeros(B, 3, 2, 2, nc + 185).cuda(), torch.zeros(B, 3, 1, 1, nc + 185).cuda()]
+    _, infer = layer(heads, training=False)
+    got = infer[:, :3 * gs * gs, 4].cpu().view(B, 3, gs, gs)
+    want = (expect.float() - 90) / 180 * 3.14159274101257324
+    assert torch.equal(got, want.float()), (got - want).abs().max()
