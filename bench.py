@@ -333,6 +333,22 @@ def bench_train(env, wl, steps, warm, sample_clocks, use_graph=True):
     tc_ms = {}
     for tag, a, b in prof:
         tc_ms[tag[0]] = tc_ms.get(tag[0], 0.0) + a.elapsed_time(b) / psteps
+    # ... and once more with the weight-gradient GEMMs on the main stream: an event pair then brackets the kernel alone
+    # (in the headline configuration a conv / dgrad launch also waits for the SMs a side-stream wgrad CTA still holds)
+    from ryolo_b200.model import backward as BW
+    tc_ser = {}
+    side = BW.WGRAD_SIDE_STREAM
+    try:
+        BW.WGRAD_SIDE_STREAM = False
+        resident(1)
+        ops.PROFILE = []
+        env.timed(resident, psteps)
+        prof, ops.PROFILE = ops.PROFILE, None
+        for tag, a, b in prof:
+            tc_ser[tag[0]] = tc_ser.get(tag[0], 0.0) + a.elapsed_time(b) / psteps
+    finally:
+        BW.WGRAD_SIDE_STREAM = side
+        ops.PROFILE = None
 
     # ---- forward + loss only (BASELINE configs[1] wording), same model and inputs
     def fwd_loss(n):
@@ -422,7 +438,7 @@ def bench_train(env, wl, steps, warm, sample_clocks, use_graph=True):
             eager["graph_error"] = repr(e)[:300]
     res = dict(value=world * BS * steps / ms_total * 1e3, ms_per_step=ms_total / steps, launches=launches, clocks=clocks,
                eager=eager, execution=execution,
-               tc_ms=tc_ms, fwd_loss_img_s=world * BS * fl_steps / ms_fl * 1e3, fwd_loss_ms=ms_fl / fl_steps,
+               tc_ms=tc_ms, tc_ser=tc_ser, fwd_loss_img_s=world * BS * fl_steps / ms_fl * 1e3, fwd_loss_ms=ms_fl / fl_steps,
                e2e=dict(value=world * BS * steps / ms_e2e * 1e3, unit=UNIT,
                         h2d_bytes_per_step=int(host_imgs[0].numel() * 4 + host_tg[0].numel() * 4),
                         d2h_bytes_per_step=32, ms_per_step=ms_e2e / steps),
@@ -449,6 +465,13 @@ def roofline_of(res, wl, pk, pk_src):
            "wgrad": {"kernel": "conv_wgrad_kernel (side stream, overlapped)", "algorithmic_gflop_per_step": wg_gflop,
                      "achieved": wg_gflop / max(tc_ms.get("wgrad", 0.0), 1e-9)},
            "step_tensor_frac": 3 * wl["fwd_gflop"] * BS / res["ms_per_step"] / peak}
+    ser = res.get("tc_ser") or {}
+    if ser.get("conv") and ser.get("dgrad"):
+        t = gflop / (ser["conv"] + ser["dgrad"])
+        out["serialized"] = {"note": "same step with the wgrad GEMMs on the main stream: every event pair brackets one "
+                                     "kernel alone (no wait for SMs held by a side-stream CTA)",
+                             "achieved": t, "frac": t / peak, "ms_per_step": {k: round(v, 3) for k, v in ser.items()},
+                             "wgrad_achieved": wg_gflop / max(ser.get("wgrad", 0.0), 1e-9)}
     for name in ("r02_conv_traffic.json", "r01_conv_traffic.json"):   # made by tools/conv_traffic.py from an ncu pass
         tp = os.path.join(ROOT, "profiles", name)
         if wl["ver"] == "yolov4" and os.path.exists(tp):

@@ -739,50 +739,74 @@ maxpool_tiled_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, cons
 }
 
 // Same routing for a stride-1 "same" pool on a small map (SPP), one block per (image, 8 channels): the map, its row
-// maxima and an fp32 gradient tile live in shared memory.  The window maximum m is separable; the first maximum in
-// row-major scan order is the first row whose row-window maximum equals m, then the first column of that row equal to m
-// (2k comparisons per output and channel instead of k*k), and no global scratch / second pass is needed.
+// maxima WITH the column of their first maximum, and an fp32 gradient tile live in shared memory.  The window maximum is
+// separable; PyTorch's winner (first maximum in row-major scan order) is the first row whose row-window maximum equals
+// the window maximum, and inside that row the first column attaining it: both "first" rules are a strict > while
+// scanning forwards.  A thread owns 4 channels of a pixel (128-bit shared loads, four independent compare chains):
+// 2(2p+1) vector loads per output instead of ~4(2p+1) scalar ones with two data-dependent while loops.
 __global__ void __launch_bounds__(256)
 maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv_bfloat16* __restrict__ dy,
                               long long dyp, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, long long dxp,
                               int accumulate) {
-  extern __shared__ float sm_pb[];             // [H*W][8] map | [H*W][8] row maxima | [H*W][8] gradient
+  extern __shared__ float sm_pb[];             // [H*W][8] map | [H*W][8] row maxima | [H*W][8] gradient | [H*W][8] u8 columns
   const int HW = H * W, p = k >> 1;
   float* sx = sm_pb;
   float* sr = sm_pb + 8 * HW;
   float* sg = sm_pb + 16 * HW;
+  unsigned char* sa = reinterpret_cast<unsigned char*>(sm_pb + 24 * HW);
   const int groups = C >> 3;
   const int n = blockIdx.x / groups, c = (blockIdx.x % groups) * 8;
   const __nv_bfloat16* xb = x + (long long)n * HW * xp + c;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
     float f[8];
     unpack8(*reinterpret_cast<const uint4*>(xb + (long long)i * xp), f);
-#pragma unroll
-    for (int j = 0; j < 8; j++) { sx[i * 8 + j] = f[j]; sg[i * 8 + j] = 0.f; }
+    *reinterpret_cast<float4*>(sx + i * 8) = make_float4(f[0], f[1], f[2], f[3]);
+    *reinterpret_cast<float4*>(sx + i * 8 + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    *reinterpret_cast<float4*>(sg + i * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(sg + i * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
-    const int j = i & 7, pix = i >> 3;
+  // pass 1: per (pixel, 4 channels) the maximum of the row window and the first column that attains it
+  for (int i = threadIdx.x; i < HW * 2; i += blockDim.x) {
+    const int pix = i >> 1, q = (i & 1) * 4;
     const int h = pix / W, w = pix - h * W;
     const int w0 = max(w - p, 0), w1 = min(w + p, W - 1);
-    float m = sx[(h * W + w0) * 8 + j];
-    for (int ww = w0 + 1; ww <= w1; ww++) m = fmaxf(m, sx[(h * W + ww) * 8 + j]);
-    sr[i] = m;
+    float4 m = *reinterpret_cast<const float4*>(sx + (h * W + w0) * 8 + q);
+    int ax = w0, ay = w0, az = w0, aw = w0;
+    for (int ww = w0 + 1; ww <= w1; ww++) {
+      const float4 v = *reinterpret_cast<const float4*>(sx + (h * W + ww) * 8 + q);
+      if (v.x > m.x) { m.x = v.x; ax = ww; }
+      if (v.y > m.y) { m.y = v.y; ay = ww; }
+      if (v.z > m.z) { m.z = v.z; az = ww; }
+      if (v.w > m.w) { m.w = v.w; aw = ww; }
+    }
+    *reinterpret_cast<float4*>(sr + pix * 8 + q) = m;
+    *reinterpret_cast<uchar4*>(sa + pix * 8 + q) = make_uchar4((unsigned char)ax, (unsigned char)ay, (unsigned char)az,
+                                                               (unsigned char)aw);
   }
   __syncthreads();
+  // pass 2: scan the rows of the window; the first row with the largest row maximum holds the winner
   const __nv_bfloat16* gb = dy + (long long)n * HW * dyp + c;
-  for (int i = threadIdx.x; i < HW * 8; i += blockDim.x) {
-    const int j = i & 7, pix = i >> 3;
+  for (int i = threadIdx.x; i < HW * 2; i += blockDim.x) {
+    const int pix = i >> 1, q = (i & 1) * 4;
     const int h = pix / W, w = pix - h * W;
     const int h0 = max(h - p, 0), h1 = min(h + p, H - 1);
-    const int w0 = max(w - p, 0), w1 = min(w + p, W - 1);
-    float m = sr[(h0 * W + w) * 8 + j];
-    for (int hh = h0 + 1; hh <= h1; hh++) m = fmaxf(m, sr[(hh * W + w) * 8 + j]);
-    int hs = h0;
-    while (hs < h1 && sr[(hs * W + w) * 8 + j] != m) hs++;          // first row holding the maximum
-    int ws = w0;
-    while (ws < w1 && sx[(hs * W + ws) * 8 + j] != m) ws++;         // first column of that row
-    atomicAdd(&sg[(hs * W + ws) * 8 + j], __bfloat162float(gb[(long long)pix * dyp + j]));
+    float4 m = *reinterpret_cast<const float4*>(sr + (h0 * W + w) * 8 + q);
+    int rx = h0, ry = h0, rz = h0, rw = h0;
+    for (int hh = h0 + 1; hh <= h1; hh++) {
+      const float4 v = *reinterpret_cast<const float4*>(sr + (hh * W + w) * 8 + q);
+      if (v.x > m.x) { m.x = v.x; rx = hh; }
+      if (v.y > m.y) { m.y = v.y; ry = hh; }
+      if (v.z > m.z) { m.z = v.z; rz = hh; }
+      if (v.w > m.w) { m.w = v.w; rw = hh; }
+    }
+    const uint2 graw = *reinterpret_cast<const uint2*>(gb + (long long)pix * dyp + q);
+    const float g0 = __uint_as_float(graw.x << 16), g1 = __uint_as_float(graw.x & 0xffff0000u);
+    const float g2 = __uint_as_float(graw.y << 16), g3 = __uint_as_float(graw.y & 0xffff0000u);
+    atomicAdd(&sg[(rx * W + sa[(rx * W + w) * 8 + q + 0]) * 8 + q + 0], g0);
+    atomicAdd(&sg[(ry * W + sa[(ry * W + w) * 8 + q + 1]) * 8 + q + 1], g1);
+    atomicAdd(&sg[(rz * W + sa[(rz * W + w) * 8 + q + 2]) * 8 + q + 2], g2);
+    atomicAdd(&sg[(rw * W + sa[(rw * W + w) * 8 + q + 3]) * 8 + q + 3], g3);
   }
   __syncthreads();
   __nv_bfloat16* db = dx + (long long)n * HW * dxp + c;
@@ -1083,12 +1107,12 @@ int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp
   const long long P = (long long)N * H * W;
   if (P == 0) return RYOLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  if (stride == 1 && (k & 1) && pad == k / 2 && H * W <= 1024 && (long long)N * (C / 8) < (1ll << 31)) {
-    const size_t smem = (size_t)24 * H * W * sizeof(float);          // <= 96 KB
+  if (stride == 1 && (k & 1) && pad == k / 2 && H * W <= 1024 && W <= 256 && (long long)N * (C / 8) < (1ll << 31)) {
+    const size_t smem = (size_t)26 * H * W * sizeof(float);          // three fp32 [HW][8] tiles + [HW][8] bytes: <= 104 KB
     static bool configured = false;
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(maxpool_same_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           96 * 1024);
+                                           104 * 1024);
       if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
       configured = true;
     }
