@@ -38,11 +38,13 @@ int ryolo_abi_version(void) { return 1; }
 //   ew_regs   BatchNorm backward (variant 3): 0 (default) = the 128-register builds, 1 = the <=104-register builds (two
 //             blocks + one wgrad CTA per SM) with the maximum shared-memory carveout, 2 = those with the default carveout
 //             (co-residency experiment, with RYOLO_BWD_PRIO=1: measured neutral on the step)
+//   nms_band  post_process: tiles (of 64 boxes) per band of the banded greedy NMS (pair work of the kept rows against
+//             still-alive columns only; default 8, at most 16), 0 = the full N^2/2 mask followed by one scan
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0, 8};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

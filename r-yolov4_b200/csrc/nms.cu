@@ -132,13 +132,36 @@ eval_match_kernel(const float* __restrict__ dets, const int32_t* __restrict__ n_
 // grid (col block, row block, image); 256 threads.  Phase 1 rejects far-apart pairs with a
 // conservative bounding-circle test and compacts the survivors into a shared queue so that phase 2
 // (the ~2 kFLOP polygon clip) runs on fully populated warps.
+//
+// Banded use (post_process, see ryolo_post_process): greedy NMS only ever needs the mask rows of boxes that end up KEPT,
+// and only against columns that are still alive.  The candidates are walked in bands of `band` tiles; per band
+//   nms_band_suppress_kernel   every box kept so far against the band's columns -> `rem` (suppressed bits), no mask stored
+//   nms_mask_kernel            (this kernel, rb0 = cb0 = first tile of the band, grid band x band) the band's own
+//                              triangle, rows / columns already suppressed skipped; mask words stored for the scan
+//   nms_band_scan_kernel       the greedy scan of the band: kept boxes, running count, `done` once max_det is reached
+// An image whose max_det keeps are complete drops out of every later launch, so no pair is evaluated for candidates
+// the scan never reaches.  Same pair decisions, same greedy order: the survivors are those of the full mask.
+struct BandState { int nk; int done; };
+constexpr int kBandMax = 16;      // tiles per band: knob nms_band (default 8)
+
 __global__ void __launch_bounds__(256)
 nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ counts, int64_t prep_stride,
-                int words, float thr, unsigned long long* __restrict__ mask, int64_t mask_stride) {
-  const int cb = blockIdx.x, rb = blockIdx.y, img = blockIdx.z;
-  if (rb > cb) return;
+                int words, float thr, unsigned long long* __restrict__ mask, int64_t mask_stride,
+                int rb0, int cb0, const unsigned long long* __restrict__ rem, const BandState* __restrict__ state) {
+  const int cb = cb0 + blockIdx.x, rb = rb0 + blockIdx.y, img = blockIdx.z;
+  if (rb > cb || cb >= words) return;
   const int K = counts[img];
   if (cb * kTile >= K) return;
+  unsigned long long rowdead = 0ull, coldead = 0ull;      // bit set = this row / column cannot matter any more
+  if (rem) {
+    if (state[img].done) return;
+    rem += (int64_t)img * words;
+    coldead = rem[cb];
+    rowdead = rem[rb];
+    const int nvc = min(kTile, K - cb * kTile);
+    const unsigned long long valid = nvc == 64 ? ~0ull : ((1ull << nvc) - 1ull);
+    if (!(~coldead & valid) || !~rowdead) return;
+  }
   prep += (int64_t)img * prep_stride;
   mask += (int64_t)img * mask_stride;
 
@@ -172,7 +195,7 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
   for (int p = tid; p < kTile * kTile; p += 256) {
     int i = p >> 6, j = p & 63;
     int gi = rb * kTile + i, gj = cb * kTile + j;
-    bool live = (gi < gj) && (gj < K);
+    bool live = (gi < gj) && (gj < K) && !((rowdead >> i) & 1ull) && !((coldead >> j) & 1ull);
     if (live && use_reject) {
       live = !rbox_far_soa(qx[0][i], qy[0][i], qw[0][i], qh[0][i], qr[0][i], qx[1][j], qy[1][j], qw[1][j], qh[1][j],
                            qr[1][j]);
@@ -220,6 +243,185 @@ nms_mask_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ coun
     int gi = rb * kTile + tid;
     if (gi < K) mask[(int64_t)gi * words + cb] = tmask[tid];
   }
+}
+
+// One block per (column tile of the band, image): streams the boxes kept so far (keep_pos[0 .. nk), 64 at a time, best
+// scores first) past the tile's 64 columns and marks the columns they suppress.  Columns die progressively — the
+// top-scoring keeps suppress most of what can be suppressed — and the loop stops when none is left alive, so a pair is
+// only evaluated between a KEPT box and a column that is still alive when its turn comes.
+__global__ void __launch_bounds__(256)
+nms_band_suppress_kernel(const RPrep* __restrict__ prep, const int32_t* __restrict__ counts, int64_t prep_stride,
+                         int words, float thr, int cb0, unsigned long long* __restrict__ rem,
+                         const BandState* __restrict__ state, const int32_t* __restrict__ keep_pos, int64_t keep_stride) {
+  const int cb = cb0 + blockIdx.x, img = blockIdx.y;
+  if (cb >= words || state[img].done) return;
+  const int K = counts[img];
+  if (cb * kTile >= K) return;
+  const int nk = state[img].nk;                  // < max_det (otherwise the image is done): all of them are in keep_pos
+  if (nk == 0) return;
+  prep += (int64_t)img * prep_stride;
+  rem += (int64_t)img * words;
+  keep_pos += (int64_t)img * keep_stride;
+
+  __shared__ RPrep srow[kTile], scol[kTile];
+  __shared__ float qx[2][kTile], qy[2][kTile], qr[2][kTile];
+  __shared__ float qw[2][kTile], qh[2][kTile], qc[2][kTile], qs[2][kTile], qa[2][kTile];
+  __shared__ unsigned short queue[kTile * kTile], queue2[kTile * kTile];
+  __shared__ unsigned long long s_dead;
+  __shared__ int qn, qn2;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int nvc = min(kTile, K - cb * kTile);
+  if (tid < kTile) {
+    const RPrep p = prep[min(cb * kTile + tid, K - 1)];
+    scol[tid] = p; qx[1][tid] = p.cx; qy[1][tid] = p.cy; qr[1][tid] = p.reach;
+    qw[1][tid] = p.w; qh[1][tid] = p.h; qc[1][tid] = p.c2; qs[1][tid] = p.s2; qa[1][tid] = p.area;
+  }
+  if (tid == 0) s_dead = rem[cb] | (nvc == 64 ? 0ull : ~((1ull << nvc) - 1ull));
+  const bool use_reject = thr >= 0.f;
+  const bool use_bounds = thr >= 1e-6f;
+  for (int r0 = 0; r0 < nk; r0 += kTile) {
+    __syncthreads();                               // previous chunk done with srow / queues; s_dead up to date
+    const unsigned long long dead = s_dead;
+    if (!~dead) break;                             // uniform: every thread read the same word after the barrier
+    const int nrow = min(kTile, nk - r0);
+    if (tid < kTile) {
+      const RPrep p = prep[keep_pos[r0 + min(tid, nrow - 1)]];
+      srow[tid] = p; qx[0][tid] = p.cx; qy[0][tid] = p.cy; qr[0][tid] = p.reach;
+      qw[0][tid] = p.w; qh[0][tid] = p.h; qc[0][tid] = p.c2; qs[0][tid] = p.s2; qa[0][tid] = p.area;
+    }
+    if (tid == 0) { qn = 0; qn2 = 0; }
+    __syncthreads();
+#pragma unroll 4
+    for (int p = tid; p < kTile * kTile; p += 256) {
+      const int i = p >> 6, j = p & 63;
+      bool live = (i < nrow) && !((dead >> j) & 1ull);
+      if (live && use_reject) {
+        live = !rbox_far_soa(qx[0][i], qy[0][i], qw[0][i], qh[0][i], qr[0][i], qx[1][j], qy[1][j], qw[1][j], qh[1][j],
+                             qr[1][j]);
+        if (live && use_bounds)
+          live = !rbox_cannot_exceed(qx[0][i], qy[0][i], qw[0][i], qh[0][i], qc[0][i], qs[0][i], qa[0][i], qx[1][j],
+                                     qy[1][j], qw[1][j], qh[1][j], qc[1][j], qs[1][j], qa[1][j], thr);
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, live);
+      if (b) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&qn, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (live) queue[base + __popc(b & ((1u << lane) - 1))] = (unsigned short)p;
+      }
+    }
+    __syncthreads();
+    const int nq = qn;
+    for (int q0 = 0; q0 < nq; q0 += 256) {
+      const int q = q0 + tid;
+      int verdict = 0, p = 0;
+      if (q < nq) {
+        p = queue[q];
+        verdict = rbox_iou_exceeds_quick(srow[p >> 6], scol[p & 63], thr);
+        if (verdict > 0) atomicOr(&s_dead, 1ull << (p & 63));
+      }
+      const unsigned b = __ballot_sync(0xffffffffu, verdict < 0);
+      if (b) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&qn2, __popc(b));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (verdict < 0) queue2[base + __popc(b & ((1u << lane) - 1))] = (unsigned short)p;
+      }
+    }
+    __syncthreads();
+    const int nq2 = qn2;
+    for (int q = tid; q < nq2; q += 256) {
+      const int p = queue2[q];
+      if (rbox_iou_full(srow[p >> 6], scol[p & 63]) > thr) atomicOr(&s_dead, 1ull << (p & 63));
+    }
+  }
+  __syncthreads();
+  if (tid == 0) rem[cb] = s_dead & (nvc == 64 ? ~0ull : ((1ull << nvc) - 1ull));
+}
+
+// One warp per image: the greedy scan of ONE band (chunks [c0, c0 + kBand)).  `rem` holds, for every chunk, the boxes
+// suppressed by kept boxes of EARLIER bands (nms_band_suppress_kernel); suppression inside the band comes from the mask
+// words nms_mask_kernel stored for the band's triangle.  Records the kept boxes (keep_pos, kept bits per chunk) and the running count.
+__global__ void __launch_bounds__(32)
+nms_band_scan_kernel(const unsigned long long* __restrict__ mask, int64_t mask_stride, int words,
+                     const int32_t* __restrict__ counts, int max_det, int c0, int kBand,
+                     const unsigned long long* __restrict__ rem, unsigned long long* __restrict__ kept,
+                     BandState* __restrict__ state, int32_t* __restrict__ keep_pos, int64_t keep_stride) {
+  __shared__ unsigned long long srem[kBandMax];
+  const int img = blockIdx.x, lane = threadIdx.x;
+  if (state[img].done) return;
+  const int K = counts[img];
+  mask += (int64_t)img * mask_stride;
+  keep_pos += (int64_t)img * keep_stride;
+  rem += (int64_t)img * words;
+  kept += (int64_t)img * words;
+  const int nchunk = (K + kTile - 1) / kTile;
+  const int c1 = min(c0 + kBand, nchunk);
+  if (lane < kBand) srem[lane] = (c0 + lane < words) ? rem[c0 + lane] : 0ull;
+  __syncwarp();
+  int nk = state[img].nk;
+  for (int c = c0; c < c1 && nk < max_det; c++) {
+    const int r0 = c * kTile;
+    unsigned long long dlo = 0, dhi = 0;
+    unsigned long long cur = srem[c - c0], kb = 0ull;
+    // rows nms_mask_kernel skipped (already suppressed) have stale mask words: they are never read (never kept)
+    if (r0 + lane < K && !((cur >> lane) & 1ull)) dlo = mask[(int64_t)(r0 + lane) * words + c];
+    if (r0 + 32 + lane < K && !((cur >> (lane + 32)) & 1ull)) dhi = mask[(int64_t)(r0 + 32 + lane) * words + c];
+    const int nb = min(kTile, K - r0);
+    for (int b = 0; b < nb; b++) {
+      unsigned long long d = __shfl_sync(0xffffffffu, (b < 32) ? dlo : dhi, b & 31);
+      if (!((cur >> b) & 1ull)) { kb |= 1ull << b; cur |= d; }
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      int b = lane + 32 * h;
+      if ((kb >> b) & 1ull) {
+        int pos = nk + __popcll(kb & ((1ull << b) - 1ull));
+        if (pos < max_det) keep_pos[pos] = r0 + b;
+      }
+    }
+    // boxes kept beyond max_det are never emitted, but they were kept: they keep suppressing (same as the full scan,
+    // which stops right after this chunk anyway)
+    nk += __popcll(kb);
+    if (lane == 0) kept[c] = kb;
+    // fold the kept rows into the later chunks of this band
+    const int w = c + 1 + lane;
+    if (w < c1) {
+      unsigned long long v = 0ull, k2 = kb;
+      while (k2) {
+        const int b0 = __ffsll((long long)k2) - 1; k2 &= k2 - 1;
+        v |= mask[(int64_t)(r0 + b0) * words + w];
+      }
+      srem[w - c0] |= v;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    state[img].nk = nk;
+    if (nk >= max_det || c1 >= nchunk) state[img].done = 1;
+  }
+}
+
+// tail of post_process (lib/general.py:178-181): first max_det kept boxes, gathered from the sorted rows
+__global__ void __launch_bounds__(128)
+nms_band_gather_kernel(const BandState* __restrict__ state, int max_det, const int32_t* __restrict__ keep_pos,
+                       int64_t keep_stride, const float* __restrict__ dets_sorted,
+                       const int32_t* __restrict__ rows_sorted, int64_t sorted_stride, float* __restrict__ dets_out,
+                       int64_t* __restrict__ rows_out, int32_t* __restrict__ n_keep) {
+  const int img = blockIdx.x;
+  const int nk = min(state[img].nk, max_det);
+  keep_pos += (int64_t)img * keep_stride;
+  dets_sorted += (int64_t)img * sorted_stride * 7;
+  rows_sorted += (int64_t)img * sorted_stride;
+  dets_out += (int64_t)img * max_det * 7;
+  rows_out += (int64_t)img * max_det;
+  if (threadIdx.x == 0) n_keep[img] = nk;
+  for (int e = threadIdx.x; e < nk * 7; e += blockDim.x) {
+    const int j = e / 7, f = e - 7 * j;
+    dets_out[e] = dets_sorted[(int64_t)keep_pos[j] * 7 + f];
+  }
+  for (int j = threadIdx.x; j < nk; j += blockDim.x) rows_out[j] = (int64_t)rows_sorted[keep_pos[j]];
 }
 
 // ------------------------------------------------------------------------------------ NMS scan
@@ -614,7 +816,7 @@ int ryolo_nms_rotated(const float* boxes5, const float* scores, int64_t n, float
   }
   prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes5, order, n, prep);
   dim3 grid(words, words, 1);
-  nms_mask_kernel<<<grid, 256, 0, st>>>(prep, count, 0, words, iou_thr, mask, 0);
+  nms_mask_kernel<<<grid, 256, 0, st>>>(prep, count, 0, words, iou_thr, mask, 0, 0, 0, nullptr, nullptr);
   size_t scan_smem = (size_t)words * 8;
   if (scan_smem > 48 * 1024)
     cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
@@ -624,7 +826,7 @@ int ryolo_nms_rotated(const float* boxes5, const float* scores, int64_t n, float
   return RYOLO_OK;
 }
 
-static void pp_layout(int64_t B, int64_t R, int max_nms, size_t* off, size_t* total) {
+static void pp_layout(int64_t B, int64_t R, int max_nms, size_t* off, size_t* total) {   // off[9]
   const int words = (max_nms + 63) / 64;
   size_t s = 0;
   off[0] = s; s += ry_align_up((size_t)B * R * 4, 256);                          // score
@@ -635,12 +837,13 @@ static void pp_layout(int64_t B, int64_t R, int max_nms, size_t* off, size_t* to
   off[5] = s; s += ry_align_up((size_t)B * 4, 256);                              // counts (K per image)
   off[6] = s; s += ry_align_up((size_t)B * max_nms * words * 8, 256);            // mask
   off[7] = s; s += ry_align_up((size_t)B * max_nms * 4, 256);                    // keep_pos
+  off[8] = s; s += ry_align_up((size_t)B * words * 8 * 2 + (size_t)B * sizeof(BandState), 256);   // rem | kept | state
   *total = s;
 }
 
 size_t ryolo_post_process_workspace(int64_t B, int64_t R, int nc, int max_nms) {
   (void)nc;
-  size_t off[8], total;
+  size_t off[9], total;
   pp_layout(B, R, max_nms, off, &total);
   return total;
 }
@@ -660,7 +863,7 @@ int ryolo_post_process(float* pred, int64_t B, int64_t R, int nc, float conf_thr
   cudaStream_t st = (cudaStream_t)stream;
   if (B == 0) return RYOLO_OK;
   if (R == 0) { cudaMemsetAsync(n_out, 0, (size_t)B * 4, st); return RYOLO_OK; }
-  size_t off[8], total;
+  size_t off[9], total;
   pp_layout(B, R, max_nms, off, &total);
   RY_CHECK_ARG(ws_bytes >= total, "post_process: workspace too small");
   char* w = (char*)workspace;
@@ -683,11 +886,36 @@ int ryolo_post_process(float* pred, int64_t B, int64_t R, int nc, float conf_thr
   cudaFuncSetAttribute(pp_select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSortCap * 8);
   pp_select_sort_kernel<<<(unsigned)B, 1024, kSortCap * 8, st>>>(pred, score, cls, R, nc, conf_thres, max_nms, max_wh,
                                                                dets_sorted, rows_sorted, prep, counts);
-  dim3 grid(words, words, (unsigned)B);
-  nms_mask_kernel<<<grid, 256, 0, st>>>(prep, counts, max_nms, words, iou_thres, mask, (int64_t)max_nms * words);
-  nms_scan_kernel<<<(unsigned)B, 32, (size_t)words * 8, st>>>(mask, (int64_t)max_nms * words, words, counts, max_det,
-                                                             keep_pos, max_nms, n_out, dets_sorted, rows_sorted,
-                                                             max_nms, dets_out, rows_out, nullptr, nullptr);
+  int kBand = ryolo_knob(RYOLO_KNOB_NMS_BAND);
+  if (kBand > kBandMax) kBand = kBandMax;
+  if (kBand <= 0) {           // the full N^2 / 2 mask, then one scan (round-1 path, A/B switch)
+    dim3 grid(words, words, (unsigned)B);
+    nms_mask_kernel<<<grid, 256, 0, st>>>(prep, counts, max_nms, words, iou_thres, mask, (int64_t)max_nms * words, 0, 0,
+                                          nullptr, nullptr);
+    nms_scan_kernel<<<(unsigned)B, 32, (size_t)words * 8, st>>>(mask, (int64_t)max_nms * words, words, counts, max_det,
+                                                               keep_pos, max_nms, n_out, dets_sorted, rows_sorted,
+                                                               max_nms, dets_out, rows_out, nullptr, nullptr);
+    RY_CHECK_LAUNCH();
+    return RYOLO_OK;
+  }
+  // Banded greedy NMS (see nms_mask_kernel): per band of kBand tiles  kept-so-far rows against the band's columns ->
+  // triangle mask of the band -> scan.  3 launches per band, no host synchronisation (the band count comes from max_nms).
+  unsigned long long* rem = (unsigned long long*)(w + off[8]);
+  unsigned long long* keptb = rem + (size_t)B * words;
+  BandState* state = (BandState*)(keptb + (size_t)B * words);
+  cudaMemsetAsync(rem, 0, (size_t)B * words * 8 * 2 + (size_t)B * sizeof(BandState), st);
+  const int64_t mstride = (int64_t)max_nms * words;
+  for (int c0 = 0; c0 < words; c0 += kBand) {
+    if (c0 > 0)          // every box kept so far against this band's columns: fills rem[c0 .. c0 + kBand)
+      nms_band_suppress_kernel<<<dim3(kBand, (unsigned)B), 256, 0, st>>>(prep, counts, max_nms, words, iou_thres, c0, rem,
+                                                                        state, keep_pos, max_nms);
+    nms_mask_kernel<<<dim3(kBand, kBand, (unsigned)B), 256, 0, st>>>(prep, counts, max_nms, words, iou_thres, mask, mstride,
+                                                                    c0, c0, rem, state);
+    nms_band_scan_kernel<<<(unsigned)B, 32, 0, st>>>(mask, mstride, words, counts, max_det, c0, kBand, rem, keptb, state,
+                                                    keep_pos, max_nms);
+  }
+  nms_band_gather_kernel<<<(unsigned)B, 128, 0, st>>>(state, max_det, keep_pos, max_nms, dets_sorted, rows_sorted, max_nms,
+                                                     dets_out, rows_out, n_out);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -83,7 +83,7 @@ def post_process_device(predictions, conf_thres=0.5, iou_thres=0.4, mutate=True)
     L.check(lib.ryolo_post_process(L.ptr(predictions), B, R, nc, float(conf_thres), float(iou_thres), MAX_NMS, MAX_DET,
                                    MAX_WH, 1 if mutate else 0, L.ptr(dets), L.ptr(rows), L.ptr(n), L.ptr(ws), nb,
                                    L.stream()))
-    L.count(4)
+    L.count(3 + 3 * (((MAX_NMS + 63) // 64 + 7) // 8))    # score, select/sort, gather + 3 launches per NMS band (8 tiles)
     return dets, rows, n
 
 

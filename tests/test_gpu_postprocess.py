@@ -181,3 +181,38 @@ def test_post_process_full_config5_bit_exact_vs_oracle():
         assert torch.equal(p[i].cpu(), mut), f"in-place cls*=obj differs for image {i}"
         kept += r.numel()
     assert 0 < kept <= 64 * 1500
+
+
+@pytest.mark.parametrize("nc,conf,iou,clustered,R_", [(2, 0.001, 0.65, True, 30000), (2, 0.001, 0.65, False, 30000),
+                                                       (16, 0.25, 0.3, True, 12000), (2, 0.9, 0.1, True, 3000)])
+def test_banded_nms_equals_full_mask_nms(nc, conf, iou, clustered, R_):
+    """post_process's banded greedy NMS (triangle mask of a band -> scan -> kept rows against the still-alive later
+    columns, early exit at max_det) returns exactly what the full N^2/2 mask + single scan returns (knob nms_band = 0):
+    same survivors, same order, same counts — also when the workspace still holds another call's masks, on images that
+    fill max_det early, images with few candidates and empty images."""
+    import ryolo_b200 as R
+    import ryolo_b200._lib as L
+    gen = torch.Generator().manual_seed(5 + nc + R_)
+    pred = _synthetic_pred(gen, 5, R_, nc, clustered)
+    pred[1, :, 5:] = 0.0                                    # no candidates
+    pred[2, 40:, 5] = 0.0                                   # 40 candidates: less than one tile
+    pred[3, 700:, 5] = 0.0                                  # a little more than one band
+    pred = pred.cuda()
+    got = {}
+    try:
+        for band in (8, 0, 3):                              # the second banded call runs on a workspace full of stale masks
+            L.tune(nms_band=band)
+            if band == 3:
+                R.post_process_device(_synthetic_pred(gen, 5, R_, nc, not clustered).cuda(), conf, iou)
+            d, rows, n = R.post_process_device(pred.clone(), conf, iou)
+            got.setdefault(min(band, 1), []).append((d.cpu(), rows.cpu(), n.cpu()))
+    finally:
+        L.tune(nms_band=8)
+    ref = got[0][0]
+    assert int(ref[2][1]) == 0 and int(ref[2][2]) <= 40
+    for d, rows, n in got[1]:
+        assert torch.equal(n, ref[2])
+        for i in range(5):
+            k = int(n[i])
+            assert torch.equal(rows[i, :k], ref[1][i, :k]), f"image {i}"
+            assert torch.equal(d[i, :k], ref[0][i, :k])
