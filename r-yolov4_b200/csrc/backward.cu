@@ -456,17 +456,15 @@ __device__ __forceinline__ void reduce_row(const uint4& vd, const uint4& vr, con
   }
 }
 
-// MAXT only sets the register budget (the block is always 256 threads): 256 -> 128 registers, 304 -> 104, which lets
-// two blocks share an SM with one 192-thread x 56-register wgrad CTA.  The block-level combine needs 8*C bytes of shared
-// memory (C <= 768) or none (direct global atomics), so that it fits beside that CTA's 13 x 16 KB boxes.
-template <int ACT, int MAXT>
-__global__ void __launch_bounds__(MAXT, 2)
-bn_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
-                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
-                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
-                          float* __restrict__ sums) {
-  ry_pdl_wait();
-  extern __shared__ float red[];   // [2][C] when C <= 768
+// Pass 1 for one block: per-channel sums of dY and dY*xhat over the rows this block walks, added to sums[2C].
+// The block-level combine needs 8*C bytes of shared memory (C <= 768) or none (direct global atomics), so that it fits
+// beside a resident wgrad CTA's boxes.
+template <int ACT>
+__device__ __forceinline__ void bn_bwd_reduce_phase(const __nv_bfloat16* __restrict__ dout, long long dp,
+                                                    const __nv_bfloat16* __restrict__ raw, long long rp,
+                                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                    long long P, int C, float* __restrict__ sums, float* red) {
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -533,6 +531,19 @@ bn_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, 
   }
 }
 
+// MAXT only sets the register budget (the block is always 256 threads): 256 -> 128 registers, 304 -> 104, which lets
+// two blocks share an SM with one 192-thread x 56-register wgrad CTA.
+template <int ACT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+bn_act_bwd_reduce4_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ mean, const float* __restrict__ invstd, long long P, int C,
+                          float* __restrict__ sums) {
+  ry_pdl_wait();
+  extern __shared__ float red[];   // [2][C] when C <= 768
+  bn_bwd_reduce_phase<ACT>(dout, dp, raw, rp, scale, shift, mean, invstd, P, C, sums, red);
+}
+
 template <int ACT>
 __device__ __forceinline__ uint4 apply_row(const uint4& vd, const uint4& vr, const float (&sc)[8], const float (&sh)[8],
                                            const float (&nk1)[8], const float (&nk2)[8]) {
@@ -547,21 +558,24 @@ __device__ __forceinline__ uint4 apply_row(const uint4& vd, const uint4& vr, con
   return pack8(o);
 }
 
-template <int ACT, int MAXT>
-__global__ void __launch_bounds__(MAXT, 2)
-bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
-                         long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
-                         const float* __restrict__ mean, const float* __restrict__ invstd,
-                         const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
-                         long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  ry_pdl_wait();
+// Pass 2 for one block: d raw = scale * (dY - s1/P - xhat * s2/P), dY recomputed from d out and raw; block 0 also emits
+// d gamma += s2, d beta += s1.  `sums` is read through L2 (it may have been written by this very launch, see the fused
+// kernel below).
+template <int ACT>
+__device__ __forceinline__ void bn_bwd_apply_phase(const __nv_bfloat16* __restrict__ dout, long long dp,
+                                                   const __nv_bfloat16* __restrict__ raw, long long rp,
+                                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                                   const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                   const float* sums, long long P, int C,
+                                                   __nv_bfloat16* __restrict__ draw, long long op,
+                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
   if (blockIdx.x == 0) {
     for (int cc = threadIdx.x; cc < C; cc += blockDim.x) {
-      if (dbeta) dbeta[cc] += sums[cc];
-      if (dgamma) dgamma[cc] += sums[C + cc];
+      if (dbeta) dbeta[cc] += __ldcg(sums + cc);
+      if (dgamma) dgamma[cc] += __ldcg(sums + C + cc);
     }
   }
   if (r >= rows) return;
@@ -573,7 +587,7 @@ bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, c
   for (int j = 0; j < 8; j++) {
     sc[j] = scale[c + j]; sh[j] = shift[c + j];
     const float is = invstd[c + j], mu = mean[c + j];
-    const float m1 = sums[c + j] * invP, m2 = sums[C + c + j] * invP;
+    const float m1 = __ldcg(sums + c + j) * invP, m2 = __ldcg(sums + C + c + j) * invP;
     nk2[j] = -(sc[j] * is * m2);
     nk1[j] = -(sc[j] * (m1 - mu * is * m2));
   }
@@ -604,6 +618,64 @@ bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, c
     po += 2 * so;
   }
   if (n & 1) *reinterpret_cast<uint4*>(po) = apply_row<ACT>(ldv(pd), ldv(pr), sc, sh, nk1, nk2);
+}
+
+template <int ACT, int MAXT>
+__global__ void __launch_bounds__(MAXT, 2)
+bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                         long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                         const float* __restrict__ mean, const float* __restrict__ invstd,
+                         const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
+                         long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  ry_pdl_wait();
+  bn_bwd_apply_phase<ACT>(dout, dp, raw, rp, scale, shift, mean, invstd, sums, P, C, draw, op, dgamma, dbeta);
+}
+
+// (Experiment, knob bn_fuse, off by default: measured neutral to slightly slower on the step.)
+// Both passes in ONE launch for layers whose d out + raw fit in L2 (the 25x25 / 50x50 maps: 56 of the 110 layers of
+// yolov4, 2.4 ms per step as launch pairs of 14-27 us that move 20-80 MB each): the grid is at most the resident
+// capacity, so the blocks can meet at a grid-wide barrier between the passes; the second pass then re-reads its
+// operands from L2 instead of HBM and the second launch (fixed cost, ramp, tail) disappears.
+// Barrier: arrival counter + generation word; a block reads the generation BEFORE it arrives, so the last arriver's bump
+// cannot be missed.  Blocks that are not resident yet (an SM still held by a side-stream wgrad CTA, which never waits for
+// this kernel) arrive late, not never; a bounded spin turns an impossible wait into a trap instead of a hang.
+__device__ unsigned int g_bn_bar_count = 0;
+__device__ volatile unsigned int g_bn_bar_gen = 0;
+
+__device__ __forceinline__ void bn_grid_barrier() {
+  __threadfence();                               // this thread's atomics into sums[] are visible device-wide
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int gen = g_bn_bar_gen;
+    __threadfence();
+    if (atomicAdd(&g_bn_bar_count, 1u) == gridDim.x - 1) {
+      g_bn_bar_count = 0;
+      __threadfence();
+      g_bn_bar_gen = gen + 1;
+    } else {
+      long long spins = 0;
+      while (g_bn_bar_gen == gen) {
+        __nanosleep(100);
+        if (++spins > (1ll << 25)) __trap();     // ~3 s: co-residency assumption violated
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(256, 2)
+bn_act_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, const __nv_bfloat16* __restrict__ raw,
+                        long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
+                        const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ sums,
+                        long long P, int C, __nv_bfloat16* __restrict__ draw, long long op,
+                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  ry_pdl_wait();
+  extern __shared__ float red[];   // [2][C] when C <= 768
+  bn_bwd_reduce_phase<ACT>(dout, dp, raw, rp, scale, shift, mean, invstd, P, C, sums, red);
+  bn_grid_barrier();
+  bn_bwd_apply_phase<ACT>(dout, dp, raw, rp, scale, shift, mean, invstd, sums, P, C, draw, op, dgamma, dbeta);
 }
 
 // ds = dout * act'(x1*s1+b1 + x2*s2+b2)   (two-branch pre-activation, RepConv)
@@ -1029,8 +1101,13 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
 #undef RY_CARVE
     carved = true;
   }
+  // one launch for both passes when the operands fit in L2 and the grid is resident (knob bn_fuse, elements <= 24 M)
+  const bool fuse = variant == 3 && !lean && ryolo_knob(RYOLO_KNOB_BN_FUSE) != 0 && P * C <= 24ll * 1000 * 1000;
 #define RY_BWD(ACT)                                                                                                  \
-  if (variant == 3 && lean) {                                                                                        \
+  if (fuse) {                                                                                                        \
+    ry_launch(bn_act_bwd_fused_kernel<ACT>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, r, rp, \
+              scale, shift, mean, invstd, sums, P, C, o, op, dgamma, dbeta);                                         \
+  } else if (variant == 3 && lean) {                                                                                        \
     ry_launch(bn_act_bwd_reduce4_kernel<ACT, 304>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, \
               r, rp, scale, shift, mean, invstd, P, C, sums);                                                        \
     ry_launch(bn_act_bwd_apply3_kernel<ACT, 304>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, \

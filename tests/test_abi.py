@@ -60,7 +60,7 @@ def test_tuning_knobs_host_api():
     from ryolo_b200 import _lib as L
     lib = L.lib()
     names = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64",
-             "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band"]
+             "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse"]
     before = [lib.ryolo_knob(i) for i in range(len(names))]
     assert before[names.index("dbg")] == 0 and before[names.index("wg_dbg")] == 0, "timing experiments must be off"
     assert before[names.index("epi_tma")] == 2 and before[names.index("wg_trans")] == 0 and before[names.index("bn_bwd")] == 3

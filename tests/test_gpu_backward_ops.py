@@ -240,8 +240,8 @@ def test_pipelined_elementwise_kernels_many_rows_per_thread(act, C, coff, Cbuf):
     rawc, doutc, resc = raw.cuda(), dout.cuda(), resid.cuda()
     got = {}
     try:
-        for variant in (3, 0):
-            L.tune(bn_bwd=variant, ssa=1 if variant else 0)
+        for variant in (3, 0, 13):                          # 13 = variant 3 through the one-launch fused kernel (bn_fuse)
+            L.tune(bn_bwd=variant % 10, ssa=1 if variant else 0, bn_fuse=1 if variant == 13 else 0)
             # forward: act(raw * scale + shift) (+ residual) into a slice of a wider buffer
             for use_res in (False, True):
                 out = torch.full((N, H, W, Cbuf), 7.0, dtype=torch.bfloat16, device="cuda")
@@ -258,7 +258,7 @@ def test_pipelined_elementwise_kernels_many_rows_per_thread(act, C, coff, Cbuf):
             assert float((draw[..., coff + C:].float() - 7).abs().max() if coff + C < Cbuf else 0.0) == 0.0
             got[("bwd", variant)] = (draw[..., coff:coff + C].float().cpu(), dg.cpu(), db.cpu())
     finally:
-        L.tune(bn_bwd=3, ssa=1)
+        L.tune(bn_bwd=3, ssa=1, bn_fuse=0)
     zr = z.detach().permute(0, 2, 3, 1)
     for use_res in (False, True):
         ref = zr + (resid[..., coff:coff + C].float() if use_res else 0.0)
@@ -269,6 +269,8 @@ def test_pipelined_elementwise_kernels_many_rows_per_thread(act, C, coff, Cbuf):
     ref = xr.grad.permute(0, 2, 3, 1)
     d3, g3, b3 = got[("bwd", 3)]
     d0, g0, b0 = got[("bwd", 0)]
+    df, gf, bf = got[("bwd", 13)]                           # same kernels' bodies, one launch: same rounding
+    assert float((df - d3).norm() / ref.norm()) < 2e-3 and (gf - g3).abs().max() < 2e-3 * g3.abs().max()
     # LeakyReLU's kink: the kernels form z = raw * scale + shift, torch (x - mean) * invstd * gamma + beta; where z is
     # within rounding of 0 the derivative flips between 1 and 0.1, so isolated elements differ by 0.9 |d out|
     for other in (ref, d0):
