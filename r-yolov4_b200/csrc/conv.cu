@@ -803,7 +803,11 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   p->ksize = d->ksize; p->stride = d->stride; p->pad = (d->ksize - 1) / 2;
   p->Ho = (d->H + 2 * p->pad - d->ksize) / d->stride + 1;
   p->Wo = (d->W + 2 * p->pad - d->ksize) / d->stride + 1;
-  p->kbk = (d->Cin == 32 && ryolo_knob(RYOLO_KNOB_SW64)) ? 32 : kBK;
+  {   // knob sw64: 1 = 32-wide K blocks for Cin == 32 only; 2 = also for every layer with Cout <= 128, 3 = for every layer
+      // (experiment: half-size stages, twice the ring depth)
+    const int sw = ryolo_knob(RYOLO_KNOB_SW64);
+    p->kbk = ((d->Cin == 32 && sw) || (sw == 2 && d->Cout <= 128 && d->Cin % 32 == 0) || (sw == 3 && d->Cin % 32 == 0)) ? 32 : kBK;
+  }
   p->kb_per_tap = (d->Cin + p->kbk - 1) / p->kbk;
   p->ntaps = d->ksize * d->ksize; p->Ktap = d->Cin;
   for (int t = 0; t < p->ntaps; t++) {
@@ -1021,7 +1025,10 @@ int ryolo_conv2d_dgrad(const void* dy, long long dy_cpitch, int N, int H, int W,
       ConvKernelParams p{};
       p.N = N; p.Ho = Hl; p.Wo = Wl; p.Cout = Cin; p.Cin = Cout; p.Ktap = Cout;
       p.ksize = ksize; p.stride = 1; p.pad = pad;
-      p.kbk = (Cout == 32 && ryolo_knob(RYOLO_KNOB_SW64)) ? 32 : kBK;
+      {
+        const int sw = ryolo_knob(RYOLO_KNOB_SW64);
+        p.kbk = ((Cout == 32 && sw) || (sw == 2 && Cin <= 128 && Cout % 32 == 0) || (sw == 3 && Cout % 32 == 0)) ? 32 : kBK;
+      }
       p.kb_per_tap = (Cout + p.kbk - 1) / p.kbk;
       p.ntaps = 0;
       for (int kh = 0; kh < ksize; kh++) {

@@ -25,7 +25,9 @@ int ryolo_abi_version(void) { return 1; }
 //   wg_tapgrp wgrad: 1 = one MMA covers as many taps as fit N = 256, 0 = one tap per MMA
 //   wg_trans  wgrad: 1 = layers with Cin <= 128 transpose their TMA boxes in smem and run K-major MMAs (correct, but
 //             measured slower than the MN-major kernel: its raw ring is only 4 boxes deep), 0 (default) = MN-major
-//   sw64      conv: 1 = Cin == 32 operands use 32-element (64-byte, SWIZZLE_64B) K blocks instead of overhanging 64-element boxes
+//   sw64      conv: 1 = Cin == 32 operands use 32-element (64-byte, SWIZZLE_64B) K blocks instead of overhanging 64-element boxes;
+//             2 / 3 = also every layer with Cout <= 128 / every layer (half-size stages, twice the ring depth: measured
+//             +9 % / +22 % on the conv stack: the per-stage hand-shake, not the ring depth, is what costs)
 //   nacc      conv: 1 = as many TMEM accumulators in rotation as fit (up to 8), 0 = two
 //   pdl       1 = the conv / wgrad / BatchNorm-backward / scale-shift-act kernels use programmatic dependent launch
 //   bn_bwd    BatchNorm backward: 0 = original passes, 1 = low-register reduce (stores dY), 2 = reduce without the dY

@@ -408,10 +408,17 @@ __global__ void __launch_bounds__(128)
 nms_band_gather_kernel(const BandState* __restrict__ state, int max_det, const int32_t* __restrict__ keep_pos,
                        int64_t keep_stride, const float* __restrict__ dets_sorted,
                        const int32_t* __restrict__ rows_sorted, int64_t sorted_stride, float* __restrict__ dets_out,
-                       int64_t* __restrict__ rows_out, int32_t* __restrict__ n_keep) {
+                       int64_t* __restrict__ rows_out, int32_t* __restrict__ n_keep,
+                       // plain nms API (one box set): order[] -> int64 indices into the caller's boxes
+                       const int32_t* __restrict__ order, int64_t* __restrict__ keep_idx64) {
   const int img = blockIdx.x;
   const int nk = min(state[img].nk, max_det);
   keep_pos += (int64_t)img * keep_stride;
+  if (keep_idx64) {
+    if (threadIdx.x == 0) n_keep[img] = nk;
+    for (int j = threadIdx.x; j < nk; j += blockDim.x) keep_idx64[j] = (int64_t)order[keep_pos[j]];
+    return;
+  }
   dets_sorted += (int64_t)img * sorted_stride * 7;
   rows_sorted += (int64_t)img * sorted_stride;
   dets_out += (int64_t)img * max_det * 7;
@@ -782,6 +789,7 @@ size_t ryolo_nms_rotated_workspace(int64_t n) {
   s += ry_align_up((size_t)n * 4, 256) * 2;                          // order, keep_pos
   s += ry_align_up((size_t)pow2_ge(n > 0 ? n : 1) * 8, 256);         // keys (large-n sort)
   s += 256;                                                          // count
+  s += ry_align_up((size_t)words * 16 + sizeof(BandState), 256);     // banded scan: rem | kept | state
   return s;
 }
 
@@ -800,7 +808,8 @@ int ryolo_nms_rotated(const float* boxes5, const float* scores, int64_t n, float
   int32_t* order = (int32_t*)w; w += ry_align_up((size_t)n * 4, 256);
   int32_t* keep_pos = (int32_t*)w; w += ry_align_up((size_t)n * 4, 256);
   unsigned long long* keys = (unsigned long long*)w; w += ry_align_up((size_t)pow2_ge(n) * 8, 256);
-  int32_t* count = (int32_t*)w;
+  int32_t* count = (int32_t*)w; w += 256;
+  unsigned long long* rem = (unsigned long long*)w;
 
   if (n <= kSortCap) {
     size_t sm = (size_t)pow2_ge(n) * 8;
@@ -815,6 +824,23 @@ int ryolo_nms_rotated(const float* boxes5, const float* scores, int64_t n, float
     keys_to_order_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(keys, n, order, count);
   }
   prep_boxes_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(boxes5, order, n, prep);
+  int kBand = ryolo_knob(RYOLO_KNOB_NMS_BAND);
+  if (kBand > kBandMax) kBand = kBandMax;
+  if (kBand > 0) {                                  // banded greedy NMS, as in ryolo_post_process (no max_det cap here)
+    unsigned long long* keptb = rem + words;
+    BandState* state = (BandState*)(keptb + words);
+    cudaMemsetAsync(rem, 0, (size_t)words * 16 + sizeof(BandState), st);
+    for (int c0 = 0; c0 < words; c0 += kBand) {
+      if (c0 > 0)
+        nms_band_suppress_kernel<<<dim3(kBand, 1), 256, 0, st>>>(prep, count, 0, words, iou_thr, c0, rem, state, keep_pos, 0);
+      nms_mask_kernel<<<dim3(kBand, kBand, 1), 256, 0, st>>>(prep, count, 0, words, iou_thr, mask, 0, c0, c0, rem, state);
+      nms_band_scan_kernel<<<1, 32, 0, st>>>(mask, 0, words, count, (int)n, c0, kBand, rem, keptb, state, keep_pos, 0);
+    }
+    nms_band_gather_kernel<<<1, 128, 0, st>>>(state, (int)n, keep_pos, 0, nullptr, nullptr, 0, nullptr, nullptr, n_keep,
+                                             order, keep);
+    RY_CHECK_LAUNCH();
+    return RYOLO_OK;
+  }
   dim3 grid(words, words, 1);
   nms_mask_kernel<<<grid, 256, 0, st>>>(prep, count, 0, words, iou_thr, mask, 0, 0, 0, nullptr, nullptr);
   size_t scan_smem = (size_t)words * 8;
@@ -915,7 +941,7 @@ int ryolo_post_process(float* pred, int64_t B, int64_t R, int nc, float conf_thr
                                                     keep_pos, max_nms);
   }
   nms_band_gather_kernel<<<(unsigned)B, 128, 0, st>>>(state, max_det, keep_pos, max_nms, dets_sorted, rows_sorted, max_nms,
-                                                     dets_out, rows_out, n_out);
+                                                     dets_out, rows_out, n_out, nullptr, nullptr);
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

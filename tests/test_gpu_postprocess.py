@@ -216,3 +216,26 @@ def test_banded_nms_equals_full_mask_nms(nc, conf, iou, clustered, R_):
             k = int(n[i])
             assert torch.equal(rows[i, :k], ref[1][i, :k]), f"image {i}"
             assert torch.equal(d[i, :k], ref[0][i, :k])
+
+
+@pytest.mark.parametrize("n,thr", [(9000, 0.3), (700, 0.65), (64, 0.1), (1, 0.5)])
+def test_banded_plain_nms_equals_full_mask(n, thr):
+    """The detectron2 drop-in (one box set, no max_det) through the banded path == the full-mask path, index for index."""
+    import ryolo_b200 as R
+    import ryolo_b200._lib as L
+    gen = torch.Generator().manual_seed(n)
+    centres = torch.rand(60, 2, generator=gen) * 600
+    xy = centres[torch.randint(0, 60, (n,), generator=gen)] + torch.randn(n, 2, generator=gen) * 8
+    w = torch.rand(n, 1, generator=gen) * 80 + 4
+    boxes = torch.cat((xy, w, w * (1 + 2 * torch.rand(n, 1, generator=gen)), (torch.rand(n, 1, generator=gen) - 0.5) * 179.9), 1)
+    scores = torch.rand(n, generator=gen)
+    scores[::7] = scores[0]                                   # ties: stable order matters
+    out = {}
+    try:
+        for band in (8, 0, 5):
+            L.tune(nms_band=band)
+            out[band] = R.nms_rotated(boxes.cuda(), scores.cuda(), thr).cpu()
+    finally:
+        L.tune(nms_band=8)
+    assert torch.equal(out[8], out[0]) and torch.equal(out[5], out[0])
+    assert 0 < out[0].numel() <= n

@@ -52,6 +52,8 @@ VARIANTS = [
     ("noaload_nostats", dict(dbg=10)),
     ("noaload_nomma", dict(dbg=12)),
     ("halo", dict(halo=1)),
+    ("k32_n128", dict(sw64=2)),
+    ("k32_all", dict(sw64=3)),
 ]
 res = {}
 for name, kn in VARIANTS:
