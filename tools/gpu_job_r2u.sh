@@ -21,12 +21,12 @@ timeout 420 ncu --set full --clock-control none --import-source on -k regex:conv
 echo "== ncu full: wgrad (bs=32) mid + last"; date
 timeout 420 ncu --set full --clock-control none --import-source on -k regex:conv_wgrad_kernel -s 300 -c 6 -o $O/r2u_wgrad python tools/train_layers.py 32 > $O/r2u_ncu_wgrad.log 2>&1
 for r in r2u_conv r2u_wgrad; do
-  if [ -f $O/$r.ncu-rep ]; then ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null; fi
+  if [ -f $O/$r.ncu-rep ]; then ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null; rm -f $O/$r.ncu-rep; fi
 done
 ls -la $O | grep r2f; date
 echo "== non-conv: nms bench, ncu launch list, ncu full"; date
 timeout 300 python tools/nms_bench.py 5 > $O/r2u_nms_bench.log 2>&1; grep -A2 '"nc' $O/r2u_nms_bench.log | grep -E "nc|ms" | paste - - | cut -c1-120
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file $O/r2u_nonconv_launches.csv python tools/nonconv_profile.py 2 > $O/r2u_ncu_list2.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:kfloss_pairs|csl_pos|kf_pos|obj_dense|pp_score|pp_select|nms_mask|nms_band|nms_scan|decode_|pairwise_iou' -o $O/r2u_nonconv python tools/nonconv_profile.py 1 > $O/r2u_ncu_full2.log 2>&1
-if [ -f $O/r2u_nonconv.ncu-rep ]; then ncu -i $O/r2u_nonconv.ncu-rep --page raw --csv > $O/r2u_nonconv_raw.csv 2>/dev/null; fi
+timeout 900 ncu --set full --clock-control none --import-source on -k 'regex:kfloss_pairs|csl_pos|kfiou_pos|obj_dense|pp_score|pp_select|decode_|pairwise_iou' -o $O/r2u_nonconv python tools/nonconv_profile.py 1 > $O/r2u_ncu_full2.log 2>&1
+if [ -f $O/r2u_nonconv.ncu-rep ]; then ncu -i $O/r2u_nonconv.ncu-rep --page raw --csv > $O/r2u_nonconv_raw.csv 2>/dev/null; rm -f $O/r2u_nonconv.ncu-rep; fi
 ls -la $O | grep r2u; date
