@@ -14,69 +14,99 @@ constexpr float kPiF = 3.14159274101257324f;  // fl32(np.pi)
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return __fdiv_rn(1.f, __fadd_rn(1.f, expf(-x))); }
 
-// ---- CSL: ch = nc + 185 (x,y,w,h,obj, nc classes, 180 angle bins). One warp per cell.
+// ---- CSL: ch = nc + 185 (x,y,w,h,obj, nc classes, 180 angle bins). One warp per cell, grid-stride: the 180 logits of
+// the NEXT cell are requested before the current one is reduced (a warp that handles one cell and exits leaves the
+// kernel latency-bound: ncu showed 1.2 TB/s with every warp waiting on its own six loads).
 __global__ void __launch_bounds__(256)
 decode_csl_kernel(const float* __restrict__ lvl, int64_t cells_total, int na, int gs, int nc, float stride,
                   float aw0, float ah0, float aw1, float ah1, float aw2, float ah2,
                   float* __restrict__ out, int64_t row0, int64_t R) {
   const int lane = threadIdx.x & 31;
-  const int64_t cell = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  int64_t cell = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   if (cell >= cells_total) return;
   const int ch = nc + 185;
-  const float* p = lvl + cell * ch;
   const int64_t per_img = (int64_t)na * gs * gs;
-  const int64_t b = cell / per_img;
-  const int64_t r = cell - b * per_img;
-  const int a = (int)(r / ((int64_t)gs * gs));
-  const int rem = (int)(r - (int64_t)a * gs * gs);
-  const int gy = rem / gs, gx = rem - gy * gs;
-
-  // angle bins: argmax over the fp32 SIGMOID values, first maximum wins (yololayer.py:39,48).  The sigmoid is monotone,
-  // so only logits near the largest one can attain the maximum: the 180 exponentials + divisions per cell that made this
-  // kernel SFU/ALU-bound (ncu: 85 % SM throughput at 1.2 TB/s) shrink to the few candidates that might TIE with it after
-  // rounding.  Ties happen when sigma'(m) (m - x) drops below an ulp of sigma(m): within 2^-23 / (1 - sigma(m)) of the
-  // maximum logit m, i.e. < 1.1 for m <= 16, and for every x >= 16.64 once the sigmoid saturates at 1.0f.  A logit is a
-  // candidate when x >= min(m, 16) - 2; everything below is smaller than sigma(m) by more than 3 ulps.
-  float xv[6];
-  float m = -INFINITY;
+  float xn[6], hn = 0.f;                              // next cell: angle logits of this lane, head value (lanes 0..4+nc)
+  {
+    const float* p = lvl + cell * ch;
 #pragma unroll
-  for (int q = 0; q < 6; q++) {
-    const int j = lane + 32 * q;
-    xv[q] = j < 180 ? p[5 + nc + j] : -INFINITY;
-    m = fmaxf(m, xv[q]);
+    for (int q = 0; q < 6; q++) { const int j = lane + 32 * q; xn[q] = j < 180 ? p[5 + nc + j] : -INFINITY; }
+    if (lane < 5 + nc) hn = p[lane];
   }
+  for (; cell < cells_total; cell += nwarps) {
+    float xv[6];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  const float cut = fminf(m, 16.f) - 2.f;
-  float best = -1.f;
-  int bi = 0x7fffffff;
+    for (int q = 0; q < 6; q++) xv[q] = xn[q];
+    const float hv = hn;
+    const float* p = lvl + cell * ch;
+    if (cell + nwarps < cells_total) {
+      const float* pn = lvl + (cell + nwarps) * ch;
 #pragma unroll
-  for (int q = 0; q < 6; q++) {
-    if (xv[q] >= cut) {                              // NaN logits never qualify, exactly like `s > best` below
-      const float s = sigmoidf_acc(xv[q]);
-      if (s > best) { best = s; bi = lane + 32 * q; }
+      for (int q = 0; q < 6; q++) { const int j = lane + 32 * q; xn[q] = j < 180 ? pn[5 + nc + j] : -INFINITY; }
+      if (lane < 5 + nc) hn = pn[lane];
     }
-  }
+    int64_t b, r;
+    int a, rem;
+    if (cells_total < (1ll << 31)) {                  // 32-bit index arithmetic (64-bit divisions cost ~100 instructions)
+      const unsigned c32 = (unsigned)cell, pi = (unsigned)per_img, g2 = (unsigned)(gs * gs);
+      const unsigned b32 = c32 / pi, r32 = c32 - b32 * pi, a32 = r32 / g2;
+      b = b32; r = r32; a = (int)a32; rem = (int)(r32 - a32 * g2);
+    } else {
+      b = cell / per_img;
+      r = cell - b * per_img;
+      a = (int)(r / ((int64_t)gs * gs));
+      rem = (int)(r - (int64_t)a * gs * gs);
+    }
+    const int gy = rem / gs, gx = rem - gy * gs;
+
+    // angle bins: argmax over the fp32 SIGMOID values, first maximum wins (yololayer.py:39,48).  The sigmoid is monotone,
+    // so only logits that can TIE with the largest one (m) after rounding need their sigmoid evaluated: 180 exponentials
+    // + IEEE divisions per cell shrink to (almost always) one.  Two logits can compare equal — or, with expf's 2-ulp
+    // error, reversed — only if their true sigmoids are within ~8 ulps: m - x < 8 ulp(s) / s'(m) <= 2^-19 (1 + e^m).
+    // Beyond m = 14 the window opens quickly and from 16.64 on every logit maps to 1.0f: the cut is then a flat 11.7
+    // (s(11.7) = 1 - 8e-6 is 100 ulps below s(14)).  Flat distributions (random init: all 180 logits within 0.1 of each
+    // other) are why the window must be this tight to pay off.
+    float m = -INFINITY;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    float ob = __shfl_xor_sync(0xffffffffu, best, o);
-    int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-    if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
-  }
-  float* o = out + (b * R + row0 + r) * (nc + 6);
-  if (lane == 0) {
+    for (int q = 0; q < 6; q++) m = fmaxf(m, xv[q]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float mc = fminf(m, 14.f);
+    const float cut = mc - 1.9073486e-6f * (1.f + __expf(mc));
+    float best = -1.f;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int q = 0; q < 6; q++) {
+      if (xv[q] >= cut) {                              // NaN logits never qualify, exactly like `s > best` below
+        const float s = sigmoidf_acc(xv[q]);
+        if (s > best) { best = s; bi = lane + 32 * q; }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+    }
+    // lanes 0..3: box, lane 4: objectness, lanes 5..: classes (the general nc > 27 tail reads its logits directly)
+    const float sg = sigmoidf_acc(hv);
+    float* o = out + (b * R + row0 + r) * (nc + 6);
     const float aw = a == 0 ? aw0 : (a == 1 ? aw1 : aw2);
     const float ah = a == 0 ? ah0 : (a == 1 ? ah1 : ah2);
-    float sx = sigmoidf_acc(p[0]), sy = sigmoidf_acc(p[1]), sw = sigmoidf_acc(p[2]), sh = sigmoidf_acc(p[3]);
-    o[0] = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sx, 2.f), 0.5f), (float)gx), stride);
-    o[1] = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sy, 2.f), 0.5f), (float)gy), stride);
-    float w2 = __fmul_rn(sw, 2.f), h2 = __fmul_rn(sh, 2.f);
-    o[2] = __fmul_rn(__fmul_rn(__fmul_rn(w2, w2), aw), stride);
-    o[3] = __fmul_rn(__fmul_rn(__fmul_rn(h2, h2), ah), stride);
-    o[4] = __fmul_rn(__fdiv_rn((float)(bi - 90), 180.f), kPiF);
-    o[5] = sigmoidf_acc(p[4]);
+    if (lane < 2) {
+      o[lane] = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(sg, 2.f), 0.5f), (float)(lane ? gy : gx)), stride);
+    } else if (lane < 4) {
+      const float w2 = __fmul_rn(sg, 2.f);
+      o[lane] = __fmul_rn(__fmul_rn(__fmul_rn(w2, w2), lane == 2 ? aw : ah), stride);
+    } else if (lane == 4) {
+      o[4] = __fmul_rn(__fdiv_rn((float)(bi - 90), 180.f), kPiF);
+      o[5] = sg;
+    } else if (lane < 5 + nc) {
+      o[1 + lane] = sg;
+    }
+    for (int c = 27 + lane; c < nc; c += 32) o[6 + c] = sigmoidf_acc(p[5 + c]);
   }
-  for (int c = lane; c < nc; c += 32) o[6 + c] = sigmoidf_acc(p[5 + c]);
 }
 
 // ---- KFIoU: ch = nc + 6 (x,y,w,h,angle,obj, nc classes). One thread per cell.
@@ -135,7 +165,10 @@ int ryolo_decode_csl(const float* level, int64_t B, int gs, int nc, float stride
   if (cells == 0) return RYOLO_OK;
   RY_CHECK_ARG(row0 + 3ll * gs * gs <= R, "decode_csl: rows exceed output");
   const int64_t threads = cells * 32;
-  decode_csl_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+  int64_t blocks = (threads + 255) / 256;
+  const int64_t cap = (int64_t)ry_sm_count() * 8 * 4;             // 8 resident blocks per SM, ~4 cells per warp and more
+  if (blocks > cap) blocks = cap;
+  decode_csl_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
       level, cells, 3, gs, nc, stride, anchors_wh[0], anchors_wh[1], anchors_wh[2], anchors_wh[3], anchors_wh[4],
       anchors_wh[5], out, row0, R);
   RY_CHECK_LAUNCH();
