@@ -212,7 +212,10 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
  * with dout*act'(.) (knob bn_bwd < 2): treat it as dead afterwards.                                                                        */
 int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
-                     float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream);
+                     float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* dres, long long resp,
+                     void* stream);
+/* dres (nullable, bf16 view with channel pitch resp): receives a COPY of d out — the gradient of the residual operand
+ * of out = residual + act(BN(raw)) (Bottleneck, model/utils.py:35-46) when nothing has been accumulated into it yet. */
 /* ds = dout * act'(x1*s1+b1 + x2*s2+b2): backward through RepConv's SiLU of two summed BN branches          */
 int ryolo_act_bwd2(const void* dout, long long dp, const void* x1, long long p1, const float* s1, const float* b1,
                    const void* x2, long long p2, const float* s2, const float* b2, int act, void* ds, long long op,

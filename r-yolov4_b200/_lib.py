@@ -75,7 +75,7 @@ SIGNATURES.update({
     "ryolo_conv2d_dgrad": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _ll, _i32, _vp]),
     "ryolo_conv2d_wgrad": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _vp, _ll, _i32, _i32, _i32, _i32, _vp, _vp]),
     "ryolo_unpack_wgrad_multi": (_i32, [_vp, _i32, _ll, _vp]),
-    "ryolo_bn_act_bwd": (_i32, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _i32, _ll, _i32, _vp, _vp, _ll, _vp, _vp, _vp]),
+    "ryolo_bn_act_bwd": (_i32, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _vp, _i32, _ll, _i32, _vp, _vp, _ll, _vp, _vp, _vp, _ll, _vp]),
     "ryolo_act_bwd2": (_i32, [_vp, _ll, _vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i32, _vp, _ll, _ll, _i32, _vp]),
     "ryolo_add_into": (_i32, [_vp, _ll, _vp, _ll, _ll, _i32, _i32, _vp]),
     "ryolo_maxpool_bwd": (_i32, [_vp, _ll, _vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _i32, _vp,

@@ -568,7 +568,8 @@ __device__ __forceinline__ void bn_bwd_apply_phase(const __nv_bfloat16* __restri
                                                    const float* __restrict__ mean, const float* __restrict__ invstd,
                                                    const float* sums, long long P, int C,
                                                    __nv_bfloat16* __restrict__ draw, long long op,
-                                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                   __nv_bfloat16* __restrict__ dres = nullptr, long long rsp = 0) {
   const int groups = C >> 3;
   const int rows = blockDim.x / groups;
   const int g = threadIdx.x % groups, r = threadIdx.x / groups;
@@ -598,6 +599,10 @@ __device__ __forceinline__ void bn_bwd_apply_phase(const __nv_bfloat16* __restri
   const __nv_bfloat16* pd = dout + c + (long long)pix0 * dp;
   const __nv_bfloat16* pr = raw + c + (long long)pix0 * rp;
   __nv_bfloat16* po = draw + c + (long long)pix0 * op;
+  // optional copy of d out into the gradient of a residual operand (out = residual + act(bn(raw)): the identity path
+  // gets d out as is); the words are already in registers, so this replaces a separate read + write pass
+  const long long sq = (long long)stride * rsp;
+  __nv_bfloat16* pq = dres ? dres + c + (long long)pix0 * rsp : nullptr;
   const int pairs = n >> 1;
   if (pairs) {
     uint4 d0 = ldv(pd), d1 = ldv(pd + sd), r0 = ldv(pr), r1 = ldv(pr + sr);
@@ -606,18 +611,24 @@ __device__ __forceinline__ void bn_bwd_apply_phase(const __nv_bfloat16* __restri
       pd += 2 * sd;
       pr += 2 * sr;
       const uint4 e0 = ldv(pd), e1 = ldv(pd + sd), q0 = ldv(pr), q1 = ldv(pr + sr);
+      if (pq) { *reinterpret_cast<uint4*>(pq) = d0; *reinterpret_cast<uint4*>(pq + sq) = d1; pq += 2 * sq; }
       *reinterpret_cast<uint4*>(po) = apply_row<ACT>(d0, r0, sc, sh, nk1, nk2);
       *reinterpret_cast<uint4*>(po + so) = apply_row<ACT>(d1, r1, sc, sh, nk1, nk2);
       po += 2 * so;
       d0 = e0; d1 = e1; r0 = q0; r1 = q1;
     }
+    if (pq) { *reinterpret_cast<uint4*>(pq) = d0; *reinterpret_cast<uint4*>(pq + sq) = d1; pq += 2 * sq; }
     *reinterpret_cast<uint4*>(po) = apply_row<ACT>(d0, r0, sc, sh, nk1, nk2);
     *reinterpret_cast<uint4*>(po + so) = apply_row<ACT>(d1, r1, sc, sh, nk1, nk2);
     pd += 2 * sd;
     pr += 2 * sr;
     po += 2 * so;
   }
-  if (n & 1) *reinterpret_cast<uint4*>(po) = apply_row<ACT>(ldv(pd), ldv(pr), sc, sh, nk1, nk2);
+  if (n & 1) {
+    const uint4 d0 = ldv(pd);
+    if (pq) *reinterpret_cast<uint4*>(pq) = d0;
+    *reinterpret_cast<uint4*>(po) = apply_row<ACT>(d0, ldv(pr), sc, sh, nk1, nk2);
+  }
 }
 
 template <int ACT, int MAXT>
@@ -626,9 +637,10 @@ bn_act_bwd_apply3_kernel(const __nv_bfloat16* __restrict__ dout, long long dp, c
                          long long rp, const float* __restrict__ scale, const float* __restrict__ shift,
                          const float* __restrict__ mean, const float* __restrict__ invstd,
                          const float* __restrict__ sums, long long P, int C, __nv_bfloat16* __restrict__ draw,
-                         long long op, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                         long long op, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         __nv_bfloat16* __restrict__ dres, long long rsp) {
   ry_pdl_wait();
-  bn_bwd_apply_phase<ACT>(dout, dp, raw, rp, scale, shift, mean, invstd, sums, P, C, draw, op, dgamma, dbeta);
+  bn_bwd_apply_phase<ACT>(dout, dp, raw, rp, scale, shift, mean, invstd, sums, P, C, draw, op, dgamma, dbeta, dres, rsp);
 }
 
 // (Experiment, knob bn_fuse, off by default: measured neutral to slightly slower on the step.)
@@ -1067,9 +1079,11 @@ extern "C" {
 //   sums: fp32[2C] scratch, zeroed;  draw: bf16 view;  dgamma / dbeta: fp32[C], accumulated into (nullable)
 int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, const float* scale,
                      const float* shift, const float* mean, const float* invstd, int act, long long P, int C,
-                     float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* stream) {
+                     float* sums, void* draw, long long op, float* dgamma, float* dbeta, void* dres, long long resp,
+                     void* stream) {
   RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && dp % 8 == 0 && rp % 8 == 0 && op % 8 == 0,
                "bn_act_bwd: channels must be a multiple of 8 in [8, 2048]");
+  RY_CHECK_ARG(!dres || (resp % 8 == 0 && (((uintptr_t)dres) & 15) == 0), "bn_act_bwd: bad residual-gradient view");
   RY_CHECK_ARG(P < (1ll << 31) - (1 << 20), "bn_act_bwd: more than 2^31 pixels");
   if (P == 0) return RYOLO_OK;
   cudaStream_t st = (cudaStream_t)stream;
@@ -1103,6 +1117,12 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
   }
   // one launch for both passes when the operands fit in L2 and the grid is resident (knob bn_fuse, elements <= 24 M)
   const bool fuse = variant == 3 && !lean && ryolo_knob(RYOLO_KNOB_BN_FUSE) != 0 && P * C <= 24ll * 1000 * 1000;
+  // the copy of d out into a residual operand's gradient rides in variant 3's apply pass; the other variants (A/B
+  // switches) do it as the separate pass it used to be, BEFORE d out can be overwritten
+  __nv_bfloat16* q = (variant == 3 && !fuse) ? (__nv_bfloat16*)dres : nullptr;
+  if (dres && !q)
+    add_into_kernel<<<grid_for(P * (C / 8), 256), 256, 0, st>>>((__nv_bfloat16*)dres, resp, (const __nv_bfloat16*)dout, dp, P,
+                                                                C, 0);
 #define RY_BWD(ACT)                                                                                                  \
   if (fuse) {                                                                                                        \
     ry_launch(bn_act_bwd_fused_kernel<ACT>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, r, rp, \
@@ -1111,12 +1131,12 @@ int ryolo_bn_act_bwd(void* dout, long long dp, const void* raw, long long rp, co
     ry_launch(bn_act_bwd_reduce4_kernel<ACT, 304>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, \
               r, rp, scale, shift, mean, invstd, P, C, sums);                                                        \
     ry_launch(bn_act_bwd_apply3_kernel<ACT, 304>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, \
-              rp, scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                       \
+              rp, scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta, q, resp);              \
   } else if (variant == 3) {                                                                                         \
     ry_launch(bn_act_bwd_reduce4_kernel<ACT, 256>, dim3(blocks3), dim3(threads), smem3, st, (const __nv_bfloat16*)d, dp, \
               r, rp, scale, shift, mean, invstd, P, C, sums);                                                        \
     ry_launch(bn_act_bwd_apply3_kernel<ACT, 256>, dim3(blocks3), dim3(threads), 0, st, (const __nv_bfloat16*)d, dp, r, \
-              rp, scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta);                       \
+              rp, scale, shift, mean, invstd, (const float*)sums, P, C, o, op, dgamma, dbeta, q, resp);              \
   } else if (variant == 2) {                                                                                                \
     ry_launch(bn_act_bwd_reduce3_kernel<ACT>, dim3(blocks), dim3(threads), smem, st, (const __nv_bfloat16*)d, dp, r, rp, \
               scale, shift, mean, invstd, P, C, sums);                                                               \

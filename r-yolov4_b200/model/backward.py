@@ -258,12 +258,18 @@ def _run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
             if not G.is_init(out):
                 return                                     # output never used downstream (cannot happen in these nets)
             dout = G.view(out)
+            dres = None
             if residual is not None:                       # out = residual + act(bn(raw)): identity path
-                _accumulate(G, residual, dout)
+                gv, acc = G.writable(residual)
+                if acc:                                    # something already flowed into it: read-add-write pass
+                    ops.add_into(gv, dout, True)
+                else:                                      # first contribution: a copy, made by the BN-backward pass
+                    dres = gv
+                G.mark(residual)
             bn = mod.conv[1]
             C = mod.c2
             ops.bn_act_bwd(dout, raw, scale, shift, mean, invstd, mod.act, sums[soff:soff + 2 * C], raw,
-                           pg(bn.weight), pg(bn.bias))     # d raw overwrites raw in place
+                           pg(bn.weight), pg(bn.bias), dres=dres)     # d raw overwrites raw in place
             state["soff"] = soff + 2 * C
             k, st = (1, 1) if mod.stem else (mod.k, mod.s)
             sink.wgrad(x, raw, C, k, st, mod.conv[0].weight, mod.stem)

@@ -239,12 +239,14 @@ def wgrad_to_oihw(dwk, Cout, Cin, k, stem=False):
     return dwk.view(Cout, k * k, Cin).permute(0, 2, 1).reshape(Cout, Cin, k, k).contiguous()
 
 
-def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, dbeta):
+def bn_act_bwd(dout, raw, scale, shift, mean, invstd, act, sums, draw, dgamma, dbeta, dres=None):
+    """dres: optional Act that receives a copy of dout (gradient of a residual operand, first contribution)."""
     if PROFILE is not None:
         _prof_begin()
     L.check(L.lib().ryolo_bn_act_bwd(_vp(dout.ptr), dout.pitch, _vp(raw.ptr), raw.pitch, _tp(scale), _tp(shift),
                                      _tp(mean), _tp(invstd), ACT[act], raw.P, raw.C, _tp(sums), _vp(draw.ptr),
-                                     draw.pitch, _tp(dgamma), _tp(dbeta), L.stream()))
+                                     draw.pitch, _tp(dgamma), _tp(dbeta), _vp(dres.ptr if dres is not None else 0),
+                                     dres.pitch if dres is not None else 0, L.stream()))
     L.count(2)
     if PROFILE is not None:
         _prof_end(('bn_bwd', raw.P, raw.C, 0))
