@@ -118,6 +118,7 @@ WGRAD_SIDE_STREAM = os.environ.get("RYOLO_WGRAD_SIDE", "1") != "0"   # False: we
 # 96-register blocks + 16 KB next to the 56-register wgrad CTA with 13 x 16 KB boxes): tensor-core work hidden behind
 # memory-bound work instead of time-sliced with it.
 BACKWARD_HIGH_PRIORITY = os.environ.get("RYOLO_BWD_PRIO", "0") != "0"
+RESIDUAL_COPY_IN_BN_BWD = os.environ.get("RYOLO_RES_FUSE", "1") != "0"     # A/B switch, see run_backward / "conv" entries
 
 
 def _side_stream(dev):
@@ -261,8 +262,8 @@ def _run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
             dres = None
             if residual is not None:                       # out = residual + act(bn(raw)): identity path
                 gv, acc = G.writable(residual)
-                if acc:                                    # something already flowed into it: read-add-write pass
-                    ops.add_into(gv, dout, True)
+                if acc or not RESIDUAL_COPY_IN_BN_BWD:     # something already flowed into it: read-add-write pass
+                    ops.add_into(gv, dout, acc)
                 else:                                      # first contribution: a copy, made by the BN-backward pass
                     dres = gv
                 G.mark(residual)
