@@ -203,7 +203,8 @@ int ryolo_unpack_wgrad_multi(const ryolo_pack_entry* table_dev, int n, long long
  * dwk = [Cout][Kpad]) += conv_backward_weight(x, dy).  x bf16 NHWC view [N,H,W,Cin]; dy bf16 NHWC view
  * [N,Ho,Wo,Cdy], Cdy >= Cout.  tcgen05 GEMM over pixels with MN-major operands, split-K across CTAs, vector fp32
  * atomics into dwk (csrc/wgrad.cu).  ryolo_unpack_wgrad_multi then adds every dwk into its OIHW gradient
- * (table as for ryolo_pack_weights_multi with src = dwk (fp32), dst = OIHW fp32 gradient, dst_t unused).       */
+ * (table as for ryolo_pack_weights_multi with src = dwk (fp32), dst = OIHW fp32 gradient, dst_t unused) and, with
+ * the default tiled kernel (knob ssa != 0), leaves every dwk element it folded ZEROED for the next step.           */
 int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, int Cin, const void* dy,
                        long long dy_cpitch, int Cdy, int Cout, int ksize, int stride, float* dwk, void* stream);
 /* d raw = backward of act(BatchNorm2d_train(raw)) given d out; d gamma, d beta (fp32[C], nullable) are ACCUMULATED

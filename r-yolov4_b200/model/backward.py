@@ -151,7 +151,9 @@ class _WgradSink:
         self.side = _side_stream(next(iter(param_grads.values())).device)
         if self.fused:
             self.views = model.wgrad_scratch()
-            model._wg_flat.zero_()
+            if not getattr(model, "_wg_clean", False):      # the tiled fold leaves the scratch zeroed (see unpack_wgrads)
+                model._wg_flat.zero_()
+            model._wg_clean = False                          # dirty until every weight gradient has been folded again
 
     def wgrad(self, x, dy, Cout, k, stride, weight, stem=False, keep=()):
         """Launch conv_wgrad on the side stream: it only reads x and dy (= d raw, final once the BN backward of this

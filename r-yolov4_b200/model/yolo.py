@@ -180,6 +180,8 @@ class Yolo(nn.Module):
         from .. import _lib as L_
         L_.check(L_.lib().ryolo_unpack_wgrad_multi(L_.ptr(self._wg_table), len(self._pack_meta), self._pack_total,
                                                    L_.stream()))
+        import os as _os
+        self._wg_clean = L_.lib().ryolo_knob(12) != 0 and _os.environ.get("RYOLO_WG_CLEAR", "1") != "0"   # knob "ssa": the tiled fold clears what it folds
         L_.count(1)
 
     def wgrad_subtable(self, param_ids):
