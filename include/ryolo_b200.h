@@ -120,7 +120,8 @@ enum { RYOLO_OUT_NHWC_BF16 = 0, RYOLO_OUT_HEAD_F32 = 1 };
  * variance) and num_batches_tracked.  The result is bit-reproducible run to run (like the reference's
  * cudnn.deterministic): within a CTA the order is fixed, across CTAs the sums are 64-bit fixed point.
  * partial = scratch of >= 4*Cout floats (2*Cout 64-bit accumulators), 8-byte aligned, ZERO on entry and left zero on
- * exit (so one zero-initialised scratch serves every layer of a stream); counter (u32) must be zero on entry;
+ * exit (so one zero-initialised scratch serves every layer of a stream); counter (u32) must be zero on entry, or NULL
+ * for a DEFERRED finalize (the kernel then only accumulates into partial; see ryolo_scale_shift_act_bn);
  * sum / sumsq (fp32[Cout]) are optional outputs.                                                              */
 #define RYOLO_BN_PARTIAL_ROWS 160   /* legacy sizing constant: callers allocate RYOLO_BN_PARTIAL_ROWS*2*Cout floats */
 typedef struct ryolo_bn_fuse {
@@ -168,6 +169,14 @@ int ryolo_conv2d_reference(const ryolo_conv_desc* d, void* stream);
  *                      also used for RepConv's two-branch sum (model/utils.py:209-215) and the Bottleneck
  *                      shortcut (model/utils.py:45-46)                                                   */
 int ryolo_bn_stats(const void* x, long long pitch, long long P, int C, float* sum, float* sumsq, void* stream);
+/* y = act(BN_train(x)) [+ residual] with the FINALIZE of the producing conv's fused statistics folded in: the conv ran
+ * with a ryolo_bn_fuse whose counter == NULL (deferred finalize: it only adds its per-channel totals to bn->partial, a
+ * zeroed per-layer accumulator of 4*C floats that nobody clears afterwards); this pass turns the totals into scale /
+ * shift per thread, publishes bn->scale / shift / save_mean / save_invstd and moves the running statistics
+ * (model/utils.py:16-23 in train mode).  count = N*Ho*Wo.                                                       */
+int ryolo_scale_shift_act_bn(const void* x, long long xp, const ryolo_bn_fuse* bn, double count, int act,
+                             const void* residual, long long rp, void* y, long long yp, long long P, int C,
+                             void* stream);
 int ryolo_bn_finalize(const float* sum, const float* sumsq, double count, int C, const float* gamma, const float* beta,
                       float eps, float momentum, float* running_mean, float* running_var, long long* num_batches,
                       float* scale, float* shift, float* save_mean, float* save_invstd, void* stream);

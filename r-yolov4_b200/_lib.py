@@ -67,6 +67,8 @@ SIGNATURES.update({
     "ryolo_bn_stats": (_i32, [_vp, _ll, _ll, _i32, _vp, _vp, _vp]),
     "ryolo_bn_finalize": (_i32, [_vp, _vp, _dbl, _i32, _vp, _vp, _f32, _f32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "ryolo_scale_shift_act": (_i32, [_vp, _ll, _vp, _vp, _vp, _ll, _vp, _vp, _i32, _vp, _ll, _vp, _ll, _ll, _i32, _vp]),
+    "ryolo_scale_shift_act_bn": (_i32, [_vp, _ll, ctypes.POINTER(BnFuse), ctypes.c_double, _i32, _vp, _ll, _vp, _ll, _ll,
+                                        _i32, _vp]),
     "ryolo_maxpool": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
     "ryolo_resize_copy": (_i32, [_vp, _ll, _i32, _i32, _i32, _i32, _i32, _vp, _ll, _vp]),
     "ryolo_stem_im2col": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),

@@ -58,6 +58,10 @@ static inline cudaError_t ry_launch(void (*kernel)(KArgs...), dim3 grid, dim3 bl
 }
 #endif
 
+// fused BatchNorm statistics: fixed-point scales of the cross-CTA 64-bit accumulators (|sum| < 2^39, sum of squares < 2^43)
+#define RY_BN_SUM_SCALE 16777216.f   /* 2^24 */
+#define RY_BN_SQ_SCALE 1048576.f     /* 2^20 */
+
 static inline size_t ry_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 __device__ __forceinline__ float ry_warp_sum(float v) {

@@ -32,8 +32,8 @@ constexpr int kThreads = 320;   // 10 warps: TMA, MMA, 2 x 4 epilogue
 constexpr int kMaxStages = 12;
 constexpr int kMaxAcc = 8;
 // fused BatchNorm statistics: fixed-point scales of the cross-CTA accumulators (|sum| < 2^39, sum of squares < 2^43)
-constexpr float kSumScale = 16777216.f;   // 2^24
-constexpr float kSqScale = 1048576.f;     // 2^20
+constexpr float kSumScale = RY_BN_SUM_SCALE;   // 2^24
+constexpr float kSqScale = RY_BN_SQ_SCALE;     // 2^20
 
 // ------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -201,7 +201,7 @@ struct ConvKernelParams {
   int kbk;                         // K elements per stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
-  int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads
+  int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads, 16 no cross-CTA statistics tail
   int halo;                        // 0 | 1 | 2: 3x3 stride-1 taps read shifted views of ONE (TH+2)x(TW+2) halo box (2: base_offset set)
   int a_slots; uint32_t a_slot_bytes;
   int epi_tma;                     // bf16 epilogue stages 64-channel slabs in smem and stores them with TMA (2: reduce-add)
@@ -640,7 +640,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-    if (do_stats) {
+    if (do_stats && !(p.dbg & 16)) {     // dbg 16 (timing experiment, wrong results): per-tile statistics only, no cross-CTA tail
       // Deterministic reduction (the reference runs with cudnn.deterministic, train.py:24): the 8 epilogue warps
       // combine through smem in a fixed order; across CTAs the sums are fixed-point (see below); the last CTA to
       // arrive turns the totals into scale/shift + running statistics.
@@ -667,6 +667,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           atomicAdd(acc + (size_t)q * p.Cout + c, (unsigned long long)__float2ll_rn(a * (q ? kSqScale : kSumScale)));
         }
       }
+      // counter == nullptr: deferred finalize.  The consumer (ryolo_scale_shift_act_bn) turns the totals into scale / shift
+      // itself, so this CTA is done: no fence, no arrival counter, no last-CTA pass (0.8 ms per yolov4 forward).
+      if (p.bn.counter != nullptr) {
       __threadfence();
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (et == 0) s_last = (atomicAdd(p.bn.counter, 1u) == gridDim.x - 1) ? 1 : 0;
@@ -697,6 +700,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
             p.bn.running_var[c] = (1.f - p.bn.momentum) * p.bn.running_var[c] + p.bn.momentum * (float)unbiased;
           }
         }
+      }
       }
     }
   }
@@ -824,7 +828,7 @@ int fill_params(const ryolo_conv_desc* d, ConvKernelParams* p) {
   if (d->bn) {
     RY_CHECK_ARG(d->out_mode == RYOLO_OUT_NHWC_BF16 && !d->scale && !d->shift && d->act == RYOLO_ACT_LINEAR &&
                      !d->residual, "conv: fused BatchNorm statistics need the raw (no scale/shift/act/residual) epilogue");
-    RY_CHECK_ARG(d->bn->partial && d->bn->counter && d->bn->gamma && d->bn->beta && d->bn->scale && d->bn->shift,
+    RY_CHECK_ARG(d->bn->partial && (!d->bn->counter || (d->bn->gamma && d->bn->beta && d->bn->scale && d->bn->shift)),
                  "conv: incomplete ryolo_bn_fuse");
     p->bn = *d->bn;
   }

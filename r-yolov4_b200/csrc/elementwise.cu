@@ -225,26 +225,11 @@ __device__ __forceinline__ uint4 ssa_row(const uint4& vx, const uint4& v2, const
 }
 
 template <int ACT, bool HAS_X2, bool HAS_RES>
-__global__ void __launch_bounds__(256, 2)
-scale_shift_act_p_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
-                         const float* __restrict__ shift, const __nv_bfloat16* __restrict__ x2, long long x2p,
-                         const float* __restrict__ scale2, const float* __restrict__ shift2,
-                         const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
-                         long long P, int C) {
-  ry_pdl_wait();
-  const int groups = C >> 3;
-  const int rows = blockDim.x / groups;
-  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
-  if (r >= rows) return;
-  const int c = 8 * g;
-  float sc[8], sh[8], sc2[8];
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    sc[j] = scale[c + j];
-    sh[j] = shift[c + j];
-    sc2[j] = 0.f;
-    if (HAS_X2) { sc2[j] = scale2[c + j]; sh[j] += shift2[c + j]; }
-  }
+__device__ __forceinline__ void ssa_walk(const __nv_bfloat16* __restrict__ x, long long xp,
+                                         const __nv_bfloat16* __restrict__ x2, long long x2p,
+                                         const __nv_bfloat16* __restrict__ res, long long rp,
+                                         __nv_bfloat16* __restrict__ y, long long yp, long long P, int c, int r, int rows,
+                                         const float (&sc)[8], const float (&sh)[8], const float (&sc2)[8]) {
   constexpr int U = (HAS_X2 || HAS_RES) ? 2 : 4;
   const int stride = (int)gridDim.x * rows;
   const int pix0 = (int)blockIdx.x * rows + r;
@@ -302,6 +287,91 @@ scale_shift_act_p_kernel(const __nv_bfloat16* __restrict__ x, long long xp, cons
     if (HAS_RES) pr += sr;
     py += sy;
   }
+}
+
+template <int ACT, bool HAS_X2, bool HAS_RES>
+__global__ void __launch_bounds__(256, 2)
+scale_shift_act_p_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const float* __restrict__ scale,
+                         const float* __restrict__ shift, const __nv_bfloat16* __restrict__ x2, long long x2p,
+                         const float* __restrict__ scale2, const float* __restrict__ shift2,
+                         const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
+                         long long P, int C) {
+  ry_pdl_wait();
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (r >= rows) return;
+  const int c = 8 * g;
+  float sc[8], sh[8], sc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    sc[j] = scale[c + j];
+    sh[j] = shift[c + j];
+    sc2[j] = 0.f;
+    if (HAS_X2) { sc2[j] = scale2[c + j]; sh[j] += shift2[c + j]; }
+  }
+  ssa_walk<ACT, HAS_X2, HAS_RES>(x, xp, x2, x2p, res, rp, y, yp, P, c, r, rows, sc, sh, sc2);
+}
+
+// The same pass with the train-mode BatchNorm FINALIZE folded in (ryolo_scale_shift_act_bn): the producing conv only
+// accumulated its per-channel fixed-point totals (ryolo_bn_fuse with counter == NULL); every thread here turns the
+// totals of its 8 channels into scale / shift (the same double-precision arithmetic as the conv kernel's last-CTA pass,
+// bit for bit), and block 0 publishes scale / shift / mean / invstd for the backward pass and moves the running
+// statistics.  Removes the fence + arrival counter + last-CTA pass from every conv launch's tail.
+struct SsaBn {
+  const unsigned long long* acc;      // [2][C] fixed-point sum | sum of squares
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var; long long* num_batches;
+  float eps, momentum;
+  double k_sum, k_sq, k_unbias;
+  float* scale; float* shift; float* save_mean; float* save_invstd;
+};
+
+template <int ACT, bool HAS_RES>
+__global__ void __launch_bounds__(256, 2)
+scale_shift_act_bn_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const SsaBn bn,
+                          const __nv_bfloat16* __restrict__ res, long long rp, __nv_bfloat16* __restrict__ y, long long yp,
+                          long long P, int C) {
+  ry_pdl_wait();
+  extern __shared__ float s_fin[];               // [2][C]: scale | shift of this launch, computed once per block
+  const int groups = C >> 3;
+  const int rows = blockDim.x / groups;
+  const int g = threadIdx.x % groups, r = threadIdx.x / groups;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bn.num_batches) *bn.num_batches += 1;
+  // One channel per thread (the first version had every thread finalize its own 8 channels: 2048 double-precision
+  // finalizations per block instead of C, ~10 us per launch).  The cancellation-prone part (E[x^2] - mean^2 on exact
+  // integer totals) is double, the reciprocal square root rsqrt.approx + one Newton step in fp32.
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    const long long is = (long long)__ldcg(bn.acc + ch), iq = (long long)__ldcg(bn.acc + C + ch);
+    const double mean = (double)is * bn.k_sum;                    // k_sum = 1 / (2^24 count)
+    double var = fma((double)iq, bn.k_sq, -mean * mean);          // k_sq  = 1 / (2^20 count)
+    if (var < 0.0) var = 0.0;
+    const float vf = (float)(var + (double)bn.eps);
+    float invstd = rsqrtf(vf);
+    invstd = invstd * fmaf(-0.5f * vf * invstd, invstd, 1.5f);
+    const float s = bn.gamma[ch] * invstd;
+    const float t = bn.beta[ch] - (float)mean * s;
+    s_fin[ch] = s;
+    s_fin[C + ch] = t;
+    if (blockIdx.x == 0) {                       // publish for the backward pass / eval mode
+      bn.scale[ch] = s;
+      bn.shift[ch] = t;
+      if (bn.save_mean) bn.save_mean[ch] = (float)mean;
+      if (bn.save_invstd) bn.save_invstd[ch] = invstd;
+      if (bn.running_mean) {
+        const double unbiased = var * bn.k_unbias;                // count / (count - 1), or 1
+        bn.running_mean[ch] = (1.f - bn.momentum) * bn.running_mean[ch] + bn.momentum * (float)mean;
+        bn.running_var[ch] = (1.f - bn.momentum) * bn.running_var[ch] + bn.momentum * (float)unbiased;
+      }
+    }
+  }
+  __syncthreads();
+  if (r >= rows) return;
+  const int c = 8 * g;
+  float sc[8], sh[8], sc2[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) { sc[j] = s_fin[c + j]; sh[j] = s_fin[C + c + j]; sc2[j] = 0.f; }
+  ssa_walk<ACT, false, HAS_RES>(x, xp, nullptr, 0, res, rp, y, yp, P, c, r, rows, sc, sh, sc2);
 }
 
 typedef void (*SsaFn)(const __nv_bfloat16*, long long, const float*, const float*, const __nv_bfloat16*, long long,
@@ -723,6 +793,53 @@ int ryolo_scale_shift_act(const void* x, long long xp, const float* scale, const
   const int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
   ry_launch(fn, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, xp, scale, shift,
             (const __nv_bfloat16*)x2, x2p, scale2, shift2, (const __nv_bfloat16*)residual, rp, (__nv_bfloat16*)y, yp, P, C);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
+// scale_shift_act with the BatchNorm finalize of a deferred-finalize conv folded in (see scale_shift_act_bn_kernel).
+// bn: HOST pointer; bn->partial = the accumulators the conv filled (NOT cleared here: the caller zeroes its arena once per
+// forward pass), bn->counter ignored; count = N*Ho*Wo of the conv output.
+int ryolo_scale_shift_act_bn(const void* x, long long xp, const ryolo_bn_fuse* bn, double count, int act,
+                             const void* residual, long long rp, void* y, long long yp, long long P, int C,
+                             void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && C >= 8 && C <= 2048 && xp % 8 == 0 && yp % 8 == 0,
+               "scale_shift_act_bn: channels must be a multiple of 8 in [8, 2048]");
+  RY_CHECK_ARG(bn && bn->partial && bn->gamma && bn->beta && bn->scale && bn->shift && count > 0,
+               "scale_shift_act_bn: incomplete ryolo_bn_fuse");
+  RY_CHECK_ARG(P < (1ll << 31) - (1 << 20), "scale_shift_act_bn: more than 2^31 pixels");
+  if (P == 0) return RYOLO_OK;
+  SsaBn b;
+  b.acc = reinterpret_cast<const unsigned long long*>(bn->partial);
+  b.gamma = bn->gamma; b.beta = bn->beta;
+  b.running_mean = bn->running_mean; b.running_var = bn->running_var; b.num_batches = bn->num_batches;
+  b.eps = bn->eps; b.momentum = bn->momentum;
+  b.k_sum = 1.0 / ((double)RY_BN_SUM_SCALE * count);
+  b.k_sq = 1.0 / ((double)RY_BN_SQ_SCALE * count);
+  b.k_unbias = count > 1.0 ? count / (count - 1.0) : 1.0;
+  b.scale = bn->scale; b.shift = bn->shift; b.save_mean = bn->save_mean; b.save_invstd = bn->save_invstd;
+  const int groups = C / 8;
+  RY_CHECK_ARG(groups <= 256, "scale_shift_act_bn: too many channels");
+  const int rows = 256 / groups;
+  const int per_trip = residual ? 2 : 4;
+  long long want = (P + (long long)rows * per_trip - 1) / ((long long)rows * per_trip);
+  const long long cap = 2ll * ry_sm_count();
+  const int blocks = (int)(want > cap ? cap : (want < 1 ? 1 : want));
+  cudaStream_t st = (cudaStream_t)stream;
+  const __nv_bfloat16* xx = (const __nv_bfloat16*)x;
+  const __nv_bfloat16* rr = (const __nv_bfloat16*)residual;
+  __nv_bfloat16* yy = (__nv_bfloat16*)y;
+  const size_t fin_smem = (size_t)2 * C * sizeof(float);
+#define RY_SSABN(ACT)                                                                                            \
+  if (residual) ry_launch(scale_shift_act_bn_kernel<ACT, true>, dim3(blocks), dim3(256), fin_smem, st, xx, xp, b, rr, rp, yy, yp, P, C); \
+  else ry_launch(scale_shift_act_bn_kernel<ACT, false>, dim3(blocks), dim3(256), fin_smem, st, xx, xp, b, rr, rp, yy, yp, P, C);
+  switch (act) {
+    case RYOLO_ACT_LEAKY: RY_SSABN(RYOLO_ACT_LEAKY) break;
+    case RYOLO_ACT_MISH: RY_SSABN(RYOLO_ACT_MISH) break;
+    case RYOLO_ACT_SWISH: RY_SSABN(RYOLO_ACT_SWISH) break;
+    default: RY_SSABN(RYOLO_ACT_LINEAR) break;
+  }
+#undef RY_SSABN
   RY_CHECK_LAUNCH();
   return RYOLO_OK;
 }

@@ -8,6 +8,8 @@ ELAN1 :98-118, ELAN2 :121-143, MaxConv :146-160, ImplicitA/M :163-186, RepConv :
 SPP :218-244, SPPCSPC :264-282.  torch.cat is replaced by writing producers into channel slices of
 one buffer.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -30,17 +32,30 @@ class Ctx:
         self._partial = torch.zeros(4 * 2048, dtype=torch.float32, device=device) if training else None
         self._counters = torch.zeros(model._bn_layers, dtype=torch.int32, device=device) if training else None
         self._ctr_off = 0
+        # deferred finalize (plain Conv blocks): one zeroed arena, a private 4*C-float accumulator per layer
+        self._acc = torch.zeros(4 * model._bn_channels, dtype=torch.float32, device=device) \
+            if training and DEFER_BN_FINALIZE else None
+        self._acc_off = 0
         if training:
             BN_EPOCH[0] += 1      # the fused conv epilogue rewrites running statistics through raw pointers
 
     def new(self, N, H, W, C):
         return Act.empty(N, H, W, C, self.device)
 
+    def acc_slot(self, C):
+        a = self._acc[self._acc_off:self._acc_off + 4 * C]
+        self._acc_off += 4 * C
+        return a
+
     def stat_slot(self, C):
         ctr = self._counters[self._ctr_off:self._ctr_off + 1]
         self._ctr_off += 1
         return self._partial, ctr
 
+
+# The conv kernel only accumulates its BatchNorm totals and scale_shift_act_bn finalizes them (no fence / arrival counter /
+# last-CTA pass in every conv launch's tail).  RYOLO_BN_DEFER=0 restores the in-conv finalize (A/B switch).
+DEFER_BN_FINALIZE = os.environ.get("RYOLO_BN_DEFER", "1") != "0"
 
 WEIGHT_EPOCH = [0]     # bumped by whoever rewrites parameters through raw pointers (TrainStep's SGD kernel)
 BN_EPOCH = [0]         # bumped by every training-mode forward: running statistics change without a torch version bump
@@ -109,14 +124,21 @@ class Conv(nn.Module):
             scale, shift = _bn_eval_affine(bn, self._affine)
             return ops.conv2d(x, w, self.c2, k, st, out=out, scale=scale, shift=shift, act=self.act,
                               residual=residual)
-        part, ctr = ctx.stat_slot(self.c2)
         aff = torch.empty(4 * self.c2, dtype=torch.float32, device=ctx.device)
         scale, shift, mean, invstd = aff[:self.c2], aff[self.c2:2 * self.c2], aff[2 * self.c2:3 * self.c2], \
             aff[3 * self.c2:]
-        raw = ops.conv2d(x, w, self.c2, k, st, bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
-        if out is None:
-            out = ctx.new(raw.N, raw.H, raw.W, self.c2)
-        ops.scale_shift_act(raw, scale, shift, self.act, out, residual=residual)
+        if ctx._acc is not None:
+            bnf = ops.bn_fuse(ctx.acc_slot(self.c2), None, bn, scale, shift, mean, invstd)
+            raw = ops.conv2d(x, w, self.c2, k, st, bn=bnf)
+            if out is None:
+                out = ctx.new(raw.N, raw.H, raw.W, self.c2)
+            ops.scale_shift_act_bn(raw, bnf, self.act, out, residual=residual)
+        else:
+            part, ctr = ctx.stat_slot(self.c2)
+            raw = ops.conv2d(x, w, self.c2, k, st, bn=ops.bn_fuse(part, ctr, bn, scale, shift, mean, invstd))
+            if out is None:
+                out = ctx.new(raw.N, raw.H, raw.W, self.c2)
+            ops.scale_shift_act(raw, scale, shift, self.act, out, residual=residual)
         ctx.tape.append(("conv", self, x, raw, out, residual, scale, shift, mean, invstd))
         return out
 

@@ -84,7 +84,10 @@ def bn_fuse(partial, counter, bn, scale, shift, save_mean=None, save_invstd=None
     partial: ZEROED fp32 scratch with >= 4*C elements (left zeroed by the kernel); counter: zeroed int32[1]."""
     f = L.BnFuse()
     assert partial.numel() >= 4 * bn.num_features and partial.data_ptr() % 8 == 0
-    f.partial, f.sum, f.sumsq, f.counter = partial.data_ptr(), None, None, counter.data_ptr()
+    # counter None: deferred finalize (the conv only accumulates; scale_shift_act_bn finalizes; `partial` is then a
+    # per-layer accumulator nobody clears)
+    f.partial, f.sum, f.sumsq = partial.data_ptr(), None, None
+    f.counter = counter.data_ptr() if counter is not None else None
     f.gamma, f.beta = bn.weight.data_ptr(), bn.bias.data_ptr()
     f.running_mean, f.running_var = bn.running_mean.data_ptr(), bn.running_var.data_ptr()
     f.num_batches = bn.num_batches_tracked.data_ptr()
@@ -181,6 +184,16 @@ def scale_shift_act(x, scale, shift, act, out, residual=None, x2=None, scale2=No
     L.check(L.lib().ryolo_scale_shift_act(
         _vp(x.ptr), x.pitch, _tp(scale), _tp(shift), _vp(x2.ptr if x2 is not None else 0),
         x2.pitch if x2 is not None else 0, _tp(scale2), _tp(shift2), ACT[act],
+        _vp(residual.ptr if residual is not None else 0), residual.pitch if residual is not None else 0,
+        _vp(out.ptr), out.pitch, x.P, x.C, L.stream()))
+    L.count(1)
+    return out
+
+
+def scale_shift_act_bn(x, bnf, act, out, residual=None):
+    """act(BN_train(x)) [+ residual] with the finalize of the producing conv's deferred statistics folded in."""
+    L.check(L.lib().ryolo_scale_shift_act_bn(
+        _vp(x.ptr), x.pitch, ctypes.byref(bnf), float(x.P), ACT[act],
         _vp(residual.ptr if residual is not None else 0), residual.pitch if residual is not None else 0,
         _vp(out.ptr), out.pitch, x.P, x.C, L.stream()))
     L.count(1)

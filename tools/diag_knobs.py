@@ -49,6 +49,7 @@ VARIANTS = [
     ("nostore_nostats", dict(dbg=3)),
     ("nomma", dict(dbg=4)),
     ("noaload", dict(dbg=8)),
+    ("nostatstail", dict(dbg=16)),
     ("noaload_nostats", dict(dbg=10)),
     ("noaload_nomma", dict(dbg=12)),
     ("halo", dict(halo=1)),
