@@ -78,3 +78,18 @@ def test_schedule_matches_reference_loop(epochs, ipe, bs, lr):
         optimizer.step()
         scheduler.step()
         assert abs(sch.epoch_end() - optimizer.param_groups[0]['lr']) <= 1e-12
+
+
+def test_decode_csl_tie_window_is_conservative():
+    """csrc/decode.cu only evaluates the sigmoid of angle logits x >= cut(m), m = the largest logit, with
+    cut = min(m, 14) - 2^-19 (1 + e^min(m, 14)).  A logit below the cut must be out of reach of a tie: its sigmoid must lie
+    more than a handful of fp32 ulps under sigmoid(m), whatever 2-ulp error the device's expf adds on either side."""
+    import numpy as np
+    for m in np.concatenate((np.linspace(-30, 13.9, 200), np.linspace(14, 40, 60))):
+        mc = min(m, 14.0)
+        cut = mc - 2.0 ** -19 * (1.0 + np.exp(mc))
+        x = np.nextafter(np.float32(cut), np.float32(-np.inf)).astype(np.float64)      # the largest excluded logit
+        s_m = 1.0 / (1.0 + np.exp(-np.float64(m)))
+        s_x = 1.0 / (1.0 + np.exp(-x))
+        ulp = np.spacing(np.float32(s_m)).astype(np.float64)
+        assert s_m - s_x > 3.0 * ulp, (m, cut, (s_m - s_x) / ulp)
