@@ -201,7 +201,7 @@ struct ConvKernelParams {
   int kbk;                         // K elements per stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
-  int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads, 16 no cross-CTA statistics tail
+  int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads, 16 no cross-CTA statistics tail, 32 no weight loads
   int halo;                        // 0 | 1 | 2: 3x3 stride-1 taps read shifted views of ONE (TH+2)x(TW+2) halo box (2: base_offset set)
   int a_slots; uint32_t a_slot_bytes;
   int epi_tma;                     // bf16 epilogue stages 64-channel slabs in smem and stores them with TMA (2: reduce-add)
@@ -289,7 +289,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && !p.halo) {
     // ================================ TMA producer (warp-uniform loop, one elected lane issues) ===============
     const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
-    const uint32_t tx_bytes = ((p.dbg & 8) ? 0u : a_bytes) + kBBytes;
+    const uint32_t tx_bytes = ((p.dbg & 8) ? 0u : a_bytes) + ((p.dbg & 32) ? 0u : kBBytes);
     const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
     int s = 0;
     uint32_t phase = 0;
@@ -307,7 +307,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_expect_tx(bar_full + 8 * s, tx_bytes);
           if (!(p.dbg & 8))
             tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * p.kbk, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
-          tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
+          if (!(p.dbg & 32))                    // dbg 32 (timing experiment, wrong results): no weight loads
+            tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; phase ^= 1u; }

@@ -50,6 +50,8 @@ VARIANTS = [
     ("nomma", dict(dbg=4)),
     ("noaload", dict(dbg=8)),
     ("nostatstail", dict(dbg=16)),
+    ("nobload", dict(dbg=32)),
+    ("noload", dict(dbg=40)),
     ("noaload_nostats", dict(dbg=10)),
     ("noaload_nomma", dict(dbg=12)),
     ("halo", dict(halo=1)),
