@@ -233,10 +233,13 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   EPI_HEAD    y = acc*scale + shift -> fp32 [B, na, gs, gs, ch]
 enum { EPI_RAW = 0, EPI_AFFINE = 1, EPI_HEAD = 2 };
 
-template <int EPI, int ACT>
+template <int EPI, int ACT, bool DBG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
+  // The timing-experiment switches only exist in the DBG instantiations: the production kernels' producer / issuer loops
+  // are serial single-warp instruction chains in which every instruction costs ~5 cycles per K stage.
+  const int dbg = DBG ? p.dbg : 0;
   const int BN = p.BN, STAGES = p.stages;
   const uint32_t kABytes = kBM * (uint32_t)p.kbk * 2, kBBytes = (uint32_t)BN * (uint32_t)p.kbk * 2;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -289,7 +292,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && !p.halo) {
     // ================================ TMA producer (warp-uniform loop, one elected lane issues) ===============
     const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
-    const uint32_t tx_bytes = ((p.dbg & 8) ? 0u : a_bytes) + ((p.dbg & 32) ? 0u : kBBytes);
+    const uint32_t tx_bytes = ((dbg & 8) ? 0u : a_bytes) + ((dbg & 32) ? 0u : kBBytes);
     const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
     int s = 0;
     uint32_t phase = 0;
@@ -305,9 +308,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bar_empty + 8 * s, phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(bar_full + 8 * s, tx_bytes);
-          if (!(p.dbg & 8))
+          if (!(dbg & 8))
             tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * p.kbk, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
-          if (!(p.dbg & 32))                    // dbg 32 (timing experiment, wrong results): no weight loads
+          if (!(dbg & 32))                    // dbg 32 (timing experiment, wrong results): no weight loads
             tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
         }
         __syncwarp();
@@ -356,8 +359,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (kb >= KB) kb -= KB;
           const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
           mbar_wait(bar_empty + 8 * s, phase ^ 1u);
-          mbar_expect_tx(bar_full + 8 * s, ((p.dbg & 8) ? 0u : a_bytes) + kBBytes);
-          if (!(p.dbg & 8))
+          mbar_expect_tx(bar_full + 8 * s, ((dbg & 8) ? 0u : a_bytes) + kBBytes);
+          if (!(dbg & 8))
             tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * p.kbk, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
           tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
           if (++s == STAGES) { s = 0; phase ^= 1u; }
@@ -385,7 +388,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         tc_fence_after();
         if (elect_one()) {
           const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * a_step), bd = bdesc0 + (uint64_t)((uint32_t)s * b_step);
-          if (!(p.dbg & 4)) {
+          if (!(dbg & 4)) {
             umma_bf16(d_tmem, ad, bd, idesc, kb ? 1u : 0u);
             umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
             if (ksteps == 4) {
@@ -442,7 +445,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           mbar_wait(bar_full + 8 * s, phase);
           tc_fence_after();
           const uint32_t a0 = sA + s * kABytes, b0 = sB + s * kBBytes;
-          if (!(p.dbg & 4)) {
+          if (!(dbg & 4)) {
             if (p.kbk == 32) {
 #pragma unroll
               for (int k = 0; k < 2; k++)
@@ -478,7 +481,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
-    const bool do_stats = (EPI == EPI_RAW) && (p.bn.partial != nullptr) && !(p.dbg & 2);
+    const bool do_stats = (EPI == EPI_RAW) && (p.bn.partial != nullptr) && !(dbg & 2);
     const bool tma = (EPI != EPI_HEAD) && p.epi_tma != 0;
     const bool leader = ((warp - 2) & 3) == 0 && lane == 0;   // issues this epilogue group's TMA stores
     const uint32_t stg = sStage + eg * 16384u;
@@ -494,7 +497,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ph = mt % p.tiles_h;
       const int img = mt / p.tiles_h;
       const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
-      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo) && !(p.dbg & 1);
+      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo) && !(dbg & 1);
       const long long pix = ((long long)img * p.OutH + ho * p.out_s + p.out_oh) * p.OutW + wo * p.out_s + p.out_ow;
       const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;   // nacc is even: tiles of one parity
       mbar_wait(bar_acc_full + 8 * buf, aphase);
@@ -629,7 +632,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               if (slab_last) {
                 fence_proxy_async();
                 group_bar(2u + eg);
-                if (leader && !(p.dbg & 1)) {
+                if (leader && !(dbg & 1)) {
                   const int cc = n0 + (ci >> 1) * 64;
                   if (p.epi_tma == 2) tma_reduce_add_4d(&tmO, stg, cc, pw * p.TW, ph * p.TH, img);
                   else tma_store_4d(&tmO, stg, cc, pw * p.TW, ph * p.TH, img);
@@ -641,7 +644,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
       }
     }
-    if (do_stats && !(p.dbg & 16)) {     // dbg 16 (timing experiment, wrong results): per-tile statistics only, no cross-CTA tail
+    if (do_stats && !(dbg & 16)) {     // dbg 16 (timing experiment, wrong results): per-tile statistics only, no cross-CTA tail
       // Deterministic reduction (the reference runs with cudnn.deterministic, train.py:24): the 8 epilogue warps
       // combine through smem in a fixed order; across CTAs the sums are fixed-point (see below); the last CTA to
       // arrive turns the totals into scale/shift + running statistics.
@@ -918,19 +921,24 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   while (cols < (uint32_t)nacc * (uint32_t)p.BN) cols <<= 1;
   p.tmem_cols = cols;
   typedef void (*KernelFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const ConvKernelParams);
-  KernelFn fn = nullptr;
   const bool affine = p.scale || p.shift || p.act != RYOLO_ACT_LINEAR || p.residual;
-  if (p.mode == RYOLO_OUT_HEAD_F32) fn = conv_fwd_kernel<EPI_HEAD, 0>;
-  else if (!affine) fn = conv_fwd_kernel<EPI_RAW, 0>;
-  else if (p.act == RYOLO_ACT_LEAKY) fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY>;
-  else if (p.act == RYOLO_ACT_MISH) fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH>;
-  else if (p.act == RYOLO_ACT_SWISH) fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH>;
-  else fn = conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR>;
+  int which;                      // 0 head | 1 raw | 2 leaky | 3 mish | 4 swish | 5 linear-affine
+  if (p.mode == RYOLO_OUT_HEAD_F32) which = 0;
+  else if (!affine) which = 1;
+  else if (p.act == RYOLO_ACT_LEAKY) which = 2;
+  else if (p.act == RYOLO_ACT_MISH) which = 3;
+  else if (p.act == RYOLO_ACT_SWISH) which = 4;
+  else which = 5;
+  static const KernelFn all[12] = {
+      conv_fwd_kernel<EPI_HEAD, 0, false>, conv_fwd_kernel<EPI_RAW, 0, false>,
+      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY, false>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH, false>,
+      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH, false>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR, false>,
+      conv_fwd_kernel<EPI_HEAD, 0, true>, conv_fwd_kernel<EPI_RAW, 0, true>,
+      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY, true>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH, true>,
+      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH, true>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR, true>};
+  const KernelFn fn = all[which + (p.dbg ? 6 : 0)];
   static bool configured = false;
   if (!configured) {
-    KernelFn all[6] = {conv_fwd_kernel<EPI_HEAD, 0>, conv_fwd_kernel<EPI_RAW, 0>,
-                       conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH>,
-                       conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR>};
     for (KernelFn k : all) {
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
       if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
