@@ -198,7 +198,8 @@ struct ConvKernelParams {
   int nacc;                        // TMEM accumulators in rotation (2..8, even): hides the MMA <-> epilogue hand-back latency
   int ksize, stride, pad, kb_per_tap;
   int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
-  int kbk;                         // K elements per stage: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
+  int kbk;                         // K elements per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
+  int kgrp;                        // K blocks per ring stage (one full / empty barrier hand-shake and one commit per stage)
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
   int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads, 16 no cross-CTA statistics tail, 32 no weight loads
@@ -233,7 +234,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   EPI_HEAD    y = acc*scale + shift -> fp32 [B, na, gs, gs, ch]
 enum { EPI_RAW = 0, EPI_AFFINE = 1, EPI_HEAD = 2 };
 
-template <int EPI, int ACT, bool DBG>
+template <int EPI, int ACT, bool DBG, int KG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
@@ -245,8 +246,11 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
   const uint32_t sA = smem_base;
-  const uint32_t sB = smem_base + (p.halo ? (uint32_t)p.a_slots * p.a_slot_bytes : (uint32_t)STAGES * kABytes);
-  const uint32_t sStage = sB + (uint32_t)STAGES * kBBytes;   // epi_tma: one 128-row x 64-channel bf16 slab per epilogue group
+  constexpr int G = KG;                                              // K blocks per ring stage (compile time: the issue loops below
+                                                                     // are single-warp serial chains, every instruction in them counts)
+  const uint32_t stA = (uint32_t)G * kABytes, stB = (uint32_t)G * kBBytes;
+  const uint32_t sB = smem_base + (p.halo ? (uint32_t)p.a_slots * p.a_slot_bytes : (uint32_t)STAGES * stA);
+  const uint32_t sStage = sB + (uint32_t)STAGES * stB;   // epi_tma: one 128-row x 64-channel bf16 slab per epilogue group
   __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kMaxAcc + 8];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
@@ -292,8 +296,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && !p.halo) {
     // ================================ TMA producer (warp-uniform loop, one elected lane issues) ===============
     const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
-    const uint32_t tx_bytes = ((dbg & 8) ? 0u : a_bytes) + ((dbg & 32) ? 0u : kBBytes);
-    const int krot = (int)((blockIdx.x * 5u) % (unsigned)KB);
+    const uint32_t tx_bytes = (((dbg & 8) ? 0u : a_bytes) + ((dbg & 32) ? 0u : kBBytes)) * (uint32_t)G;
+    // A stage carries G consecutive K blocks behind ONE full / empty barrier pair: the issue loops pay their fixed cost
+    // (barrier wait, fence, elect, commit: ~0.2 us whatever the stage carries) once per G blocks.
+    const int KS = KB / G;
+    // every CTA walks the K blocks in its own rotation: otherwise all 148 CTAs request the SAME weight tile from the same
+    // L2 lines at the same time (the sum is order-independent up to fp32 rounding, and the tile -> CTA map is static, so
+    // results stay reproducible)
+    const int krot = (int)((blockIdx.x * 5u) % (unsigned)KS) * G;
     int s = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -303,19 +313,28 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       const int ph = mt % p.tiles_h;
       const int img = mt / p.tiles_h;
       const int hs = ph * p.TH * p.stride, ws = pw * p.TW * p.stride, n0 = nt * BN;
-      int tap = krot / p.kb_per_tap, cb = krot - tap * p.kb_per_tap;       // per-CTA rotation of the K blocks (see below)
-      for (int kb0 = 0; kb0 < KB; kb0++) {
+      int tap = krot / p.kb_per_tap, cb = krot - tap * p.kb_per_tap;
+      for (int ks = 0; ks < KS; ks++) {
         mbar_wait(bar_empty + 8 * s, phase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(bar_full + 8 * s, tx_bytes);
-          if (!(dbg & 8))
-            tma_load_4d(sA + s * kABytes, &tmA, bar_full + 8 * s, cb * p.kbk, ws + p.tap_dw[tap], hs + p.tap_dh[tap], img);
-          if (!(dbg & 32))                    // dbg 32 (timing experiment, wrong results): no weight loads
-            tma_load_2d(sB + s * kBBytes, &tmB, bar_full + 8 * s, (int)p.tap_k[tap] * p.Ktap + cb * p.kbk, n0);
+          int tp = tap, c = cb;
+          uint32_t da = sA + s * stA, db = sB + s * stB;
+#pragma unroll
+          for (int g = 0; g < G; g++) {
+            if (!(dbg & 8))
+              tma_load_4d(da, &tmA, bar_full + 8 * s, c * p.kbk, ws + p.tap_dw[tp], hs + p.tap_dh[tp], img);
+            if (!(dbg & 32))                    // dbg 32 (timing experiment, wrong results): no weight loads
+              tma_load_2d(db, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk, n0);
+            da += kABytes; db += kBBytes;
+            if (++c == p.kb_per_tap) { c = 0; if (++tp == p.ntaps) tp = 0; }
+          }
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; phase ^= 1u; }
-        if (++cb == p.kb_per_tap) { cb = 0; if (++tap == p.ntaps) tap = 0; }
+#pragma unroll
+        for (int g = 0; g < G; g++)
+          if (++cb == p.kb_per_tap) { cb = 0; if (++tap == p.ntaps) tap = 0; }
       }
     }
   } else if (warp == 0) {
@@ -374,8 +393,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // descriptors differ between stages only in their 14-bit start-address field (bytes >> 4, no carry out of it)
     const uint64_t adesc0 = sw64 ? umma_desc_k_sw64(sA) : umma_desc_k_sw128(sA);
     const uint64_t bdesc0 = sw64 ? umma_desc_k_sw64(sB) : umma_desc_k_sw128(sB);
-    const uint32_t a_step = kABytes >> 4, b_step = kBBytes >> 4;
+    const uint32_t a_step = stA >> 4, b_step = stB >> 4, a_blk = kABytes >> 4, b_blk = kBBytes >> 4;
     const int ksteps = p.kbk >> 4;
+    const int KS = KB / G;
     int s = 0;
     uint32_t phase = 0, it = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
@@ -383,21 +403,31 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * (uint32_t)BN;
-      for (int kb = 0; kb < KB; kb++) {
+      for (int ks = 0; ks < KS; ks++) {
         mbar_wait(bar_full + 8 * s, phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * a_step), bd = bdesc0 + (uint64_t)((uint32_t)s * b_step);
+          uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * a_step), bd = bdesc0 + (uint64_t)((uint32_t)s * b_step);
           if (!(dbg & 4)) {
-            umma_bf16(d_tmem, ad, bd, idesc, kb ? 1u : 0u);
+            umma_bf16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
             umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
             if (ksteps == 4) {
               umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
               umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
             }
+#pragma unroll
+            for (int g = 1; g < G; g++) {
+              ad += a_blk; bd += b_blk;
+              umma_bf16(d_tmem, ad, bd, idesc, 1u);
+              umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
+              if (ksteps == 4) {
+                umma_bf16(d_tmem, ad + 4, bd + 4, idesc, 1u);
+                umma_bf16(d_tmem, ad + 6, bd + 6, idesc, 1u);
+              }
+            }
           }
           umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
-          if (kb == KB - 1) umma_commit(bar_acc_full + 8 * buf);  // accumulator complete
+          if (ks == KS - 1) umma_commit(bar_acc_full + 8 * buf);  // accumulator complete
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; phase ^= 1u; }
@@ -906,6 +936,25 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
     stage_bytes = (size_t)p.BN * kBK * 2;
   }
   const size_t slab_bytes = p.epi_tma ? 2 * 16384 : 0;      // one slab per epilogue group, after the ring
+  // K blocks per stage (knob kgrp: 0 = always one; 1 (default) = N <= 32 tiles only, stages of up to 40 KB with a ring of
+  // >= 3; 2 = any tile, up to 64 KB with a ring of >= 2; 3 = up to 72 KB): the largest divisor (<= 3) of the tile's K-block
+  // count that fits.  Measured per layer (gpurun_out/r4b_diag_knobs_bs32.txt -> profiles/r02_kgrp_ab.txt): the Cin = 32
+  // 3x3 layers on 400x400 maps (10 KB per block, two N = 32 MMAs) spend their time on the per-stage barrier hand-shake:
+  // three taps per stage take them from 0.47 to 0.35 ms (forward and dgrad alike), the stride-2 dgrad classes of the
+  // 32 -> 64 layer gain 9 %.  Wider tiles lose: a 64 KB stage leaves N = 128 layers a ring of two (+12 %).
+  p.kgrp = 1;
+  if (!p.halo && !p.dbg) {
+    const int knob_g = ryolo_knob(RYOLO_KNOB_KGRP);
+    const size_t limit = knob_g == 1 ? 40 * 1024 : knob_g == 2 ? 64 * 1024 : knob_g >= 3 ? 72 * 1024 : 0;
+    const size_t min_ring = knob_g == 1 ? 3 : 2;
+    const int KB = p.ntaps * p.kb_per_tap;
+    for (int g = 2; g <= 3; g++) {
+      if (KB % g) continue;
+      if (knob_g == 1 && p.BN > 32) continue;
+      if (g * stage_bytes <= limit && (kSmemBudget - 1024 - slab_bytes) / (g * stage_bytes) >= min_ring) p.kgrp = g;
+    }
+    stage_bytes *= (size_t)p.kgrp;
+  }
   int stages = (int)((kSmemBudget - 1024 - fixed - slab_bytes) / stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   p.stages = stages;
@@ -929,17 +978,18 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   else if (p.act == RYOLO_ACT_MISH) which = 3;
   else if (p.act == RYOLO_ACT_SWISH) which = 4;
   else which = 5;
-  static const KernelFn all[12] = {
-      conv_fwd_kernel<EPI_HEAD, 0, false>, conv_fwd_kernel<EPI_RAW, 0, false>,
-      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY, false>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH, false>,
-      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH, false>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR, false>,
-      conv_fwd_kernel<EPI_HEAD, 0, true>, conv_fwd_kernel<EPI_RAW, 0, true>,
-      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LEAKY, true>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_MISH, true>,
-      conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_SWISH, true>, conv_fwd_kernel<EPI_AFFINE, RYOLO_ACT_LINEAR, true>};
-  const KernelFn fn = all[which + (p.dbg ? 6 : 0)];
+  // [epilogue kind][K blocks per stage - 1 | 3 = the timing-experiment build (one block per stage)]
+#define RY_CONV_ROW(E, A) \
+  { conv_fwd_kernel<E, A, false, 1>, conv_fwd_kernel<E, A, false, 2>, conv_fwd_kernel<E, A, false, 3>, conv_fwd_kernel<E, A, true, 1> }
+  static const KernelFn all[6][4] = {RY_CONV_ROW(EPI_HEAD, 0), RY_CONV_ROW(EPI_RAW, 0), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LEAKY),
+                                     RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_MISH), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_SWISH),
+                                     RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LINEAR)};
+#undef RY_CONV_ROW
+  const KernelFn fn = all[which][p.dbg ? 3 : p.kgrp - 1];
   static bool configured = false;
   if (!configured) {
-    for (KernelFn k : all) {
+    for (int i = 0; i < 24; i++) {
+      const KernelFn k = all[i / 4][i % 4];
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
       if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     }
