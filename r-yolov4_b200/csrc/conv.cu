@@ -257,7 +257,9 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                  bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + kMaxAcc]),
                  bar_afull = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc]),
                  bar_aempty = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc + 4]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role loops' state in uniform
+  // registers and drops the per-stage R2UR / constant-bank reloads from the single-warp issue chains
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.ntaps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   __shared__ __align__(16) float s_aff[2 * 256];           // scale | shift of this CTA's n-tile (EPI_AFFINE / EPI_HEAD)

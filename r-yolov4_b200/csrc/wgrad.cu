@@ -152,7 +152,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const uint32_t bar_bfull = smem_u32(&bars[0]), bar_bempty = smem_u32(&bars[kMaxBStages]),
                  bar_afull = smem_u32(&bars[2 * kMaxBStages]), bar_aempty = smem_u32(&bars[2 * kMaxBStages + kMaxASlots]),
                  bar_acc = smem_u32(&bars[2 * kMaxBStages + 2 * kMaxASlots]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so the role loops keep their state in uniform registers (csrc/conv.cu)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   // split-K shares are proportional to the taps a group carries (a 9-tap layer with tg = 8 has groups of 8 and 1 taps)
   const int pr = blockIdx.x % p.ks_total;
@@ -387,7 +388,7 @@ conv_wgrad_t_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_consta
                  bar_bfull = smem_u32(&bars[2 * kRawSlots + 2 * kTaSlots]),
                  bar_bempty = smem_u32(&bars[2 * kRawSlots + 2 * kTaSlots + kTbStages]),
                  bar_acc = smem_u32(&bars[2 * kRawSlots + 2 * kTaSlots + 2 * kTbStages]);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform (see above)
 
   const int pr = blockIdx.x % p.ks_total;
   const int pair = blockIdx.x / p.ks_total;
