@@ -82,6 +82,22 @@ __device__ __forceinline__ void tma_reduce_add_4d(const CUtensorMap* map, uint32
   asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
+// Cluster-pair variants (PAIR kernels): one TMA load lands in the same smem offset of every CTA in `mask` and completes
+// bytes on each CTA's own barrier at the same offset; one commit arrives on the same barrier offset of every CTA in `mask`.
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -139,6 +155,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -200,6 +220,7 @@ struct ConvKernelParams {
   int ntaps, Ktap;                 // taps of this launch; K elements per tap in the weight matrix
   int kbk;                         // K elements per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
   int kgrp;                        // K blocks per ring stage (one full / empty barrier hand-shake and one commit per stage)
+  int pair;                        // 1: clusters of two CTAs share every weight tile (each loads half, multicast to both)
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
   int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads, 16 no cross-CTA statistics tail, 32 no weight loads
@@ -234,7 +255,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   EPI_HEAD    y = acc*scale + shift -> fp32 [B, na, gs, gs, ch]
 enum { EPI_RAW = 0, EPI_AFFINE = 1, EPI_HEAD = 2 };
 
-template <int EPI, int ACT, bool DBG, int KG>
+template <int EPI, int ACT, bool DBG, int KG, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
@@ -262,6 +283,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KB = p.ntaps * p.kb_per_tap;
   const int total_tiles = p.N * p.tiles_h * p.tiles_w * p.n_tiles;
+  // Tile walk.  Plain: CTA b takes tiles b, b + grid, ... (n-tile fastest).  PAIR (clusters of two CTAs): the pair takes
+  // (n-tile, m-tile pair) items and rank r works on m-tile 2*mp + r, so both CTAs need the SAME weight tile at the same
+  // time: each loads half of it and multicasts it to both (the L2 -> SM weight traffic of the pair halves).  An odd tile
+  // count leaves rank 1 a ghost tile past the last image: TMA zero-fills its loads and clips its stores.
+  const int rank = PAIR ? (int)cluster_ctarank() : 0;
+  const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int ntile = PAIR ? p.n_tiles * ((p.N * p.tiles_h * p.tiles_w + 1) >> 1) : total_tiles;
   __shared__ __align__(16) float s_aff[2 * 256];           // scale | shift of this CTA's n-tile (EPI_AFFINE / EPI_HEAD)
   __shared__ float s_tr[8 * 32 * 17];                      // per-warp 32x16-word transpose tile (BN statistics, head stores)
   __shared__ int s_last;
@@ -272,7 +301,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     if (p.epi_tma) prefetch_tmap(&tmO);
     for (int s = 0; s < STAGES; s++) {
       mbar_init(bar_full + 8 * s, 1);
-      mbar_init(bar_empty + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1);    // PAIR: a slot is free once BOTH CTAs' MMAs have read it (the peer writes half of it)
     }
     for (int b = 0; b < p.nacc; b++) {
       mbar_init(bar_acc_full + 8 * b, 1);
@@ -291,6 +320,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (threadIdx.x == 0) ry_pdl_trigger();       // every CTA is resident from the start: the next kernel may queue up now
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // the peer's barriers exist before anything arrives on them
   tc_fence_after();
   ry_pdl_wait();                                // nothing above touches global memory
   const uint32_t tmem_base = tmem_slot;
@@ -305,12 +335,14 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // every CTA walks the K blocks in its own rotation: otherwise all 148 CTAs request the SAME weight tile from the same
     // L2 lines at the same time (the sum is order-independent up to fp32 rounding, and the tile -> CTA map is static, so
     // results stay reproducible)
-    const int krot = (int)((blockIdx.x * 5u) % (unsigned)KS) * G;
+    const int krot = (int)(((unsigned)tile0 * 5u) % (unsigned)KS) * G;
+    const uint32_t b_half = PAIR ? (uint32_t)rank * (kBBytes >> 1) : 0u;      // PAIR: this CTA loads rows [rank*BN/2, +BN/2) of the weight tile
     int s = 0;
     uint32_t phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+    for (int t = tile0; t < ntile; t += tstep) {
       const int nt = t % p.n_tiles;
       int mt = t / p.n_tiles;
+      if (PAIR) mt = 2 * mt + rank;
       const int pw = mt % p.tiles_w; mt /= p.tiles_w;
       const int ph = mt % p.tiles_h;
       const int img = mt / p.tiles_h;
@@ -326,7 +358,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int g = 0; g < G; g++) {
             if (!(dbg & 8))
               tma_load_4d(da, &tmA, bar_full + 8 * s, c * p.kbk, ws + p.tap_dw[tp], hs + p.tap_dh[tp], img);
-            if (!(dbg & 32))                    // dbg 32 (timing experiment, wrong results): no weight loads
+            if (PAIR)
+              tma_load_2d_mc(db + b_half, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk,
+                             n0 + rank * (BN >> 1), (uint16_t)3);
+            else if (!(dbg & 32))               // dbg 32 (timing experiment, wrong results): no weight loads
               tma_load_2d(db, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk, n0);
             da += kABytes; db += kBBytes;
             if (++c == p.kb_per_tap) { c = 0; if (++tp == p.ntaps) tp = 0; }
@@ -400,7 +435,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int KS = KB / G;
     int s = 0;
     uint32_t phase = 0, it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, it++) {
+    for (int t = tile0; t < ntile; t += tstep, it++) {
       const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
       mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
       tc_fence_after();
@@ -428,7 +463,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
               }
             }
           }
-          umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
+          if (PAIR) umma_commit_mc(bar_empty + 8 * s, (uint16_t)3);   // one arrival on this slot's barrier in both CTAs
+          else umma_commit(bar_empty + 8 * s);     // frees the smem slot once these MMAs have read it
           if (ks == KS - 1) umma_commit(bar_acc_full + 8 * buf);  // accumulator complete
         }
         __syncwarp();
@@ -505,7 +541,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const uint32_t eg = (uint32_t)(warp - 2) >> 2;   // epilogue group 0|1 owns TMEM accumulator 0|1 (tiles it%2 == eg)
     if (EPI != EPI_RAW) {
       // every tile of this CTA has the same n-tile when n_tiles divides gridDim.x (host guarantees it)
-      const int n0c = (blockIdx.x % p.n_tiles) * BN;
+      const int n0c = (tile0 % p.n_tiles) * BN;
       for (int i = et; i < BN; i += 256) {
         const int c = n0c + i;
         s_aff[i] = (p.scale && c < p.Cout) ? p.scale[c] : 1.f;
@@ -522,14 +558,15 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     for (int i = 0; i < 8; i++) { st_s[i] = 0.f; st_q[i] = 0.f; }
     float* tw = s_tr + (warp - 2) * (32 * 17);
     uint32_t it = eg;
-    for (int t = blockIdx.x + (int)eg * (int)gridDim.x; t < total_tiles; t += 2 * gridDim.x, it += 2) {
+    for (int t = tile0 + (int)eg * tstep; t < ntile; t += 2 * tstep, it += 2) {
       const int nt = t % p.n_tiles;
       int mt = t / p.n_tiles;
+      if (PAIR) mt = 2 * mt + rank;
       const int pw = mt % p.tiles_w; mt /= p.tiles_w;
       const int ph = mt % p.tiles_h;
       const int img = mt / p.tiles_h;
       const int ho = ph * p.TH + hl, wo = pw * p.TW + wl, n0 = nt * BN;
-      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo) && !(dbg & 1);
+      const bool row_ok = (r < p.TH * p.TW) && (ho < p.Ho) && (wo < p.Wo) && (!PAIR || img < p.N) && !(dbg & 1);
       const long long pix = ((long long)img * p.OutH + ho * p.out_s + p.out_oh) * p.OutW + wo * p.out_s + p.out_ow;
       const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;   // nacc is even: tiles of one parity
       mbar_wait(bar_acc_full + 8 * buf, aphase);
@@ -680,7 +717,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // Deterministic reduction (the reference runs with cudnn.deterministic, train.py:24): the 8 epilogue warps
       // combine through smem in a fixed order; across CTAs the sums are fixed-point (see below); the last CTA to
       // arrive turns the totals into scale/shift + running statistics.
-      const int n0c = (blockIdx.x % p.n_tiles) * BN;
+      const int n0c = (tile0 % p.n_tiles) * BN;
       float* comb = s_tr;                                  // reused as [8 warps][2][256]
       asm volatile("bar.sync 1, 256;" ::: "memory");       // every warp is done with its transpose tile
 #pragma unroll
@@ -743,6 +780,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (p.epi_tma && warp >= 2 && ((warp - 2) & 3) == 0 && lane == 0) bulk_wait0();   // stores complete before exit
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();                 // no CTA leaves while its peer may still arrive on its barriers
   if (warp == 1) tmem_dealloc(tmem_base, p.tmem_cols);
 }
 
@@ -945,7 +983,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   // three taps per stage take them from 0.47 to 0.35 ms (forward and dgrad alike), the stride-2 dgrad classes of the
   // 32 -> 64 layer gain 9 %.  Wider tiles lose: a 64 KB stage leaves N = 128 layers a ring of two (+12 %).
   p.kgrp = 1;
-  if (!p.halo && !p.dbg) {
+  if (!p.halo && !p.dbg && !p.pair) {
     const int knob_g = ryolo_knob(RYOLO_KNOB_KGRP);
     const size_t limit = knob_g == 1 ? 40 * 1024 : knob_g == 2 ? 64 * 1024 : knob_g >= 3 ? 72 * 1024 : 0;
     const size_t min_ring = knob_g == 1 ? 3 : 2;
@@ -980,18 +1018,19 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   else if (p.act == RYOLO_ACT_MISH) which = 3;
   else if (p.act == RYOLO_ACT_SWISH) which = 4;
   else which = 5;
-  // [epilogue kind][K blocks per stage - 1 | 3 = the timing-experiment build (one block per stage)]
-#define RY_CONV_ROW(E, A) \
-  { conv_fwd_kernel<E, A, false, 1>, conv_fwd_kernel<E, A, false, 2>, conv_fwd_kernel<E, A, false, 3>, conv_fwd_kernel<E, A, true, 1> }
-  static const KernelFn all[6][4] = {RY_CONV_ROW(EPI_HEAD, 0), RY_CONV_ROW(EPI_RAW, 0), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LEAKY),
+  // [epilogue kind][K blocks per stage - 1 | 3 = the timing-experiment build (one block per stage) | 4 = cluster pairs]
+#define RY_CONV_ROW(E, A)                                                                                              \
+  { conv_fwd_kernel<E, A, false, 1, false>, conv_fwd_kernel<E, A, false, 2, false>, conv_fwd_kernel<E, A, false, 3, false>, \
+    conv_fwd_kernel<E, A, true, 1, false>, conv_fwd_kernel<E, A, false, 1, true> }
+  static const KernelFn all[6][5] = {RY_CONV_ROW(EPI_HEAD, 0), RY_CONV_ROW(EPI_RAW, 0), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LEAKY),
                                      RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_MISH), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_SWISH),
                                      RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LINEAR)};
 #undef RY_CONV_ROW
-  const KernelFn fn = all[which][p.dbg ? 3 : p.kgrp - 1];
+  const KernelFn fn = all[which][p.pair ? 4 : p.dbg ? 3 : p.kgrp - 1];
   static bool configured = false;
   if (!configured) {
-    for (int i = 0; i < 24; i++) {
-      const KernelFn k = all[i / 4][i % 4];
+    for (int i = 0; i < 30; i++) {
+      const KernelFn k = all[i / 5][i % 5];
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
       if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     }
@@ -1000,6 +1039,39 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   const long long tiles = (long long)p.N * p.tiles_h * p.tiles_w * p.n_tiles;
   RY_CHECK_ARG(tiles > 0 && tiles < (1ll << 31), "conv: tile count out of range");
   RY_CHECK_ARG(p.n_tiles <= sm_count(), "conv: too many output-channel tiles");
+  if (p.pair) {
+    // clusters of two: as many pairs as can be resident at once (a multiple of n_tiles, so that a pair keeps its n-tile)
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static int max_pairs[6] = {0, 0, 0, 0, 0, 0};
+    if (!max_pairs[which]) {
+      cfg.gridDim = dim3(sm_count() & ~1);
+      int n = 0;
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&n, fn, &cfg);
+      if (e != cudaSuccess || n <= 0) { cudaGetLastError(); n = sm_count() / 2 - 4; }
+      max_pairs[which] = n < sm_count() / 2 ? n : sm_count() / 2;
+    }
+    const long long pair_items = (long long)p.n_tiles * (((long long)p.N * p.tiles_h * p.tiles_w + 1) / 2);
+    int pairs = max_pairs[which];
+    pairs -= pairs % p.n_tiles;
+    if (pair_items < pairs) pairs = (int)pair_items;
+    RY_CHECK_ARG(pairs > 0, "conv: no room for a cluster pair");
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.numAttrs = ryolo_knob(RYOLO_KNOB_PDL) ? 2 : 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, fn, tmA, tmB, tmO, p);
+    if (le != cudaSuccess) { ryolo_set_error(cudaGetErrorString(le)); return RYOLO_ERR_CUDA; }
+    RY_CHECK_LAUNCH();
+    return RYOLO_OK;
+  }
   int grid = sm_count();
   grid -= grid % p.n_tiles;                          // a CTA always sees the same n-tile
   if (tiles < grid) grid = (int)tiles;               // tiles is a multiple of n_tiles, so this keeps the property
@@ -1028,6 +1100,19 @@ int encode_and_launch(const void* x, int N, int H, int W, int C, long long cpitc
   if (!enc) { ryolo_set_error("cuTensorMapEncodeTiled not available from the driver"); return RYOLO_ERR_CUDA; }
   CUtensorMap tmA, tmB;
   {
+    // knob pair: 0 = off, otherwise the narrowest output-channel tile that runs as cluster pairs (weight tile multicast;
+    // default 256).  Deep N = 256 layers are bound by L2 -> SM operand traffic (48 KB per K block; without operand loads
+    // they run at the burst MMA rate, profiles/r02_knockout_uniform.txt): sharing the weight tile takes the K >= 2304
+    // layers down 3-8 % (profiles/r02_pair_ab.txt).  Shorter K loops lose (the two CTAs release every ring slot
+    // together, and with the store slab the ring is three deep), so they stay unpaired.
+    const int kp = ryolo_knob(RYOLO_KNOB_PAIR);              // + 1024: also layers too small to gain (parity tests)
+    const int min_bn = kp & 1023;
+    const bool any_size = (kp & 1024) != 0;
+    const long long mtiles = (long long)p.N * p.tiles_h * p.tiles_w;
+    p.pair = (min_bn > 0 && !p.halo && !ryolo_knob(RYOLO_KNOB_DBG) && p.BN >= min_bn && p.BN % 16 == 0 && p.kbk == kBK &&
+              mtiles >= 2 && (any_size || (mtiles * ((p.Cout + p.BN - 1) / p.BN) >= 2 * (long long)sm_count() && p.ntaps * p.kb_per_tap >= 36))) ? 1 : 0;
+  }
+  {
     cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
     cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * W, (cuuint64_t)cpitch * 2 * W * H};
     cuuint32_t box[4] = {(cuuint32_t)p.kbk, (cuuint32_t)(p.halo ? p.TW + 2 : p.TW * estride),
@@ -1042,7 +1127,7 @@ int encode_and_launch(const void* x, int N, int H, int W, int C, long long cpitc
   {
     cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)wrows};
     cuuint64_t strides[1] = {(cuuint64_t)Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.kbk, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {(cuuint32_t)p.kbk, (cuuint32_t)(p.pair ? p.BN / 2 : p.BN)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, p.kbk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,

@@ -48,11 +48,14 @@ int ryolo_abi_version(void) { return 1; }
 //   kgrp      conv: K blocks per operand-ring stage (one barrier hand-shake and one commit per stage): 0 = one,
 //             1 (default) = up to three for N <= 32 tiles (stages <= 40 KB, ring >= 3), 2 = any tile, <= 64 KB / ring
 //             >= 2, 3 = <= 72 KB (see csrc/conv.cu launch(): only the narrow tiles gain)
+//   pair      conv: 0 = off, n (default 256) = output-channel tiles of >= n columns with K >= 2304 run as clusters of two
+//             CTAs that share every weight tile (each loads half of it, TMA multicast to both; csrc/conv.cu PAIR kernels);
+//             + 1024 = also short K loops and small layers (parity tests)
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0, 8, 0, 1};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0, 8, 0, 1, 256};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

@@ -24,7 +24,7 @@ step = R.TrainStep(m, crit)
 img = torch.rand(bs, 3, S, S, device="cuda")
 tg = make_targets(0, bs, 2).cuda()
 flat0 = step.flat.clone()
-KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp"]
+KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair"]
 BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the library's defaults
 VARIANTS = [
     ("base", {}),
@@ -57,6 +57,10 @@ VARIANTS = [
     ("halo", dict(halo=1)),
     ("k32_n128", dict(sw64=2)),
     ("k32_all", dict(sw64=3)),
+    ("pair0", dict(pair=0)),
+    ("pair256", dict(pair=256)),
+    ("pair128", dict(pair=128)),
+    ("pair64", dict(pair=64)),
     ("kgrp0", dict(kgrp=0)),
     ("kgrp1", dict(kgrp=1)),
     ("kgrp2", dict(kgrp=2)),
