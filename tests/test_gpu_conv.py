@@ -54,6 +54,37 @@ def test_conv_raw(shape, epi):
     assert (got - got_chk).abs().max() <= 1.5e-2 * ref.abs().max()
 
 
+@pytest.mark.parametrize("shape", SHAPES + [(5, 25, 25, 256, 512, 3, 1), (3, 20, 24, 128, 96, 1, 1)])
+def test_conv_operand_ring_variants(shape, issue):
+    """Cluster pairs (odd tile counts leave rank 1 a ghost tile), grouped K blocks and the plain ring against the
+    CUDA-core checker: raw output, affine + activation + residual epilogue, and an accumulating dgrad."""
+    from ryolo_b200 import ops
+    N, H, W, Cin, Cout, k, s = shape
+    gen = torch.Generator().manual_seed(sum(shape) + 1)
+    x, w = _mk(gen, N, H, W, Cin, Cout, k)
+    xa, wp = ops.Act(x.cuda()), ops.pack_weights(w.cuda())
+    got = ops.conv2d(xa, wp, Cout, k, s).torch().float().cpu()
+    chk = ops.conv2d(xa, wp, Cout, k, s, reference=True).torch().float().cpu()
+    ref = _ref_conv(x, w, s)
+    assert (chk - ref).abs().max() < 2e-2 * ref.abs().max()
+    assert (got - chk).abs().max() <= 1.5e-2 * ref.abs().max()
+    Ho, Wo = got.shape[1], got.shape[2]
+    scale, shift = (torch.rand(Cout, generator=gen) + 0.5).cuda(), torch.randn(Cout, generator=gen).cuda()
+    res = ops.Act(torch.randn(N, Ho, Wo, Cout, generator=gen).bfloat16().cuda())
+    kw = dict(scale=scale, shift=shift, act="mish", residual=res)
+    got2 = ops.conv2d(xa, wp, Cout, k, s, **kw).torch().float().cpu()
+    chk2 = ops.conv2d(xa, wp, Cout, k, s, reference=True, **kw).torch().float().cpu()
+    assert (got2 - chk2).abs().max() <= 2e-2 * chk2.abs().max()
+    # dgrad (the same kernel with mirrored taps), accumulating into a pre-filled gradient
+    dy = torch.randn(N, Ho, Wo, Cout, generator=gen).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    F.conv2d(xr, w.bfloat16().float(), None, s, (k - 1) // 2).backward(dy.float().permute(0, 3, 1, 2))
+    dx_ref = xr.grad.permute(0, 2, 3, 1)
+    dx = ops.Act(torch.full((N, H, W, Cin), 1.0).bfloat16().cuda())
+    ops.conv2d_dgrad(ops.Act(dy.cuda()), ops.pack_weights(w.cuda(), transpose=True), Cin, k, s, dx, accumulate=True)
+    assert (dx.torch().float().cpu() - 1.0 - dx_ref).abs().max() < 2e-2 * dx_ref.abs().max() + 2e-2
+
+
 @pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
 def test_conv_epilogue_scale_shift_act_residual_concat_slice(act, epi):
     from ryolo_b200 import ops
