@@ -221,6 +221,7 @@ struct ConvKernelParams {
   int kbk;                         // K elements per K block: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
   int kgrp;                        // K blocks per ring stage (one full / empty barrier hand-shake and one commit per stage)
   int pair;                        // 1: clusters of two CTAs share every weight tile (each loads half, multicast to both)
+  int wres;                        // 1: the whole weight matrix is loaded once per CTA and stays in shared memory (WRES kernels)
   signed char tap_dh[9], tap_dw[9]; // input offset of each tap (rows / cols, input-lattice units)
   unsigned char tap_k[9];          // weight K-block index of each tap
   int dbg;                         // RYOLO_DBG timing experiments (wrong results): 1 no stores, 2 no BN statistics, 4 no MMAs, 8 no A loads, 16 no cross-CTA statistics tail, 32 no weight loads
@@ -255,7 +256,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 //   EPI_HEAD    y = acc*scale + shift -> fp32 [B, na, gs, gs, ch]
 enum { EPI_RAW = 0, EPI_AFFINE = 1, EPI_HEAD = 2 };
 
-template <int EPI, int ACT, bool DBG, int KG, bool PAIR>
+template <int EPI, int ACT, bool DBG, int KG, bool PAIR, bool WRES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                 const __grid_constant__ CUtensorMap tmO, const ConvKernelParams p) {
@@ -271,13 +272,17 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
                                                                      // are single-warp serial chains, every instruction in them counts)
   const uint32_t stA = (uint32_t)G * kABytes, stB = (uint32_t)G * kBBytes;
   const uint32_t sB = smem_base + (p.halo ? (uint32_t)p.a_slots * p.a_slot_bytes : (uint32_t)STAGES * stA);
-  const uint32_t sStage = sB + (uint32_t)STAGES * stB;   // epi_tma: one 128-row x 64-channel bf16 slab per epilogue group
-  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kMaxAcc + 8];
+  // WRES: the layer's whole weight matrix (one n-tile, <= 96 KB) stays resident after sB for the life of the CTA, K block
+  // (tap, cb) at sB + (tap*kb_per_tap + cb)*kBBytes; the ring then carries activation boxes only.
+  const uint32_t sStage = sB + (WRES ? (uint32_t)(p.ntaps * p.kb_per_tap) * kBBytes
+                                     : (uint32_t)STAGES * stB);   // epi_tma: one 128-row x 64-channel bf16 slab per epilogue group
+  __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 2 * kMaxAcc + 9];
   __shared__ uint32_t tmem_slot;
   const uint32_t bar_full = smem_u32(&bars[0]), bar_empty = smem_u32(&bars[kMaxStages]),
                  bar_acc_full = smem_u32(&bars[2 * kMaxStages]), bar_acc_empty = smem_u32(&bars[2 * kMaxStages + kMaxAcc]),
                  bar_afull = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc]),
-                 bar_aempty = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc + 4]);
+                 bar_aempty = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc + 4]),
+                 bar_w = smem_u32(&bars[2 * kMaxStages + 2 * kMaxAcc + 8]);      // WRES: resident weights have landed
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role loops' state in uniform
   // registers and drops the per-stage R2UR / constant-bank reloads from the single-warp issue chains
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -311,6 +316,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       mbar_init(bar_afull + 8 * b, 1);
       mbar_init(bar_aempty + 8 * b, 1);
     }
+    mbar_init(bar_w, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -328,7 +334,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && !p.halo) {
     // ================================ TMA producer (warp-uniform loop, one elected lane issues) ===============
     const uint32_t a_bytes = (uint32_t)(p.TH * p.TW) * (uint32_t)p.kbk * 2;
-    const uint32_t tx_bytes = (((dbg & 8) ? 0u : a_bytes) + ((dbg & 32) ? 0u : kBBytes)) * (uint32_t)G;
+    const uint32_t tx_bytes = (((dbg & 8) ? 0u : a_bytes) + ((WRES || (dbg & 32)) ? 0u : kBBytes)) * (uint32_t)G;
     // A stage carries G consecutive K blocks behind ONE full / empty barrier pair: the issue loops pay their fixed cost
     // (barrier wait, fence, elect, commit: ~0.2 us whatever the stage carries) once per G blocks.
     const int KS = KB / G;
@@ -337,6 +343,16 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // results stay reproducible)
     const int krot = (int)(((unsigned)tile0 * 5u) % (unsigned)KS) * G;
     const uint32_t b_half = PAIR ? (uint32_t)rank * (kBBytes >> 1) : 0u;      // PAIR: this CTA loads rows [rank*BN/2, +BN/2) of the weight tile
+    if (WRES && tile0 < ntile) {
+      if (elect_one()) {
+        mbar_expect_tx(bar_w, (uint32_t)KB * kBBytes);
+        int kb = 0;
+        for (int tp = 0; tp < p.ntaps; tp++)
+          for (int c = 0; c < p.kb_per_tap; c++, kb++)
+            tma_load_2d(sB + (uint32_t)kb * kBBytes, &tmB, bar_w, (int)p.tap_k[tp] * p.Ktap + c * p.kbk, 0);
+      }
+      __syncwarp();
+    }
     int s = 0;
     uint32_t phase = 0;
     for (int t = tile0; t < ntile; t += tstep) {
@@ -358,7 +374,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int g = 0; g < G; g++) {
             if (!(dbg & 8))
               tma_load_4d(da, &tmA, bar_full + 8 * s, c * p.kbk, ws + p.tap_dw[tp], hs + p.tap_dh[tp], img);
-            if (PAIR)
+            if (WRES) {
+            } else if (PAIR)
               tma_load_2d_mc(db + b_half, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk,
                              n0 + rank * (BN >> 1), (uint16_t)3);
             else if (!(dbg & 32))               // dbg 32 (timing experiment, wrong results): no weight loads
@@ -435,6 +452,10 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const int KS = KB / G;
     int s = 0;
     uint32_t phase = 0, it = 0;
+    // WRES: the weights are addressed by K block, walked in the producer's rotation (groups never straddle the wrap:
+    // G divides KB and the rotation is a multiple of G)
+    int kbw = WRES ? (int)(((unsigned)tile0 * 5u) % (unsigned)KS) * G : 0;
+    if (WRES && tile0 < ntile) mbar_wait(bar_w, 0);
     for (int t = tile0; t < ntile; t += tstep, it++) {
       const uint32_t buf = it % (uint32_t)p.nacc, aphase = (it / (uint32_t)p.nacc) & 1u;
       mbar_wait(bar_acc_empty + 8 * buf, aphase ^ 1u);       // epilogue has drained this accumulator
@@ -444,7 +465,8 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         mbar_wait(bar_full + 8 * s, phase);
         tc_fence_after();
         if (elect_one()) {
-          uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * a_step), bd = bdesc0 + (uint64_t)((uint32_t)s * b_step);
+          uint64_t ad = adesc0 + (uint64_t)((uint32_t)s * a_step),
+                   bd = bdesc0 + (uint64_t)(WRES ? (uint32_t)kbw * b_blk : (uint32_t)s * b_step);
           if (!(dbg & 4)) {
             umma_bf16(d_tmem, ad, bd, idesc, ks ? 1u : 0u);
             umma_bf16(d_tmem, ad + 2, bd + 2, idesc, 1u);
@@ -469,6 +491,7 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         }
         __syncwarp();
         if (++s == STAGES) { s = 0; phase ^= 1u; }
+        if (WRES) { kbw += G; if (kbw == KB) kbw = 0; }
       }
     }
   } else if (warp == 1) {
@@ -975,6 +998,25 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
     fixed = (size_t)p.a_slots * p.a_slot_bytes;
     stage_bytes = (size_t)p.BN * kBK * 2;
   }
+  // Resident weights (knob wres = largest weight matrix in KB that stays in shared memory, default 96; 0 = off; + 1024 =
+  // also layers with few tiles per CTA): a layer with ONE n-tile whose K blocks all fit loads them once per CTA; the ring
+  // then carries activation boxes only, which halves the TMA issues of the narrow layers (their 2-8 KB weight boxes cost
+  // a full issue + barrier transaction each).  Measured per layer (profiles/r02_wres_ab.txt): stem 0.83 -> 0.68 ms,
+  // 3x3 s2 32->64 @400x400 0.61 -> 0.46, the 1x1 32/64-channel layers on 400x400 maps -15..-28 %, forward and dgrad alike.
+  // Layers with ~17 tiles per CTA (100x100 maps) lose up to 10 %: the first MMA waits for the whole matrix, so the
+  // mode needs >= 32 tiles per CTA to pay for its start.
+  p.wres = 0;
+  {
+    const size_t wbytes = (size_t)p.ntaps * p.kb_per_tap * p.BN * p.kbk * 2;
+    const int kw = ryolo_knob(RYOLO_KNOB_WRES);
+    const long long mtiles = (long long)p.N * p.tiles_h * p.tiles_w;
+    if ((kw & 1023) > 0 && !p.halo && !p.pair && !p.dbg && p.n_tiles == 1 && wbytes <= (size_t)(kw & 1023) * 1024 &&
+        ((kw & 1024) || mtiles >= 32ll * sm_count())) {
+      p.wres = 1;
+      fixed = wbytes;
+      stage_bytes = (size_t)kBM * p.kbk * 2;
+    }
+  }
   const size_t slab_bytes = p.epi_tma ? 2 * 16384 : 0;      // one slab per epilogue group, after the ring
   // K blocks per stage (knob kgrp: 0 = always one; 1 (default) = N <= 32 tiles only, stages of up to 40 KB with a ring of
   // >= 3; 2 = any tile, up to 64 KB with a ring of >= 2; 3 = up to 72 KB): the largest divisor (<= 3) of the tile's K-block
@@ -991,7 +1033,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
     for (int g = 2; g <= 3; g++) {
       if (KB % g) continue;
       if (knob_g == 1 && p.BN > 32) continue;
-      if (g * stage_bytes <= limit && (kSmemBudget - 1024 - slab_bytes) / (g * stage_bytes) >= min_ring) p.kgrp = g;
+      if (g * stage_bytes <= limit && (kSmemBudget - 1024 - fixed - slab_bytes) / (g * stage_bytes) >= min_ring) p.kgrp = g;
     }
     stage_bytes *= (size_t)p.kgrp;
   }
@@ -1018,19 +1060,22 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, ConvKernelParams& p, 
   else if (p.act == RYOLO_ACT_MISH) which = 3;
   else if (p.act == RYOLO_ACT_SWISH) which = 4;
   else which = 5;
-  // [epilogue kind][K blocks per stage - 1 | 3 = the timing-experiment build (one block per stage) | 4 = cluster pairs]
-#define RY_CONV_ROW(E, A)                                                                                              \
-  { conv_fwd_kernel<E, A, false, 1, false>, conv_fwd_kernel<E, A, false, 2, false>, conv_fwd_kernel<E, A, false, 3, false>, \
-    conv_fwd_kernel<E, A, true, 1, false>, conv_fwd_kernel<E, A, false, 1, true> }
-  static const KernelFn all[6][5] = {RY_CONV_ROW(EPI_HEAD, 0), RY_CONV_ROW(EPI_RAW, 0), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LEAKY),
+  // [epilogue kind][K blocks per stage - 1 | 3 = the timing-experiment build (one block per stage) | 4 = cluster pairs |
+  //                  5..7 = resident weights with 1..3 K blocks per stage]
+#define RY_CONV_ROW(E, A)                                                                                                  \
+  { conv_fwd_kernel<E, A, false, 1, false, false>, conv_fwd_kernel<E, A, false, 2, false, false>,                          \
+    conv_fwd_kernel<E, A, false, 3, false, false>, conv_fwd_kernel<E, A, true, 1, false, false>,                           \
+    conv_fwd_kernel<E, A, false, 1, true, false>, conv_fwd_kernel<E, A, false, 1, false, true>,                            \
+    conv_fwd_kernel<E, A, false, 2, false, true>, conv_fwd_kernel<E, A, false, 3, false, true> }
+  static const KernelFn all[6][8] = {RY_CONV_ROW(EPI_HEAD, 0), RY_CONV_ROW(EPI_RAW, 0), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LEAKY),
                                      RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_MISH), RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_SWISH),
                                      RY_CONV_ROW(EPI_AFFINE, RYOLO_ACT_LINEAR)};
 #undef RY_CONV_ROW
-  const KernelFn fn = all[which][p.pair ? 4 : p.dbg ? 3 : p.kgrp - 1];
+  const KernelFn fn = all[which][p.pair ? 4 : p.dbg ? 3 : p.wres ? 4 + p.kgrp : p.kgrp - 1];
   static bool configured = false;
   if (!configured) {
-    for (int i = 0; i < 30; i++) {
-      const KernelFn k = all[i / 5][i % 5];
+    for (int i = 0; i < 48; i++) {
+      const KernelFn k = all[i / 8][i % 8];
       cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
       if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
     }

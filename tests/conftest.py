@@ -29,15 +29,16 @@ def epi(request):
     L.tune(epi_tma=old[0], epi_maxbn=old[1])
 
 
-@pytest.fixture(params=["pair_any", "kgrp_wide", "plain"])
+@pytest.fixture(params=["pair_any", "kgrp_wide", "plain", "wres"])
 def issue(request):
     """Runs a conv test under each operand-ring variant of the conv kernel (library knobs pair / kgrp): cluster pairs
     with weight-tile multicast forced on every eligible layer, up to three K blocks per ring stage on any tile width,
-    and one K block per stage without pairing."""
+    one K block per stage without pairing, and weight matrices of up to 128 KB resident in shared memory."""
     from ryolo_b200 import _lib as L
     names = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc",
-             "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair"]
-    old = (L.lib().ryolo_knob(names.index("kgrp")), L.lib().ryolo_knob(names.index("pair")))
-    L.tune(**{"pair_any": dict(pair=1024 + 32, kgrp=0), "kgrp_wide": dict(pair=0, kgrp=3), "plain": dict(pair=0, kgrp=0)}[request.param])
+             "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres"]
+    old = [L.lib().ryolo_knob(names.index(k)) for k in ("kgrp", "pair", "wres")]
+    L.tune(**{"pair_any": dict(pair=1024 + 32, kgrp=0, wres=0), "kgrp_wide": dict(pair=0, kgrp=3, wres=0),
+              "plain": dict(pair=0, kgrp=0, wres=0), "wres": dict(pair=0, kgrp=1, wres=1024 + 128)}[request.param])
     yield request.param
-    L.tune(kgrp=old[0], pair=old[1])
+    L.tune(kgrp=old[0], pair=old[1], wres=old[2])

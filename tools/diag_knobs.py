@@ -24,7 +24,7 @@ step = R.TrainStep(m, crit)
 img = torch.rand(bs, 3, S, S, device="cuda")
 tg = make_targets(0, bs, 2).cuda()
 flat0 = step.flat.clone()
-KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair"]
+KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres"]
 BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the library's defaults
 VARIANTS = [
     ("base", {}),
@@ -57,6 +57,10 @@ VARIANTS = [
     ("halo", dict(halo=1)),
     ("k32_n128", dict(sw64=2)),
     ("k32_all", dict(sw64=3)),
+    ("wres0", dict(wres=0)),
+    ("wres48", dict(wres=48)),
+    ("wres96", dict(wres=96)),
+    ("wres128", dict(wres=128)),
     ("pair0", dict(pair=0)),
     ("pair256", dict(pair=256)),
     ("pair128", dict(pair=128)),
