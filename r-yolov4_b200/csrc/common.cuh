@@ -12,7 +12,7 @@ extern "C" void ryolo_set_error(const char* msg);
 
 // process-wide tuning knobs (lib.cu); ids index ryolo_tune's keys
 enum { RYOLO_KNOB_HALO = 0, RYOLO_KNOB_DBG, RYOLO_KNOB_WG_SPLIT, RYOLO_KNOB_WG_DBG, RYOLO_KNOB_EPI_TMA,
-       RYOLO_KNOB_EPI_MAXBN, RYOLO_KNOB_WG_TAPGRP, RYOLO_KNOB_BN_BWD, RYOLO_KNOB_WG_TRANS, RYOLO_KNOB_SW64, RYOLO_KNOB_NACC, RYOLO_KNOB_PDL, RYOLO_KNOB_SSA, RYOLO_KNOB_WG_BOXES, RYOLO_KNOB_EW_REGS, RYOLO_KNOB_NMS_BAND, RYOLO_KNOB_BN_FUSE, RYOLO_KNOB_KGRP, RYOLO_KNOB_PAIR, RYOLO_KNOB_WRES, RYOLO_KNOB_COUNT };
+       RYOLO_KNOB_EPI_MAXBN, RYOLO_KNOB_WG_TAPGRP, RYOLO_KNOB_BN_BWD, RYOLO_KNOB_WG_TRANS, RYOLO_KNOB_SW64, RYOLO_KNOB_NACC, RYOLO_KNOB_PDL, RYOLO_KNOB_SSA, RYOLO_KNOB_WG_BOXES, RYOLO_KNOB_EW_REGS, RYOLO_KNOB_NMS_BAND, RYOLO_KNOB_BN_FUSE, RYOLO_KNOB_KGRP, RYOLO_KNOB_PAIR, RYOLO_KNOB_WRES, RYOLO_KNOB_WG_X32, RYOLO_KNOB_COUNT };
 extern "C" int ryolo_knob(int id);
 extern "C" int ry_sm_count(void);      // multiprocessors of the current device (cached)
 

@@ -54,11 +54,13 @@ int ryolo_abi_version(void) { return 1; }
 //   wres      conv: largest weight matrix (KB, default 96) that is loaded once per CTA and stays resident in shared memory
 //             (layers with one n-tile and >= 32 tiles per CTA; the ring then carries activation boxes only), 0 = off,
 //             + 1024 = also layers with few tiles per CTA (parity tests)
+//   wg_x32    wgrad: 1 (default) = the X boxes of Cin == 32 layers are 32 channels wide (SWIZZLE_64B MN-major atoms), 0 = 64-channel
+//             boxes overhanging the tensor
 //   epi_tma   conv bf16 epilogue: 0 per-thread 16-byte stores | 1 TMA slab stores | 2 (default) + TMA reduce-add for
 //             dgrad's accumulation;  epi_maxbn: widest tile that always takes the slab path (wider ones only with K <= 1152)
 static const char* const kKnobNames[RYOLO_KNOB_COUNT] = {"halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn",
-                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres"};
-static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0, 8, 0, 1, 256, 96};
+                                                          "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres", "wg_x32"};
+static const int kKnobDefaults[RYOLO_KNOB_COUNT] = {0, 0, 1, 0, 2, 128, 1, 3, 0, 1, 1, 1, 1, 14, 0, 8, 0, 1, 256, 96, 1};
 static int g_knobs[RYOLO_KNOB_COUNT];
 static bool g_knob_set[RYOLO_KNOB_COUNT];
 

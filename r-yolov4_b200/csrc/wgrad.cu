@@ -118,6 +118,13 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t 
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
          ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
+// MN-major SWIZZLE_64B: 32-element (64-byte) rows along MN, 8-row K groups 512 bytes apart.  Used for the X operand of
+// Cin == 32 layers: a 64-channel box over a 32-channel tensor overhangs it, and TMA serves overhanging rows on a ~2x
+// slower path (tools/oob_probe.py); a [pixels x 32 channels] box is one canonical SWIZZLE_64B MN-major atom column.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw64(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+         ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
 // D fp32, A/B bf16, both MN-major, M = 128, N = n
 __device__ __forceinline__ uint32_t umma_idesc_bf16_mn(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) |
@@ -128,7 +135,8 @@ struct WgradParams {
   int N, Ho, Wo, Cin, Cout;
   int TH, TW, tiles_h, tiles_w;
   int ksize, stride, pad, ntaps;
-  int nb, tg;                               // X boxes per item (N = 64*nb), taps per item
+  int nb, tg;                               // X boxes per item (N = xw*nb), taps per item
+  int xw;                                   // channels per X box: 64 (SWIZZLE_128B rows) or 32 (SWIZZLE_64B rows, Cin == 32)
   int tap_grp;                              // taps issued per MMA (tap_grp * 64 * nb <= 256)
   int n_co_tiles, n_ci_tiles, n_tap_groups;
   int ks_total;                             // CTAs per (Cout tile, Cin tile) pair = sum of the tap groups' split counts
@@ -165,8 +173,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int cit = pair % p.n_ci_tiles;
   const int cot = pair / p.n_ci_tiles;
   const int tap0 = tgi * p.tg, ntap = min(p.tg, p.ntaps - tap0);
-  const int co0 = cot * 128, ci0 = cit * 64 * p.nb;
-  const int CIT = 64 * p.nb;
+  const int co0 = cot * 128, ci0 = cit * p.xw * p.nb;
+  const int CIT = p.xw * p.nb;
   // smem partition of THIS CTA (in 16 KB boxes): [A ring: a_slots x a_boxes][zero box when a_boxes == 1][B ring].  A patch
   // costs a_boxes + ntap*nb boxes; a CTA whose tap group is short keeps more patches in flight (with two A slots a
   // one-tap item ran at two patches per memory round trip).
@@ -180,6 +188,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int n_patches = p.N * p.tiles_h * p.tiles_w;
   const int rows = p.TH * p.TW;
   const uint32_t box_bytes = (uint32_t)rows * 128u;
+  const uint32_t xrow = (uint32_t)p.xw * 2u;                       // bytes per pixel row of an X box (128 or 64)
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmG);
@@ -202,12 +211,16 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   {
     // rows the TMA boxes never write but the last K step reads must be zeros; so must the whole shared zero box
     uint8_t* base = smem_raw + (smem_base - smem_u32(smem_raw));
-    const int tail16 = (p.slot_rows - rows) * 8;                   // 16-byte words per box tail
-    if (rows < ((rows + 15) & ~15)) {
+    // (an X box with 64-byte rows occupies the first half of its slot: everything after its last row is cleared)
+    const int first_x = a_slots * p.a_boxes + zero_box;            // boxes [first_x, smem_boxes) are X boxes
+    const int tail16 = (int)((kBoxBytes - (uint32_t)rows * xrow) / 16u);   // 16-byte words after the last row of an X box (>= an A box's tail)
+    if (rows < ((rows + 15) & ~15) || p.xw != 64) {
       for (int i = threadIdx.x; i < p.smem_boxes * tail16; i += kThreads) {
         const int b = i / tail16, w = i - b * tail16;
-        *reinterpret_cast<uint4*>(base + (size_t)b * kBoxBytes + (size_t)rows * 128 + (size_t)w * 16) =
-            make_uint4(0, 0, 0, 0);
+        const uint32_t rb = b >= first_x ? xrow : 128u;
+        const uint32_t off = (uint32_t)rows * rb + (uint32_t)w * 16u;
+        if (off < kBoxBytes)
+          *reinterpret_cast<uint4*>(base + (size_t)b * kBoxBytes + off) = make_uint4(0, 0, 0, 0);
       }
     }
     if (zero_box) {
@@ -237,7 +250,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     // TMA producer: warp-uniform loop, one elected lane issues
     int s = 0, ab = 0;
     uint32_t bphase = 0, aphase = 0;
-    const uint32_t b_tx = (p.dbg & 2) ? 0u : (uint32_t)p.nb * box_bytes;
+    const uint32_t b_tx = (p.dbg & 2) ? 0u : (uint32_t)p.nb * (uint32_t)rows * xrow;
     for (int patch = split; patch < n_patches; patch += ksplit) {
       const int pw = patch % p.tiles_w;
       const int ph = (patch / p.tiles_w) % p.tiles_h;
@@ -258,7 +271,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
           mbar_expect_tx(bar_bfull + 8 * s, b_tx);
           if (!(p.dbg & 2)) {
             for (int j = 0; j < p.nb; j++)
-              tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + 64 * j,
+              tma_load_4d(sB + (uint32_t)(s * p.nb + j) * kBoxBytes, &tmX, bar_bfull + 8 * s, ci0 + p.xw * j,
                           w0 * p.stride + kw - p.pad, h0 * p.stride + kh - p.pad, img);
           }
         }
@@ -288,11 +301,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         for (int i = 0; i < g; i++) mbar_wait(bar_bfull + 8 * (s + i), bphase);
         tc_fence_after();
         if (elect_one()) {
-          const uint64_t bdesc = umma_desc_mn_sw128(sB + (uint32_t)(s * p.nb) * kBoxBytes, kBoxBytes);
+          const uint32_t b0 = sB + (uint32_t)(s * p.nb) * kBoxBytes;
+          const uint64_t bdesc = p.xw == 64 ? umma_desc_mn_sw128(b0, kBoxBytes) : umma_desc_mn_sw64(b0, kBoxBytes);
+          const uint32_t bstep = xrow;                         // one K step = 16 pixel rows = 16 * xrow bytes = xrow units
           const uint32_t idesc_g = umma_idesc_bf16_mn(g * CIT);
           const uint32_t d = tmem_base + (uint32_t)(ti * CIT);
-          for (int kk = 0; kk < ksteps; kk++)                  // one K step = 16 pixel rows = 2048 bytes = 128 units
-            umma_bf16(d, adesc + (uint64_t)(kk * 128), bdesc + (uint64_t)(kk * 128), idesc_g, (pit | (uint32_t)kk) ? 1u : 0u);
+          for (int kk = 0; kk < ksteps; kk++)                  // dY: one K step = 16 pixel rows = 2048 bytes = 128 units
+            umma_bf16(d, adesc + (uint64_t)(kk * 128), bdesc + (uint64_t)((uint32_t)kk * bstep), idesc_g,
+                      (pit | (uint32_t)kk) ? 1u : 0u);
           for (int i = 0; i < g; i++) umma_commit(bar_bempty + 8 * (s + i));
           if (ti + g == ntap) {
             umma_commit(bar_aempty + 8 * ab);
@@ -608,14 +624,14 @@ int sm_count() {
 }
 
 int encode_nhwc(EncodeTiledFn enc, CUtensorMap* tm, const void* ptr, int N, int H, int W, int C, long long cpitch,
-                int TH, int TW, int estride) {
+                int TH, int TW, int estride, int boxc = 64) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)cpitch * 2, (cuuint64_t)cpitch * 2 * W, (cuuint64_t)cpitch * 2 * W * H};
-  cuuint32_t box[4] = {64, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), 1};
+  cuuint32_t box[4] = {(cuuint32_t)boxc, (cuuint32_t)(TW * estride), (cuuint32_t)(TH * estride), 1};
   cuuint32_t estr[4] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, boxc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? 0 : 1;
 }
 
@@ -651,7 +667,11 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   if (p.TW * stride > 256) { p.TW = 256 / stride; p.TH = p.slot_rows / p.TW; if (p.TH > p.Ho) p.TH = p.Ho; }
   p.tiles_h = (p.Ho + p.TH - 1) / p.TH;
   p.tiles_w = (p.Wo + p.TW - 1) / p.TW;
-  const int CIT = 64 * p.nb;
+  const bool trans = ryolo_knob(RYOLO_KNOB_WG_TRANS) && p.nb <= 2;
+  // knob wg_x32: X boxes of Cin == 32 layers are 32 channels wide (SWIZZLE_64B rows): no overhanging TMA boxes, half the
+  // operand bytes, and up to eight taps per N = 256 MMA
+  p.xw = (Cin == 32 && !trans && ryolo_knob(RYOLO_KNOB_WG_X32)) ? 32 : 64;
+  const int CIT = p.xw * p.nb;
   p.n_ci_tiles = (Cin + CIT - 1) / CIT;
   p.n_co_tiles = (Cout + 127) / 128;
   p.tg = 512 / CIT;
@@ -705,14 +725,13 @@ int ryolo_conv2d_wgrad(const void* x, long long x_cpitch, int N, int H, int W, i
   const size_t kBoxBytes = (size_t)p.slot_rows * 128;
   int boxes = ryolo_knob(RYOLO_KNOB_WG_BOXES);
   p.smem_boxes = boxes < 10 ? 10 : (boxes > kSmemBoxes ? kSmemBoxes : boxes);
-  const bool trans = ryolo_knob(RYOLO_KNOB_WG_TRANS) && p.nb <= 2;
   if (trans) p.smem_boxes = kSmemBoxes;
   const size_t smem = 1024 + (size_t)p.smem_boxes * kBoxBytes, smem_max = 1024 + (size_t)kSmemBoxes * kBoxBytes;
   p.dw = dwk;
   p.dbg = ryolo_knob(RYOLO_KNOB_WG_DBG);
   CUtensorMap tmG, tmX;
   if (encode_nhwc(enc, &tmG, dy, N, p.Ho, p.Wo, Cdy, dy_cpitch, p.TH, p.TW, 1) ||
-      encode_nhwc(enc, &tmX, x, N, H, W, Cin, x_cpitch, p.TH, p.TW, stride)) {
+      encode_nhwc(enc, &tmX, x, N, H, W, Cin, x_cpitch, p.TH, p.TW, stride, p.xw)) {
     ryolo_set_error("cuTensorMapEncodeTiled failed in wgrad");
     return RYOLO_ERR_CUDA;
   }

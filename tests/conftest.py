@@ -36,7 +36,7 @@ def issue(request):
     one K block per stage without pairing, and weight matrices of up to 128 KB resident in shared memory."""
     from ryolo_b200 import _lib as L
     names = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc",
-             "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres"]
+             "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres", "wg_x32"]
     old = [L.lib().ryolo_knob(names.index(k)) for k in ("kgrp", "pair", "wres")]
     L.tune(**{"pair_any": dict(pair=1024 + 32, kgrp=0, wres=0), "kgrp_wide": dict(pair=0, kgrp=3, wres=0),
               "plain": dict(pair=0, kgrp=0, wres=0), "wres": dict(pair=0, kgrp=1, wres=1024 + 128)}[request.param])

@@ -24,7 +24,7 @@ step = R.TrainStep(m, crit)
 img = torch.rand(bs, 3, S, S, device="cuda")
 tg = make_targets(0, bs, 2).cuda()
 flat0 = step.flat.clone()
-KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres"]
+KNOBS = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64", "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres", "wg_x32"]
 BASE = {k: L.lib().ryolo_knob(i) for i, k in enumerate(KNOBS)}          # the library's defaults
 VARIANTS = [
     ("base", {}),
@@ -57,6 +57,8 @@ VARIANTS = [
     ("halo", dict(halo=1)),
     ("k32_n128", dict(sw64=2)),
     ("k32_all", dict(sw64=3)),
+    ("wg_x32", dict(wg_x32=1)),
+    ("wg_x64", dict(wg_x32=0)),
     ("wres0", dict(wres=0)),
     ("wres48", dict(wres=48)),
     ("wres96", dict(wres=96)),
