@@ -22,6 +22,8 @@ FWD = [  # H, W, Cin, Cout, k, stride          (yolov4 @800^2, SURVEY.md Appendi
     (200, 200, 64, 64, 3, 1),
     (200, 200, 128, 64, 1, 1),
     (100, 100, 128, 128, 3, 1),
+    (50, 50, 256, 512, 3, 1),     # N = 256 tiles, 36 K blocks: runs as cluster pairs with weight-tile multicast
+    (25, 25, 512, 1024, 3, 1),    # 160 m-tiles x 4 n-tiles, 72 K blocks (pairs; 5 tiles per image)
 ]
 
 
@@ -58,7 +60,7 @@ def test_forward_at_bench_shape(shape):
 
 
 @pytest.mark.parametrize("shape", [(400, 400, 32, 32, 3, 1), (400, 400, 64, 32, 1, 1), (200, 200, 64, 64, 3, 1),
-                                   (100, 100, 128, 128, 3, 1)], ids=lambda s: "x".join(map(str, s)))
+                                   (100, 100, 128, 128, 3, 1), (50, 50, 256, 512, 3, 1)], ids=lambda s: "x".join(map(str, s)))
 def test_dgrad_stride1_at_bench_shape(shape):
     from ryolo_b200 import ops
     H, W, Cin, Cout, k, s = shape
