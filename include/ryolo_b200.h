@@ -236,6 +236,10 @@ int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, l
 /* nn.MaxPool2d backward: dx (+)= route(dy) (first maximum of each window); scratch = fp32[N*H*W*C]           */
 int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp, int N, int H, int W, int C, int k,
                       int stride, int pad, void* dx, long long dxp, int accumulate, float* scratch, void* stream);
+/* SPP backward (model/utils.py:231-241): the three stride-1 "same" pools (odd k0/k1/k2) of ONE map with H*W <= 1024 in
+   one launch: dx (+)= route(dy0,k0) + route(dy1,k1) + route(dy2,k2); the dy views share one channel pitch           */
+int ryolo_spp_bwd(const void* x, long long xp, const void* dy0, const void* dy1, const void* dy2, long long dyp, int N, int H,
+                  int W, int C, int k0, int k1, int k2, void* dx, long long dxp, int accumulate, void* stream);
 /* nearest x2 upsample backward: dx[N,H,W,C] (+)= 2x2 block sums of dy[N,2H,2W,C]                             */
 int ryolo_upsample2x_bwd(const void* dy, long long dyp, int N, int H, int W, int C, void* dx, long long dxp,
                          int accumulate, void* stream);

@@ -828,12 +828,19 @@ maxpool_tiled_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, cons
 // the window maximum, and inside that row the first column attaining it: both "first" rules are a strict > while
 // scanning forwards.  A thread owns 4 channels of a pixel (128-bit shared loads, four independent compare chains):
 // 2(2p+1) vector loads per output instead of ~4(2p+1) scalar ones with two data-dependent while loops.
+// Up to three pools of the SAME map (SPP: 5 / 9 / 13) in one launch: the map is read once, every pool routes its
+// gradient into the same fp32 tile, and dx is written (or read-added) once instead of three times.
+struct SppGrads {
+  const __nv_bfloat16* dy[3];
+  int k[3];
+  int n;
+};
+
 __global__ void __launch_bounds__(256)
-maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, const __nv_bfloat16* __restrict__ dy,
-                              long long dyp, int H, int W, int C, int k, __nv_bfloat16* __restrict__ dx, long long dxp,
-                              int accumulate) {
+maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp, SppGrads dys, long long dyp, int H, int W,
+                              int C, __nv_bfloat16* __restrict__ dx, long long dxp, int accumulate) {
   extern __shared__ float sm_pb[];             // [H*W][8] map | [H*W][8] row maxima | [H*W][8] gradient | [H*W][8] u8 columns
-  const int HW = H * W, p = k >> 1;
+  const int HW = H * W;
   float* sx = sm_pb;
   float* sr = sm_pb + 8 * HW;
   float* sg = sm_pb + 16 * HW;
@@ -849,6 +856,8 @@ maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp,
     *reinterpret_cast<float4*>(sg + i * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(sg + i * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
   }
+  for (int pi = 0; pi < dys.n; pi++) {
+  const int p = dys.k[pi] >> 1;
   __syncthreads();
   // pass 1: per (pixel, 4 channels) the maximum of the row window and the first column that attains it
   for (int i = threadIdx.x; i < HW * 2; i += blockDim.x) {
@@ -870,7 +879,7 @@ maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp,
   }
   __syncthreads();
   // pass 2: scan the rows of the window; the first row with the largest row maximum holds the winner
-  const __nv_bfloat16* gb = dy + (long long)n * HW * dyp + c;
+  const __nv_bfloat16* gb = dys.dy[pi] + (long long)n * HW * dyp + c;
   for (int i = threadIdx.x; i < HW * 2; i += blockDim.x) {
     const int pix = i >> 1, q = (i & 1) * 4;
     const int h = pix / W, w = pix - h * W;
@@ -893,6 +902,7 @@ maxpool_same_small_bwd_kernel(const __nv_bfloat16* __restrict__ x, long long xp,
     atomicAdd(&sg[(rw * W + sa[(rw * W + w) * 8 + q + 3]) * 8 + q + 3], g3);
   }
   __syncthreads();
+  }
   __nv_bfloat16* db = dx + (long long)n * HW * dxp + c;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
     float a[8];
@@ -1195,6 +1205,31 @@ int ryolo_add_into(void* dst, long long dpitch, const void* src, long long sp, l
   return RYOLO_OK;
 }
 
+// SPP backward (model/utils.py:231-241): the three stride-1 "same" pools (odd k0 / k1 / k2) of ONE small map in one launch.
+//   dx (+)= route(dy0, k0) + route(dy1, k1) + route(dy2, k2);  the dy views share one channel pitch (slices of the concat buffer)
+// Returns RYOLO_ERR_INVALID when the map does not fit the shared-memory kernel (callers then use ryolo_maxpool_bwd per pool).
+int ryolo_spp_bwd(const void* x, long long xp, const void* dy0, const void* dy1, const void* dy2, long long dyp, int N, int H,
+                  int W, int C, int k0, int k1, int k2, void* dx, long long dxp, int accumulate, void* stream) {
+  RY_CHECK_ARG(C % 8 == 0 && (k0 & 1) && (k1 & 1) && (k2 & 1) && k0 >= 1 && k1 >= 1 && k2 >= 1, "spp_bwd: bad arguments");
+  RY_CHECK_ARG(H * W <= 1024 && W <= 256 && (long long)N * (C / 8) < (1ll << 31), "spp_bwd: map too large for the fused kernel");
+  if ((long long)N * H * W == 0) return RYOLO_OK;
+  const size_t smem = (size_t)26 * H * W * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(maxpool_same_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         104 * 1024);
+    if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
+    configured = true;
+  }
+  SppGrads g{};
+  g.dy[0] = (const __nv_bfloat16*)dy0; g.dy[1] = (const __nv_bfloat16*)dy1; g.dy[2] = (const __nv_bfloat16*)dy2;
+  g.k[0] = k0; g.k[1] = k1; g.k[2] = k2; g.n = 3;
+  maxpool_same_small_bwd_kernel<<<(unsigned)(N * (C / 8)), 256, smem, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)x, xp, g, dyp, H, W, C, (__nv_bfloat16*)dx, dxp, accumulate);
+  RY_CHECK_LAUNCH();
+  return RYOLO_OK;
+}
+
 // scratch: fp32 [N*H*W*C] (16-byte aligned); it is zeroed, filled with the routed gradients, then dx (+)= scratch.
 int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp, int N, int H, int W, int C, int k,
                       int stride, int pad, void* dx, long long dxp, int accumulate, float* scratch, void* stream) {
@@ -1213,8 +1248,10 @@ int ryolo_maxpool_bwd(const void* x, long long xp, const void* dy, long long dyp
       if (e != cudaSuccess) { ryolo_set_error(cudaGetErrorString(e)); return RYOLO_ERR_CUDA; }
       configured = true;
     }
+    SppGrads g{};
+    g.dy[0] = (const __nv_bfloat16*)dy; g.k[0] = k; g.n = 1;
     maxpool_same_small_bwd_kernel<<<(unsigned)(N * (C / 8)), 256, smem, st>>>(
-        (const __nv_bfloat16*)x, xp, (const __nv_bfloat16*)dy, dyp, H, W, C, k, (__nv_bfloat16*)dx, dxp, accumulate);
+        (const __nv_bfloat16*)x, xp, g, dyp, H, W, C, (__nv_bfloat16*)dx, dxp, accumulate);
     RY_CHECK_LAUNCH();
     return RYOLO_OK;
   }

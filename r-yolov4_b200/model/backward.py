@@ -292,6 +292,18 @@ def _run_backward(model, ctx, dlevels, param_grads, seed=(), on_entry=None):
             gs, acc = G.writable(src)
             ops.maxpool_bwd(src, G.view(dst), k, s, p, gs, acc)
             G.mark(src)
+        elif kind == "spp3":
+            _, src, dsts, ks = e
+            if not all(G.is_init(d) for d in dsts):       # a pool output nobody consumed: route the others one by one
+                for d, k in zip(dsts, ks):
+                    if G.is_init(d):
+                        gs, acc = G.writable(src)
+                        ops.maxpool_bwd(src, G.view(d), k, 1, k // 2, gs, acc)
+                        G.mark(src)
+                return
+            gs, acc = G.writable(src)
+            ops.spp_bwd(src, [G.view(d) for d in dsts], ks, gs, acc)
+            G.mark(src)
         elif kind == "resize":
             _, src, dst, factor = e
             if not G.is_init(dst):

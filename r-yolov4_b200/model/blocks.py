@@ -204,7 +204,11 @@ def _spp_pools(ctx, src, dsts):
         return
     for dst, k in dsts:
         ops.maxpool(src, k, 1, k // 2, out=dst)
-        ctx.tape.append(("maxpool", src, dst, k, 1, k // 2))
+    if src.H * src.W <= 1024 and len(dsts) == 3:      # one fused backward launch for the three pools (ryolo_spp_bwd)
+        ctx.tape.append(("spp3", src, [d for d, _ in dsts], [k for _, k in dsts]))
+    else:
+        for dst, k in dsts:
+            ctx.tape.append(("maxpool", src, dst, k, 1, k // 2))
 
 
 class SPP(nn.Module):

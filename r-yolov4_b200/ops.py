@@ -285,6 +285,15 @@ def maxpool_bwd(x, dy, k, stride, pad, dx, accumulate):
     L.count(2)
 
 
+def spp_bwd(x, dys, ks, dx, accumulate):
+    """dx (+)= gradients of the three stride-1 'same' pools `ks` of x (SPP, model/utils.py:231-241) in one launch."""
+    assert len(dys) == 3 and dys[0].pitch == dys[1].pitch == dys[2].pitch
+    L.check(L.lib().ryolo_spp_bwd(_vp(x.ptr), x.pitch, _vp(dys[0].ptr), _vp(dys[1].ptr), _vp(dys[2].ptr), dys[0].pitch,
+                                  x.N, x.H, x.W, x.C, ks[0], ks[1], ks[2], _vp(dx.ptr), dx.pitch, 1 if accumulate else 0,
+                                  L.stream()))
+    L.count(1)
+
+
 def upsample2x_bwd(dy, dx, accumulate):
     L.check(L.lib().ryolo_upsample2x_bwd(_vp(dy.ptr), dy.pitch, dx.N, dx.H, dx.W, dx.C, _vp(dx.ptr), dx.pitch,
                                          1 if accumulate else 0, L.stream()))

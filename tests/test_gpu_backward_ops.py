@@ -103,6 +103,33 @@ def test_wgrad_stem():
     assert (ops.wgrad_to_oihw(dwk6, 64, 3, 6, stem=True).cpu() - w6.grad).abs().max() < 1e-2 * w6.grad.abs().max()
 
 
+def test_spp_backward_three_pools_one_launch():
+    """ryolo_spp_bwd (5 / 9 / 13 stride-1 pools of one map, gradients in channel slices of one concat buffer, ties in the
+    map) against torch autograd, overwriting and accumulating into a slice of a wider gradient buffer."""
+    from ryolo_b200 import ops
+    gen = torch.Generator().manual_seed(11)
+    N, H, W, C = 3, 25, 25, 64
+    x = (torch.randn(N, H, W, C, generator=gen) * 2).round().div(2).bfloat16()       # quantised: many ties per window
+    xn = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    cat = torch.randn(N, H, W, 4 * C, generator=gen).bfloat16()                      # d cat: slices 13 | 9 | 5 | x
+    ks = [5, 9, 13]
+    sl = {5: 2 * C, 9: C, 13: 0}
+    tot = sum(F.max_pool2d(xn, k, 1, k // 2) * cat[..., sl[k]:sl[k] + C].float().permute(0, 3, 1, 2) for k in ks)
+    tot.sum().backward()
+    ref = xn.grad.permute(0, 2, 3, 1)
+    g = ops.Act(cat.clone().cuda())
+    dys = [g.slice(sl[k], C) for k in ks]
+    dx = ops.Act(torch.full((N, H, W, C), 7.0).bfloat16().cuda())
+    ops.spp_bwd(ops.Act(x.cuda()), dys, ks, dx, False)
+    assert (dx.torch().float().cpu() - ref).abs().max() <= 1e-2 * ref.abs().max()
+    # accumulate into the x slice of the same gradient buffer (what the SPP block's backward does)
+    ops.spp_bwd(ops.Act(x.cuda()), dys, ks, g.slice(3 * C, C), True)
+    got = g.buf.float().cpu()
+    want = cat[..., 3 * C:].float() + ref
+    assert (got[..., 3 * C:] - want).abs().max() <= 1e-2 * want.abs().max()
+    assert torch.equal(got[..., :3 * C], cat[..., :3 * C].float())                  # the dy slices are untouched
+
+
 @pytest.mark.parametrize("act", ["linear", "leaky", "mish", "swish"])
 def test_bn_act_backward(act):
     from ryolo_b200 import ops
