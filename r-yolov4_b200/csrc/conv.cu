@@ -13,6 +13,10 @@
 //                  loop, one elected lane) into 2-8 rotating TMEM accumulators | warps 2-5 / 6-9: two epilogue groups
 //                  taking alternate tiles (tcgen05.ld -> scale/shift/activation/residual/BN statistics -> global)
 //                  overlapping the following tiles' main loops; mbarrier smem ring; programmatic dependent launch
+//   ring variants  (compile-time, chosen per layer in launch()): 1-3 K blocks per stage (narrow tiles) | cluster pairs:
+//                  two CTAs on neighbouring m-tiles share every weight tile through TMA multicast (deep N = 256
+//                  layers) | resident weights: the whole weight matrix loaded once per CTA, activation-only ring
+//                  (one n-tile, <= 96 KB of weights, many tiles per CTA)
 //   epilogue       mode 0: bf16 NHWC into a channel slice of a (concat) buffer, staged in smem and stored (or, for
 //                  dgrad's accumulation, reduce-added) by TMA; per-channel scale/shift = folded BatchNorm (eval) or
 //                  identity (train: raw conv output + fused BatchNorm statistics and finalize);
@@ -374,12 +378,13 @@ conv_fwd_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           for (int g = 0; g < G; g++) {
             if (!(dbg & 8))
               tma_load_4d(da, &tmA, bar_full + 8 * s, c * p.kbk, ws + p.tap_dw[tp], hs + p.tap_dh[tp], img);
-            if (WRES) {
-            } else if (PAIR)
-              tma_load_2d_mc(db + b_half, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk,
-                             n0 + rank * (BN >> 1), (uint16_t)3);
-            else if (!(dbg & 32))               // dbg 32 (timing experiment, wrong results): no weight loads
-              tma_load_2d(db, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk, n0);
+            if (!WRES) {                        // (resident weights were loaded once, above)
+              if (PAIR)
+                tma_load_2d_mc(db + b_half, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk,
+                               n0 + rank * (BN >> 1), (uint16_t)3);
+              else if (!(dbg & 32))             // dbg 32 (timing experiment, wrong results): no weight loads
+                tma_load_2d(db, &tmB, bar_full + 8 * s, (int)p.tap_k[tp] * p.Ktap + c * p.kbk, n0);
+            }
             da += kABytes; db += kBBytes;
             if (++c == p.kb_per_tap) { c = 0; if (++tp == p.ntaps) tp = 0; }
           }
