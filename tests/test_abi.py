@@ -60,8 +60,11 @@ def test_tuning_knobs_host_api():
     from ryolo_b200 import _lib as L
     lib = L.lib()
     names = ["halo", "dbg", "wg_split", "wg_dbg", "epi_tma", "epi_maxbn", "wg_tapgrp", "bn_bwd", "wg_trans", "sw64",
-             "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse"]
+             "nacc", "pdl", "ssa", "wg_boxes", "ew_regs", "nms_band", "bn_fuse", "kgrp", "pair", "wres", "wg_x32"]
     before = [lib.ryolo_knob(i) for i in range(len(names))]
+    if not any(os.environ.get("RYOLO_" + n.upper()) for n in ("kgrp", "pair", "wres", "wg_x32")):
+        # operand-ring variants of the conv / wgrad kernels as shipped (csrc/lib.cu)
+        assert [before[names.index(n)] for n in ("kgrp", "pair", "wres", "wg_x32")] == [1, 256, 96, 1]
     assert before[names.index("dbg")] == 0 and before[names.index("wg_dbg")] == 0, "timing experiments must be off"
     assert before[names.index("epi_tma")] == 2 and before[names.index("wg_trans")] == 0 and before[names.index("bn_bwd")] == 3
     try:
