@@ -182,13 +182,19 @@ csl_pos_kernel(LevelArgs L, int lvl, const int* __restrict__ counts, const float
     }
     a_th += (double)lsum;
   }
+  // one set of atomics per BLOCK: ~9500 warps adding three doubles each to the same three addresses serialise in L2 and
+  // were most of this kernel's time (lane 0 holds a_reg, every lane a share of a_cls / a_th)
+  __shared__ double spart[3][8];
   a_reg = ry_warp_sum_d(a_reg);
   a_cls = ry_warp_sum_d(a_cls);
   a_th = ry_warp_sum_d(a_th);
-  if (lane == 0 && n > 0) {
-    atomicAdd(&sums[lvl * 4 + 0], a_reg);
-    atomicAdd(&sums[lvl * 4 + 1], a_cls);
-    atomicAdd(&sums[lvl * 4 + 2], a_th);
+  const int wib = threadIdx.x >> 5;
+  if (lane == 0) { spart[0][wib] = a_reg; spart[1][wib] = a_cls; spart[2][wib] = a_th; }
+  __syncthreads();
+  if (threadIdx.x < 3 && n > 0 && (int)(blockIdx.x * (blockDim.x >> 5)) < n) {     // blocks without a positive add nothing
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += spart[threadIdx.x][w];
+    atomicAdd(&sums[lvl * 4 + threadIdx.x], t);
   }
 }
 
@@ -239,11 +245,16 @@ kfiou_pos_kernel(LevelArgs L, int lvl, const int* __restrict__ counts, const flo
       a_cls += (double)lsum;
     }
   }
+  __shared__ double spart[2][4];                 // one pair of atomics per block (see csl_pos_kernel)
   a_reg = ry_warp_sum_d(a_reg);
   a_cls = ry_warp_sum_d(a_cls);
-  if (lane == 0 && n > 0) {
-    atomicAdd(&sums[lvl * 4 + 0], a_reg);
-    atomicAdd(&sums[lvl * 4 + 1], a_cls);
+  const int wib = threadIdx.x >> 5;
+  if (lane == 0) { spart[0][wib] = a_reg; spart[1][wib] = a_cls; }
+  __syncthreads();
+  if (threadIdx.x < 2 && n > 0 && (int)(blockIdx.x * blockDim.x) < n) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += spart[threadIdx.x][w];
+    atomicAdd(&sums[lvl * 4 + threadIdx.x], t);
   }
 }
 
